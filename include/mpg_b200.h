@@ -1,0 +1,183 @@
+/*
+ * mpg_b200 -- C ABI of the B200-native MPG model-based learner hot path.
+ *
+ * The reference (idthanm/mpg) has NO FFI: its two plugin boundaries are duck-typed Python classes
+ * (learners/*.py selected at train_scripts/train_script.py:40-46; env models selected at
+ * envs_and_models/__init__.py:13-15).  This header is the boundary a maintainer would bind with
+ * ctypes from those classes; every entry point names the reference code it
+ * replaces.  Plain C: opaque handle, POD structs, raw device pointers, explicit sizes, a
+ * caller-supplied cudaStream_t (passed as void*).  No torch types, no C++ exceptions.
+ *
+ * Conventions
+ *   - all tensors fp32, row-major, DEVICE pointers unless the name ends in _host;
+ *   - network weights use the Keras layout of the reference: kernels (in, out), list order
+ *     [W1, b1, W2, b2, W3, b3] (model.py:20-43); gradients are written in the same order into one
+ *     flat buffer (W1|b1|W2|b2|W3|b3);
+ *   - every function returns 0 on success, <0 on error; mpg_last_error() gives the message;
+ *   - nothing is freed or retained from caller memory; workspace belongs to the handle;
+ *   - all work is enqueued on `stream`; no hidden synchronisation.
+ */
+#ifndef MPG_B200_H
+#define MPG_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mpg_ctx mpg_ctx;
+
+/* env_id registry: envs_and_models/__init__.py:13-15 */
+enum {
+  MPG_ENV_PATH_TRACKING = 0,            /* 'PathTracking-v0'            path_tracking_env.py:245-297 */
+  MPG_ENV_INVERTED_PENDULUM = 1,        /* 'InvertedPendulumConti-v0'   inverted_pendulum_model.py:77-97 */
+  MPG_ENV_INVERTED_DOUBLE_PENDULUM = 2  /* 'InvertedDoublePendulum-v2'  inverted_double_pendulum_model.py:103-144 */
+};
+
+/* network slots: PolicyWithQs.models + target_models (policy.py:72-89) */
+enum {
+  MPG_NET_Q1 = 0, MPG_NET_Q2 = 1, MPG_NET_POLICY = 2,
+  MPG_NET_Q1_TARGET = 3, MPG_NET_Q2_TARGET = 4, MPG_NET_POLICY_TARGET = 5,
+  MPG_NUM_NETS = 6
+};
+
+enum { MPG_OK = 0, MPG_ERR_ARG = -1, MPG_ERR_CUDA = -2, MPG_ERR_UNSUPPORTED = -3, MPG_ERR_STATE = -4 };
+
+#define MPG_MAX_OBS 16
+#define MPG_MAX_LIST 8
+
+/* What the learner constructors read from `args` (mpg_learner.py:30-58, nadp.py:29-47) that the
+ * device path needs. */
+typedef struct {
+  int32_t env;               /* MPG_ENV_* */
+  int32_t num_future_data;   /* PathTracking only (path_tracking_env.py:265-271) */
+  int32_t obs_dim;           /* 6+nfd | 4 | 11 */
+  int32_t act_dim;           /* 2 | 1 | 1 */
+  int32_t hidden;            /* *_num_hidden_units; this build supports 256 with 2 hidden layers */
+  int32_t policy_out_tanh;   /* policy_out_activation == 'tanh' */
+  float action_range;        /* policy.py:197; <= 0 means None */
+  float obs_scale[MPG_MAX_OBS]; /* preprocessor.py:134-145, 'scale' mode */
+  float rew_scale;           /* preprocessor.py:147-159 */
+  float rew_shift;
+  float gamma;
+  int32_t max_rows;          /* capacity: M * rows per call on this device */
+  int32_t max_horizon;       /* capacity: max rollout length n */
+} mpg_config;
+
+/* One model rollout (mpg_learner.py:226-286, nadp.py:87-171). */
+typedef struct {
+  int32_t rows;              /* B on this device (before M-tiling) */
+  int32_t M;                 /* args.M: tf.tile factor */
+  int32_t horizon;           /* n = max(rollout list) */
+  int32_t n_list;            /* len(num_rollout_list_*) <= MPG_MAX_LIST */
+  int32_t list[MPG_MAX_LIST];   /* rollout indices k (each <= horizon) */
+  float list_w[MPG_MAX_LIST];   /* loss weights w_k (rule_based_weights; 1 for NADP) */
+  int32_t full_bptt;         /* 1: dW at every step (NADP, deriv_interval_policy); 0: a_0 only (default MPG) */
+  int32_t q_net;             /* bootstrap net: MPG_NET_Q1 / MPG_NET_Q1_TARGET, or -1 for none (AMPC) */
+  int32_t policy_net;        /* MPG_NET_POLICY (a_t = pi(p_t)) */
+  int64_t global_rows;       /* B summed over all ranks (loss scale 1/(M*global_rows)); 0 -> rows */
+  int64_t row_offset;        /* first global row of this shard (keys the noise stream) */
+  uint64_t noise_seed;       /* Philox key when `noise` is NULL */
+  int32_t use_philox;        /* 1: in-kernel Philox4x32-10 N(0,1); 0: read `noise` (NULL noise + 0 => no noise) */
+  int32_t reserved;
+} mpg_rollout_params;
+
+/* ---- lifetime ---------------------------------------------------------------------------- */
+int mpg_create(const mpg_config* cfg, mpg_ctx** out);
+void mpg_destroy(mpg_ctx* ctx);
+const char* mpg_last_error(const mpg_ctx* ctx);   /* ctx may be NULL: last create() error */
+size_t mpg_workspace_bytes(const mpg_ctx* ctx);
+int mpg_num_sms(const mpg_ctx* ctx);
+int mpg_param_count(const mpg_ctx* ctx, int net); /* floats in one net's flat gradient */
+
+/* ---- weights: PolicyWithQs.set_weights (policy.py:116-121) -------------------------------- */
+/* w[0..5] = W1,b1,W2,b2,W3,b3 device pointers in Keras layout; repacked into the kernel layouts. */
+int mpg_set_weights(mpg_ctx* ctx, int net, const float* const w[6], void* stream);
+/* copy back in Keras layout (PolicyWithQs.get_weights, policy.py:112-114) */
+int mpg_get_weights(mpg_ctx* ctx, int net, float* const w[6], void* stream);
+
+/* ---- policy gradient through the model rollout ------------------------------------------- */
+/* MPGLearner.policy_forward_and_backward (mpg_learner.py:356-365) /
+ * NADPLearner.policy_forward_and_backward (nadp.py:186-194): forward rollout with per-step state
+ * checkpoints, fused BPTT backward with recompute.
+ *   obs        (rows, obs_dim)
+ *   noise      (horizon, M*rows) standard-normal eps, or NULL (see use_philox)
+ *   grad_out   (param_count(policy)) UNCLIPPED d loss / d theta, loss = sum_k w_k * (-mean R_k),
+ *              scaled by 1/(M*global_rows) so that per-rank results add up under all-reduce
+ *   returns_out (n_list, M*rows) per-row R_k = sum_{t<k} gamma^t rho r_t + gamma^k Q(p_k, a_k)
+ */
+int mpg_policy_grad(mpg_ctx* ctx, const mpg_rollout_params* p, const float* obs, const float* noise,
+                    float* grad_out, float* returns_out, void* stream);
+
+/* Forward-only rollout: NADPLearner.model_rollout_for_q_estimation (nadp.py:87-126) when
+ * start_actions != NULL, and the trajectory view used by the parity tests.
+ *   start_actions (rows, act_dim) or NULL (a_0 = pi(p_0))
+ *   returns_out (n_list, M*rows)
+ *   traj_obs (horizon, M*rows, obs_dim) raw obs_{t+1};  traj_rew (horizon, M*rows) processed
+ *   rewards;  traj_act (horizon+1, M*rows, act_dim) actions; each may be NULL */
+int mpg_rollout_forward(mpg_ctx* ctx, const mpg_rollout_params* p, const float* obs, const float* start_actions,
+                        const float* noise, float* returns_out, float* traj_obs, float* traj_rew, float* traj_act,
+                        void* stream);
+
+/* mean over the M tiles, then sum / sum of squares over rows (mpg_learner.py:272-274):
+ * out[0..n_list) = sum_i mean_m R_k ; out[n_list..2 n_list) = sum_i (mean_m R_k)^2 */
+int mpg_returns_stats(mpg_ctx* ctx, const float* returns, int n_list, int rows, int M, float* out, void* stream);
+/* tile mean only: out (n_list, rows) -- the stop_gradient targets of nadp.py:120-126 */
+int mpg_returns_tile_mean(mpg_ctx* ctx, const float* returns, int n_list, int rows, int M, float* out, void* stream);
+
+/* ---- Q side ------------------------------------------------------------------------------- */
+/* q_forward_and_backward (mpg_learner.py:326-354, nadp.py:173-184): loss = 0.5 mean (Q(sigma o, a) - target)^2.
+ *   grad_out (param_count(net)) scaled by 1/global_rows; loss_sum_out[0] = sum_i 0.5 (Q - target)^2 */
+int mpg_q_grad(mpg_ctx* ctx, int net, int rows, int64_t global_rows, const float* obs, const float* act,
+               const float* target, float* grad_out, float* loss_sum_out, void* stream);
+/* compute_action / compute_target_action (policy.py:193-212) on RAW obs (scale applied inside) */
+int mpg_policy_forward(mpg_ctx* ctx, int net, int rows, const float* obs, float* act_out, void* stream);
+/* compute_Q1/Q2/Q1_target/Q2_target (policy.py:219-241) on RAW obs */
+int mpg_q_forward(mpg_ctx* ctx, int net, int rows, const float* obs, const float* act, float* q_out, void* stream);
+/* compute_clipped_double_q_target (mpg_learner.py:126-134) when double_q, else the 1-step target of
+ * compute_n_step_target (mpg_learner.py:147-152): rho (r + shift) + gamma min(Q1t, Q2t)(o', pi_t(o')) */
+int mpg_q_target(mpg_ctx* ctx, int double_q, int rows, const float* rew, const float* obs_tp1, float* target_out,
+                 void* stream);
+/* compute_td_error (mpg_learner.py:136-144, nadp.py:67-76) */
+int mpg_td_error(mpg_ctx* ctx, int rows, const float* obs, const float* act, const float* rew, const float* obs_tp1,
+                 float* td_out, void* stream);
+
+/* ---- single model step: <Env>Model.rollout_out ------------------------------------------- */
+/* state (rows, state_dim) in/out; obs_out (rows, obs_dim); rew_out (rows) RAW reward.
+ * eps (rows) standard normal or NULL. */
+int mpg_model_reset(mpg_ctx* ctx, int rows, const float* obs, float* state_out, void* stream);
+int mpg_model_step(mpg_ctx* ctx, int rows, const float* state_in, const float* action, const float* eps,
+                   float* state_out, float* obs_out, float* rew_out, void* stream);
+/* adjoint of mpg_model_step: given d/d obs_out and d/d rew_out, accumulate d/d state_in, d/d action */
+int mpg_model_step_bwd(mpg_ctx* ctx, int rows, const float* state_in, const float* action, const float* eps,
+                       const float* g_obs_out, const float* g_rew_out, const float* g_state_out, float* g_state_in,
+                       float* g_action, void* stream);
+/* VehicleDynamics.compute_rewards(states, scaled actions) / Dynamics.compute_rewards(states) */
+int mpg_compute_rewards(mpg_ctx* ctx, int rows, const float* state, const float* scaled_action, float* rew_out,
+                        void* stream);
+int mpg_state_dim(const mpg_ctx* ctx);
+
+/* ---- tf.clip_by_global_norm (mpg_learner.py:415-431, nadp.py:220-225) --------------------- */
+/* in place over one net's flat gradient; norm_out[0] = pre-clip global norm */
+int mpg_clip_global_norm(mpg_ctx* ctx, float* grad, int n, float clip, float* norm_out, void* stream);
+
+/* standard-normal noise of the in-kernel Philox stream, for tests: out (horizon, M*rows) */
+int mpg_philox_noise(mpg_ctx* ctx, const mpg_rollout_params* p, float* out, void* stream);
+
+/* Kernel family used by mpg_policy_grad / mpg_rollout_forward:
+ *   MPG_BACKEND_FFMA  fp32 CUDA-core contractions (every env / shape this build supports)
+ *   MPG_BACKEND_TC    tcgen05 tensor-core contractions with split-bf16 operands (fp32-accurate);
+ *                     returns MPG_ERR_UNSUPPORTED for configurations it does not cover */
+enum { MPG_BACKEND_FFMA = 0, MPG_BACKEND_TC = 1 };
+int mpg_set_backend(mpg_ctx* ctx, int backend);
+int mpg_get_backend(const mpg_ctx* ctx);
+
+/* counters for bench.py: kernels launched by this handle since creation */
+uint64_t mpg_launch_count(const mpg_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MPG_B200_H */

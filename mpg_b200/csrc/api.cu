@@ -1,0 +1,556 @@
+// C ABI of libmpg_b200.so (include/mpg_b200.h): handle, weight packing, launches.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+
+#include "rollout_kernels.cuh"
+#include "tc_rollout.cuh"
+
+using namespace mpg;
+
+namespace {
+
+struct NetStore {
+  float* flat = nullptr;   // Keras order W1|b1|W2|b2|W3|b3 (natural layouts)
+  float* W1p = nullptr;
+  float* W2p = nullptr;
+  float* W2Tp = nullptr;
+  int in_dim = 0, out_dim = 0;
+  bool set = false;
+};
+
+thread_local char g_create_err[512] = "";
+
+}  // namespace
+
+struct mpg_ctx {
+  mpg_config cfg;
+  int device = 0, sms = 0, S = 0;
+  NetStore nets[MPG_NUM_NETS];
+  float* ckpt = nullptr;
+  float* partial = nullptr;
+  float* loss_partial = nullptr;
+  size_t partial_stride = 0;
+  size_t ws_bytes = 0;
+  uint64_t launches = 0;
+  int backend = MPG_BACKEND_FFMA;
+  char err[512];
+  TcState tc;
+};
+
+namespace {
+
+int fail(mpg_ctx* ctx, int code, const char* fmt, const char* detail = "") {
+  char* dst = ctx ? ctx->err : g_create_err;
+  snprintf(dst, 512, fmt, detail);
+  return code;
+}
+
+#define CUDA_OK(ctx, expr)                                                              \
+  do {                                                                                  \
+    cudaError_t e__ = (expr);                                                           \
+    if (e__ != cudaSuccess) return fail(ctx, MPG_ERR_CUDA, #expr ": %s", cudaGetErrorString(e__)); \
+  } while (0)
+
+NetDev net_dev(const mpg_ctx* c, int net) {
+  const NetStore& n = c->nets[net];
+  GradLayout L(n.in_dim, n.out_dim);
+  NetDev d;
+  d.W1p = n.W1p; d.b1 = n.flat + L.ob1; d.W2p = n.W2p; d.b2 = n.flat + L.ob2; d.W2Tp = n.W2Tp;
+  d.W3 = n.flat + L.oW3; d.b3 = n.flat + L.ob3; d.W1 = n.flat + L.oW1;
+  d.in_dim = n.in_dim; d.out_dim = n.out_dim;
+  return d;
+}
+
+__global__ void pack_kernel(const float* __restrict__ flat, int in_dim, int out_dim, float* __restrict__ W1p,
+                            float* __restrict__ W2p, float* __restrict__ W2Tp) {
+  const GradLayout L(in_dim, out_dim);
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= H * H) return;
+  const int k = idx / H, pc = idx % H, l = pc >> 3, j = pc & 7, c = l + 32 * j;
+  W2p[idx] = flat[L.oW2 + k * H + c];
+  W2Tp[idx] = flat[L.oW2 + c * H + k];   // W2T[n=k][col c] = W2[c][k]
+  if (k < in_dim) W1p[idx] = flat[L.oW1 + k * H + c];
+}
+
+__global__ void reduce_partials_kernel(const float* __restrict__ partial, size_t stride, int nparts, int n,
+                                       float* __restrict__ out, const float* __restrict__ loss_partial,
+                                       float* __restrict__ loss_out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    float s = 0.f;
+    for (int c = 0; c < nparts; ++c) s += partial[(size_t)c * stride + i];
+    out[i] = s;
+  }
+  if (loss_out && blockIdx.x == 0 && threadIdx.x == 0) {
+    float s = 0.f;
+    for (int c = 0; c < nparts; ++c) s += loss_partial[c];
+    loss_out[0] = s;
+  }
+}
+
+__global__ void clip_kernel(float* __restrict__ g, int n, float clip, float* __restrict__ norm_out) {
+  __shared__ float red[1024];
+  float s = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s = fmaf(g[i], g[i], s);
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  const float norm = sqrtf(red[0]);
+  const float scale = clip * fminf(1.f / norm, 1.f / clip);   // tf.clip_by_global_norm
+  for (int i = threadIdx.x; i < n; i += blockDim.x) g[i] *= scale;
+  if (threadIdx.x == 0 && norm_out) norm_out[0] = norm;
+}
+
+// returns (n_list, M*rows) -> tile mean (n_list, rows) and/or sums over rows of mean, mean^2
+__global__ void returns_stats_kernel(const float* __restrict__ ret, int n_list, int rows, int M,
+                                     float* __restrict__ mean_out, float* __restrict__ stats_out) {
+  __shared__ float red[2][256];
+  const int k = blockIdx.x;
+  float s1 = 0.f, s2 = 0.f;
+  for (int i = threadIdx.x; i < rows; i += blockDim.x) {
+    float m = 0.f;
+    for (int t = 0; t < M; ++t) m += ret[(size_t)k * M * rows + (size_t)t * rows + i];
+    m /= (float)M;
+    if (mean_out) mean_out[(size_t)k * rows + i] = m;
+    s1 += m; s2 = fmaf(m, m, s2);
+  }
+  red[0][threadIdx.x] = s1; red[1][threadIdx.x] = s2;
+  __syncthreads();
+  for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+    if (threadIdx.x < o) { red[0][threadIdx.x] += red[0][threadIdx.x + o]; red[1][threadIdx.x] += red[1][threadIdx.x + o]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0 && stats_out) { stats_out[k] = red[0][0]; stats_out[n_list + k] = red[1][0]; }
+}
+
+__global__ void philox_noise_kernel(unsigned long long seed, long long global_rows, long long row_offset, int rows,
+                                    int M, int horizon, float* __restrict__ out) {
+  const int MB = rows * M;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)horizon * MB) return;
+  const int t = (int)(idx / MB), grow = (int)(idx % MB);
+  const unsigned long long nr = (unsigned long long)(grow / rows) * global_rows + row_offset + (grow % rows);
+  out[idx] = philox_normal(seed, nr, (uint32_t)t);
+}
+
+template <typename K>
+int set_smem(mpg_ctx* ctx, K kernel) {
+  CUDA_OK(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::FLOATS * 4));
+  return MPG_OK;
+}
+
+int check_net(mpg_ctx* ctx, int net) {
+  if (net < 0 || net >= MPG_NUM_NETS) return fail(ctx, MPG_ERR_ARG, "bad net id%s");
+  if (!ctx->nets[net].set) return fail(ctx, MPG_ERR_STATE, "weights of a required net were never set%s");
+  return MPG_OK;
+}
+
+int fill_rollout_args(mpg_ctx* ctx, const mpg_rollout_params* p, RolloutArgs& a) {
+  const mpg_config& c = ctx->cfg;
+  if (p->rows <= 0 || p->M <= 0 || p->horizon < 0 || p->n_list < 0 || p->n_list > MPG_MAX_LIST)
+    return fail(ctx, MPG_ERR_ARG, "bad rollout params%s");
+  if ((long long)p->rows * p->M > c.max_rows || p->horizon > c.max_horizon)
+    return fail(ctx, MPG_ERR_ARG, "rollout exceeds the capacity given to mpg_create (max_rows / max_horizon)%s");
+  for (int k = 0; k < p->n_list; ++k)
+    if (p->list[k] < 0 || p->list[k] > p->horizon) return fail(ctx, MPG_ERR_ARG, "rollout index outside [0, horizon]%s");
+  memset(&a, 0, sizeof(a));
+  a.obs_dim = c.obs_dim; a.act_dim = c.act_dim; a.nfd = c.num_future_data; a.policy_out_tanh = c.policy_out_tanh;
+  a.action_range = c.action_range;
+  for (int i = 0; i < MPG_MAX_OBS; ++i) a.obs_scale[i] = c.obs_scale[i];
+  a.rew_scale = c.rew_scale; a.rew_shift = c.rew_shift; a.gamma = c.gamma;
+  a.rows = p->rows; a.M = p->M; a.horizon = p->horizon; a.n_list = p->n_list;
+  for (int k = 0; k < p->n_list; ++k) { a.list[k] = p->list[k]; a.list_w[k] = p->list_w[k]; }
+  a.full_bptt = p->full_bptt;
+  a.has_q = p->q_net >= 0;
+  a.global_rows = p->global_rows > 0 ? p->global_rows : p->rows;
+  a.row_offset = p->row_offset;
+  a.seed = p->noise_seed;
+  int rc = check_net(ctx, p->policy_net);
+  if (rc) return rc;
+  a.pol = net_dev(ctx, p->policy_net);
+  if (a.has_q) {
+    rc = check_net(ctx, p->q_net);
+    if (rc) return rc;
+    a.q = net_dev(ctx, p->q_net);
+  }
+  a.ckpt = ctx->ckpt;
+  a.partial = ctx->partial;
+  return MPG_OK;
+}
+
+template <bool BWD>
+int launch_rollout(mpg_ctx* ctx, const RolloutArgs& a, int grid, cudaStream_t st) {
+  const size_t smem = Smem::FLOATS * 4;
+  switch (ctx->cfg.env) {
+    case MPG_ENV_PATH_TRACKING: rollout_kernel<MPG_ENV_PATH_TRACKING, BWD><<<grid, NT, smem, st>>>(a); break;
+    case MPG_ENV_INVERTED_PENDULUM: rollout_kernel<MPG_ENV_INVERTED_PENDULUM, BWD><<<grid, NT, smem, st>>>(a); break;
+    default: rollout_kernel<MPG_ENV_INVERTED_DOUBLE_PENDULUM, BWD><<<grid, NT, smem, st>>>(a); break;
+  }
+  ctx->launches++;
+  CUDA_OK(ctx, cudaGetLastError());
+  return MPG_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* mpg_last_error(const mpg_ctx* ctx) { return ctx ? ctx->err : g_create_err; }
+size_t mpg_workspace_bytes(const mpg_ctx* ctx) { return ctx->ws_bytes; }
+int mpg_num_sms(const mpg_ctx* ctx) { return ctx->sms; }
+int mpg_state_dim(const mpg_ctx* ctx) { return ctx->S; }
+uint64_t mpg_launch_count(const mpg_ctx* ctx) { return ctx->launches; }
+
+int mpg_get_backend(const mpg_ctx* ctx) { return ctx->backend; }
+int mpg_set_backend(mpg_ctx* ctx, int backend) {
+  if (!ctx || (backend != MPG_BACKEND_FFMA && backend != MPG_BACKEND_TC)) return fail(ctx, MPG_ERR_ARG, "bad backend%s");
+  if (backend == MPG_BACKEND_TC && !ctx->tc.ready)
+    return fail(ctx, MPG_ERR_UNSUPPORTED, "tensor-core backend does not cover this configuration%s");
+  ctx->backend = backend;
+  return MPG_OK;
+}
+
+int mpg_param_count(const mpg_ctx* ctx, int net) {
+  if (net < 0 || net >= MPG_NUM_NETS) return -1;
+  return GradLayout(ctx->nets[net].in_dim, ctx->nets[net].out_dim).total;
+}
+
+int mpg_create(const mpg_config* cfg, mpg_ctx** out) {
+  if (!cfg || !out) return fail(nullptr, MPG_ERR_ARG, "null argument%s");
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(nullptr, MPG_ERR_CUDA, "no CUDA device: mpg_b200 has no CPU fallback%s");
+  if (cfg->hidden != H) return fail(nullptr, MPG_ERR_UNSUPPORTED, "only hidden = 256 (2 hidden layers) is built%s");
+  if (cfg->env < 0 || cfg->env > 2) return fail(nullptr, MPG_ERR_ARG, "unknown env%s");
+  static const int SD[3] = {6, 4, 6}, AD[3] = {2, 1, 1};
+  if (cfg->act_dim != AD[cfg->env]) return fail(nullptr, MPG_ERR_ARG, "act_dim does not match env%s");
+  const int want_obs = cfg->env == 0 ? 6 + cfg->num_future_data : (cfg->env == 1 ? 4 : 11);
+  if (cfg->obs_dim != want_obs || cfg->obs_dim > MPG_MAX_OBS) return fail(nullptr, MPG_ERR_ARG, "obs_dim does not match env%s");
+  if (cfg->max_rows <= 0 || cfg->max_horizon < 0) return fail(nullptr, MPG_ERR_ARG, "bad capacity%s");
+  mpg_ctx* c = new (std::nothrow) mpg_ctx();
+  if (!c) return fail(nullptr, MPG_ERR_ARG, "out of host memory%s");
+  c->cfg = *cfg;
+  c->err[0] = 0;
+  c->S = SD[cfg->env];
+  cudaDeviceProp prop;
+  if (cudaGetDevice(&c->device) != cudaSuccess || cudaGetDeviceProperties(&prop, c->device) != cudaSuccess) {
+    delete c;
+    return fail(nullptr, MPG_ERR_CUDA, "cudaGetDeviceProperties failed%s");
+  }
+  c->sms = prop.multiProcessorCount;
+  if (prop.major < 10) {
+    delete c;
+    return fail(nullptr, MPG_ERR_UNSUPPORTED, "built for sm_100a (B200) only%s");
+  }
+  auto alloc = [&](float** p, size_t n) -> bool {
+    if (cudaMalloc(p, n * sizeof(float)) != cudaSuccess) return false;
+    c->ws_bytes += n * sizeof(float);
+    return true;
+  };
+  bool ok = true;
+  size_t maxP = 0;
+  for (int n = 0; n < MPG_NUM_NETS && ok; ++n) {
+    NetStore& ns = c->nets[n];
+    const bool is_pol = (n == MPG_NET_POLICY || n == MPG_NET_POLICY_TARGET);
+    ns.in_dim = is_pol ? cfg->obs_dim : cfg->obs_dim + cfg->act_dim;
+    ns.out_dim = is_pol ? 2 * cfg->act_dim : 1;
+    GradLayout L(ns.in_dim, ns.out_dim);
+    maxP = L.total > (int)maxP ? L.total : maxP;
+    ok = ok && alloc(&ns.flat, L.total) && alloc(&ns.W1p, (size_t)MAX_IN * H) && alloc(&ns.W2p, (size_t)H * H)
+         && alloc(&ns.W2Tp, (size_t)H * H);
+  }
+  c->partial_stride = (maxP + 3) & ~size_t(3);
+  ok = ok && alloc(&c->ckpt, (size_t)(cfg->max_horizon + 1) * cfg->max_rows * c->S)
+       && alloc(&c->partial, (size_t)c->sms * c->partial_stride) && alloc(&c->loss_partial, c->sms);
+  if (ok) ok = tc_init(c->tc, c->cfg, c->sms, c->ws_bytes);
+  if (!ok) {
+    snprintf(g_create_err, 512, "cudaMalloc of the workspace failed: %s", cudaGetErrorString(cudaGetLastError()));
+    mpg_destroy(c);
+    return MPG_ERR_CUDA;
+  }
+  int rc = 0;
+  rc |= set_smem(c, rollout_kernel<MPG_ENV_PATH_TRACKING, true>);
+  rc |= set_smem(c, rollout_kernel<MPG_ENV_PATH_TRACKING, false>);
+  rc |= set_smem(c, rollout_kernel<MPG_ENV_INVERTED_PENDULUM, true>);
+  rc |= set_smem(c, rollout_kernel<MPG_ENV_INVERTED_PENDULUM, false>);
+  rc |= set_smem(c, rollout_kernel<MPG_ENV_INVERTED_DOUBLE_PENDULUM, true>);
+  rc |= set_smem(c, rollout_kernel<MPG_ENV_INVERTED_DOUBLE_PENDULUM, false>);
+  rc |= set_smem(c, q_grad_kernel);
+  rc |= set_smem(c, eval_kernel);
+  if (rc) {
+    strncpy(g_create_err, c->err, 512);
+    mpg_destroy(c);
+    return MPG_ERR_CUDA;
+  }
+  *out = c;
+  return MPG_OK;
+}
+
+void mpg_destroy(mpg_ctx* c) {
+  if (!c) return;
+  for (int n = 0; n < MPG_NUM_NETS; ++n) {
+    cudaFree(c->nets[n].flat); cudaFree(c->nets[n].W1p); cudaFree(c->nets[n].W2p); cudaFree(c->nets[n].W2Tp);
+  }
+  cudaFree(c->ckpt); cudaFree(c->partial); cudaFree(c->loss_partial);
+  tc_destroy(c->tc);
+  delete c;
+}
+
+int mpg_set_weights(mpg_ctx* ctx, int net, const float* const w[6], void* stream) {
+  if (!ctx || net < 0 || net >= MPG_NUM_NETS || !w) return fail(ctx, MPG_ERR_ARG, "bad argument to mpg_set_weights%s");
+  cudaStream_t st = (cudaStream_t)stream;
+  NetStore& ns = ctx->nets[net];
+  GradLayout L(ns.in_dim, ns.out_dim);
+  const int off[6] = {L.oW1, L.ob1, L.oW2, L.ob2, L.oW3, L.ob3};
+  const int cnt[6] = {ns.in_dim * H, H, H * H, H, H * ns.out_dim, ns.out_dim};
+  for (int i = 0; i < 6; ++i) {
+    if (!w[i]) return fail(ctx, MPG_ERR_ARG, "null weight pointer%s");
+    CUDA_OK(ctx, cudaMemcpyAsync(ns.flat + off[i], w[i], cnt[i] * sizeof(float), cudaMemcpyDefault, st));
+  }
+  pack_kernel<<<(H * H + 255) / 256, 256, 0, st>>>(ns.flat, ns.in_dim, ns.out_dim, ns.W1p, ns.W2p, ns.W2Tp);
+  ctx->launches++;
+  CUDA_OK(ctx, cudaGetLastError());
+  ns.set = true;
+  return tc_pack_weights(ctx->tc, net, ns.flat, ns.in_dim, ns.out_dim, st) ? MPG_OK
+                                                                           : fail(ctx, MPG_ERR_CUDA, "tc weight pack failed%s");
+}
+
+int mpg_get_weights(mpg_ctx* ctx, int net, float* const w[6], void* stream) {
+  int rc = check_net(ctx, net);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  NetStore& ns = ctx->nets[net];
+  GradLayout L(ns.in_dim, ns.out_dim);
+  const int off[6] = {L.oW1, L.ob1, L.oW2, L.ob2, L.oW3, L.ob3};
+  const int cnt[6] = {ns.in_dim * H, H, H * H, H, H * ns.out_dim, ns.out_dim};
+  for (int i = 0; i < 6; ++i)
+    CUDA_OK(ctx, cudaMemcpyAsync(w[i], ns.flat + off[i], cnt[i] * sizeof(float), cudaMemcpyDefault, st));
+  return MPG_OK;
+}
+
+int mpg_policy_grad(mpg_ctx* ctx, const mpg_rollout_params* p, const float* obs, const float* noise, float* grad_out,
+                    float* returns_out, void* stream) {
+  if (!ctx || !p || !obs || !grad_out) return fail(ctx, MPG_ERR_ARG, "null argument to mpg_policy_grad%s");
+  cudaStream_t st = (cudaStream_t)stream;
+  RolloutArgs a;
+  int rc = fill_rollout_args(ctx, p, a);
+  if (rc) return rc;
+  a.obs = obs; a.noise = noise; a.returns_out = returns_out;
+  a.noise_mode = noise ? 1 : (p->use_philox ? 2 : 0);
+  const int MB = p->rows * p->M;
+  const int ntiles = (MB + TILE_R - 1) / TILE_R;
+  const int grid = ntiles < ctx->sms ? ntiles : ctx->sms;
+  const GradLayout L(a.pol.in_dim, a.pol.out_dim);
+  a.partial = ctx->partial;
+  // partial stride must equal L.total for the kernel's indexing
+  CUDA_OK(ctx, cudaMemsetAsync(ctx->partial, 0, (size_t)grid * L.total * sizeof(float), st));
+  rc = launch_rollout<true>(ctx, a, grid, st);
+  if (rc) return rc;
+  reduce_partials_kernel<<<(L.total + 255) / 256, 256, 0, st>>>(ctx->partial, L.total, grid, L.total, grad_out,
+                                                                nullptr, nullptr);
+  ctx->launches++;
+  CUDA_OK(ctx, cudaGetLastError());
+  return MPG_OK;
+}
+
+int mpg_rollout_forward(mpg_ctx* ctx, const mpg_rollout_params* p, const float* obs, const float* start_actions,
+                        const float* noise, float* returns_out, float* traj_obs, float* traj_rew, float* traj_act,
+                        void* stream) {
+  if (!ctx || !p || !obs) return fail(ctx, MPG_ERR_ARG, "null argument to mpg_rollout_forward%s");
+  cudaStream_t st = (cudaStream_t)stream;
+  RolloutArgs a;
+  int rc = fill_rollout_args(ctx, p, a);
+  if (rc) return rc;
+  a.obs = obs; a.noise = noise; a.returns_out = returns_out;
+  a.start_actions = start_actions; a.use_start_actions = start_actions != nullptr;
+  a.traj_obs = traj_obs; a.traj_rew = traj_rew; a.traj_act = traj_act;
+  a.noise_mode = noise ? 1 : (p->use_philox ? 2 : 0);
+  const int MB = p->rows * p->M;
+  const int ntiles = (MB + TILE_R - 1) / TILE_R;
+  const int grid = ntiles < ctx->sms ? ntiles : ctx->sms;
+  return launch_rollout<false>(ctx, a, grid, st);
+}
+
+int mpg_returns_stats(mpg_ctx* ctx, const float* returns, int n_list, int rows, int M, float* out, void* stream) {
+  if (!ctx || !returns || !out || n_list <= 0) return fail(ctx, MPG_ERR_ARG, "bad argument to mpg_returns_stats%s");
+  returns_stats_kernel<<<n_list, 256, 0, (cudaStream_t)stream>>>(returns, n_list, rows, M, nullptr, out);
+  ctx->launches++;
+  CUDA_OK(ctx, cudaGetLastError());
+  return MPG_OK;
+}
+
+int mpg_returns_tile_mean(mpg_ctx* ctx, const float* returns, int n_list, int rows, int M, float* out, void* stream) {
+  if (!ctx || !returns || !out || n_list <= 0) return fail(ctx, MPG_ERR_ARG, "bad argument to mpg_returns_tile_mean%s");
+  returns_stats_kernel<<<n_list, 256, 0, (cudaStream_t)stream>>>(returns, n_list, rows, M, out, nullptr);
+  ctx->launches++;
+  CUDA_OK(ctx, cudaGetLastError());
+  return MPG_OK;
+}
+
+int mpg_q_grad(mpg_ctx* ctx, int net, int rows, int64_t global_rows, const float* obs, const float* act,
+               const float* target, float* grad_out, float* loss_sum_out, void* stream) {
+  if (!ctx || !obs || !act || !target || !grad_out || rows <= 0) return fail(ctx, MPG_ERR_ARG, "bad argument to mpg_q_grad%s");
+  int rc = check_net(ctx, net);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  QGradArgs a;
+  memset(&a, 0, sizeof(a));
+  a.obs_dim = ctx->cfg.obs_dim; a.act_dim = ctx->cfg.act_dim; a.rows = rows;
+  for (int i = 0; i < MPG_MAX_OBS; ++i) a.obs_scale[i] = ctx->cfg.obs_scale[i];
+  a.inv_global_rows = 1.f / (float)(global_rows > 0 ? global_rows : rows);
+  a.obs = obs; a.act = act; a.target = target;
+  a.partial = ctx->partial; a.loss_partial = ctx->loss_partial;
+  a.q = net_dev(ctx, net);
+  const int ntiles = (rows + TILE_R - 1) / TILE_R;
+  const int grid = ntiles < ctx->sms ? ntiles : ctx->sms;
+  const GradLayout L(a.q.in_dim, a.q.out_dim);
+  CUDA_OK(ctx, cudaMemsetAsync(ctx->partial, 0, (size_t)grid * L.total * sizeof(float), st));
+  q_grad_kernel<<<grid, NT, Smem::FLOATS * 4, st>>>(a);
+  reduce_partials_kernel<<<(L.total + 255) / 256, 256, 0, st>>>(ctx->partial, L.total, grid, L.total, grad_out,
+                                                                ctx->loss_partial, loss_sum_out);
+  ctx->launches += 2;
+  CUDA_OK(ctx, cudaGetLastError());
+  return MPG_OK;
+}
+
+static int launch_eval(mpg_ctx* ctx, EvalArgs& a, void* stream) {
+  const mpg_config& c = ctx->cfg;
+  a.obs_dim = c.obs_dim; a.act_dim = c.act_dim; a.policy_out_tanh = c.policy_out_tanh;
+  a.action_range = c.action_range; a.rew_scale = c.rew_scale; a.rew_shift = c.rew_shift; a.gamma = c.gamma;
+  for (int i = 0; i < MPG_MAX_OBS; ++i) a.obs_scale[i] = c.obs_scale[i];
+  const int ntiles = (a.rows + TILE_R - 1) / TILE_R;
+  const int grid = ntiles < ctx->sms ? ntiles : ctx->sms;
+  eval_kernel<<<grid, NT, Smem::FLOATS * 4, (cudaStream_t)stream>>>(a);
+  ctx->launches++;
+  CUDA_OK(ctx, cudaGetLastError());
+  return MPG_OK;
+}
+
+int mpg_policy_forward(mpg_ctx* ctx, int net, int rows, const float* obs, float* act_out, void* stream) {
+  if (!ctx || !obs || !act_out || rows <= 0) return fail(ctx, MPG_ERR_ARG, "bad argument to mpg_policy_forward%s");
+  int rc = check_net(ctx, net);
+  if (rc) return rc;
+  EvalArgs a;
+  memset(&a, 0, sizeof(a));
+  a.mode = 0; a.rows = rows; a.obs = obs; a.out = act_out; a.net0 = net_dev(ctx, net);
+  return launch_eval(ctx, a, stream);
+}
+
+int mpg_q_forward(mpg_ctx* ctx, int net, int rows, const float* obs, const float* act, float* q_out, void* stream) {
+  if (!ctx || !obs || !act || !q_out || rows <= 0) return fail(ctx, MPG_ERR_ARG, "bad argument to mpg_q_forward%s");
+  int rc = check_net(ctx, net);
+  if (rc) return rc;
+  EvalArgs a;
+  memset(&a, 0, sizeof(a));
+  a.mode = 1; a.rows = rows; a.obs = obs; a.act = act; a.out = q_out; a.net0 = net_dev(ctx, net);
+  return launch_eval(ctx, a, stream);
+}
+
+int mpg_q_target(mpg_ctx* ctx, int double_q, int rows, const float* rew, const float* obs_tp1, float* target_out,
+                 void* stream) {
+  if (!ctx || !rew || !obs_tp1 || !target_out || rows <= 0) return fail(ctx, MPG_ERR_ARG, "bad argument to mpg_q_target%s");
+  int rc = check_net(ctx, MPG_NET_POLICY_TARGET);
+  if (!rc) rc = check_net(ctx, MPG_NET_Q1_TARGET);
+  if (!rc && double_q) rc = check_net(ctx, MPG_NET_Q2_TARGET);
+  if (rc) return rc;
+  EvalArgs a;
+  memset(&a, 0, sizeof(a));
+  a.mode = 2; a.rows = rows; a.obs = obs_tp1; a.rew = rew; a.out = target_out; a.n_q = double_q ? 2 : 1;
+  a.net0 = net_dev(ctx, MPG_NET_POLICY_TARGET); a.net1 = net_dev(ctx, MPG_NET_Q1_TARGET);
+  if (double_q) a.net2 = net_dev(ctx, MPG_NET_Q2_TARGET);
+  return launch_eval(ctx, a, stream);
+}
+
+int mpg_td_error(mpg_ctx* ctx, int rows, const float* obs, const float* act, const float* rew, const float* obs_tp1,
+                 float* td_out, void* stream) {
+  if (!ctx || !obs || !act || !rew || !obs_tp1 || !td_out || rows <= 0) return fail(ctx, MPG_ERR_ARG, "bad argument to mpg_td_error%s");
+  int rc = check_net(ctx, MPG_NET_POLICY_TARGET);
+  if (!rc) rc = check_net(ctx, MPG_NET_Q1_TARGET);
+  if (!rc) rc = check_net(ctx, MPG_NET_Q1);
+  if (rc) return rc;
+  EvalArgs a;
+  memset(&a, 0, sizeof(a));
+  a.mode = 3; a.rows = rows; a.obs = obs; a.obs2 = obs_tp1; a.act = act; a.rew = rew; a.out = td_out;
+  a.net0 = net_dev(ctx, MPG_NET_POLICY_TARGET); a.net1 = net_dev(ctx, MPG_NET_Q1_TARGET); a.net2 = net_dev(ctx, MPG_NET_Q1);
+  return launch_eval(ctx, a, stream);
+}
+
+#define ENV_SWITCH(ctx, CALL)                                             \
+  switch ((ctx)->cfg.env) {                                               \
+    case MPG_ENV_PATH_TRACKING: { constexpr int EV = MPG_ENV_PATH_TRACKING; CALL; } break; \
+    case MPG_ENV_INVERTED_PENDULUM: { constexpr int EV = MPG_ENV_INVERTED_PENDULUM; CALL; } break; \
+    default: { constexpr int EV = MPG_ENV_INVERTED_DOUBLE_PENDULUM; CALL; } break; \
+  }
+
+int mpg_model_reset(mpg_ctx* ctx, int rows, const float* obs, float* state_out, void* stream) {
+  if (!ctx || !obs || !state_out || rows <= 0) return fail(ctx, MPG_ERR_ARG, "bad argument to mpg_model_reset%s");
+  cudaStream_t st = (cudaStream_t)stream;
+  ENV_SWITCH(ctx, (model_reset_kernel<EV><<<(rows + 127) / 128, 128, 0, st>>>(rows, ctx->cfg.obs_dim, obs, state_out)));
+  ctx->launches++;
+  CUDA_OK(ctx, cudaGetLastError());
+  return MPG_OK;
+}
+
+int mpg_model_step(mpg_ctx* ctx, int rows, const float* state_in, const float* action, const float* eps,
+                   float* state_out, float* obs_out, float* rew_out, void* stream) {
+  if (!ctx || !state_in || !action || !state_out || rows <= 0) return fail(ctx, MPG_ERR_ARG, "bad argument to mpg_model_step%s");
+  cudaStream_t st = (cudaStream_t)stream;
+  ENV_SWITCH(ctx, (model_step_kernel<EV><<<(rows + 127) / 128, 128, 0, st>>>(
+                      rows, ctx->cfg.obs_dim, ctx->cfg.num_future_data, state_in, action, eps, state_out, obs_out, rew_out)));
+  ctx->launches++;
+  CUDA_OK(ctx, cudaGetLastError());
+  return MPG_OK;
+}
+
+int mpg_model_step_bwd(mpg_ctx* ctx, int rows, const float* state_in, const float* action, const float* eps,
+                       const float* g_obs_out, const float* g_rew_out, const float* g_state_out, float* g_state_in,
+                       float* g_action, void* stream) {
+  if (!ctx || !state_in || !action || !g_state_in || !g_action || rows <= 0)
+    return fail(ctx, MPG_ERR_ARG, "bad argument to mpg_model_step_bwd%s");
+  cudaStream_t st = (cudaStream_t)stream;
+  ENV_SWITCH(ctx, (model_step_bwd_kernel<EV><<<(rows + 127) / 128, 128, 0, st>>>(
+                      rows, ctx->cfg.obs_dim, ctx->cfg.num_future_data, state_in, action, eps, g_obs_out, g_rew_out,
+                      g_state_out, g_state_in, g_action)));
+  ctx->launches++;
+  CUDA_OK(ctx, cudaGetLastError());
+  return MPG_OK;
+}
+
+int mpg_compute_rewards(mpg_ctx* ctx, int rows, const float* state, const float* scaled_action, float* rew_out,
+                        void* stream) {
+  if (!ctx || !state || !rew_out || rows <= 0) return fail(ctx, MPG_ERR_ARG, "bad argument to mpg_compute_rewards%s");
+  if (ctx->cfg.env == MPG_ENV_PATH_TRACKING && !scaled_action) return fail(ctx, MPG_ERR_ARG, "PathTracking rewards need actions%s");
+  cudaStream_t st = (cudaStream_t)stream;
+  ENV_SWITCH(ctx, (rewards_kernel<EV><<<(rows + 127) / 128, 128, 0, st>>>(rows, state, scaled_action, rew_out)));
+  ctx->launches++;
+  CUDA_OK(ctx, cudaGetLastError());
+  return MPG_OK;
+}
+
+int mpg_clip_global_norm(mpg_ctx* ctx, float* grad, int n, float clip, float* norm_out, void* stream) {
+  if (!ctx || !grad || n <= 0 || !(clip > 0.f)) return fail(ctx, MPG_ERR_ARG, "bad argument to mpg_clip_global_norm%s");
+  clip_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(grad, n, clip, norm_out);
+  ctx->launches++;
+  CUDA_OK(ctx, cudaGetLastError());
+  return MPG_OK;
+}
+
+int mpg_philox_noise(mpg_ctx* ctx, const mpg_rollout_params* p, float* out, void* stream) {
+  if (!ctx || !p || !out) return fail(ctx, MPG_ERR_ARG, "bad argument to mpg_philox_noise%s");
+  const long long total = (long long)p->horizon * p->rows * p->M;
+  if (total <= 0) return MPG_OK;
+  const long long gr = p->global_rows > 0 ? p->global_rows : p->rows;
+  philox_noise_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(p->noise_seed, gr, p->row_offset,
+                                                                                        p->rows, p->M, p->horizon, out);
+  ctx->launches++;
+  CUDA_OK(ctx, cudaGetLastError());
+  return MPG_OK;
+}
+
+}  // extern "C"

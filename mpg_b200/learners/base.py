@@ -1,0 +1,112 @@
+"""Shared host logic of the model-based learners: batch intake, sharded data parallelism, the
+flat gradient buffer, clipping, conversion back to the reference's list-of-numpy format."""
+import numpy as np
+import torch
+
+from ..engine import Engine  # noqa: F401  (documentation of the dependency)
+from ..preprocessor import Preprocessor
+from ..utils.misc import TimerStat
+
+
+def rule_based_weights(ite, total_ite, eta, rollout_list):
+    """MPGLearner.rule_based_weights (mpg_learner.py:384-399), evaluated in float32 like the TF graph.
+    Host-side: a handful of scalars per update, not device work."""
+    f = np.float32
+    lam = f(1. - eta) + f(2. * eta / total_ite) * f(ite)
+    lam = f(min(max(lam, f(0.)), f(1.5)))
+    if lam < 1.:
+        biases = np.array([np.power(lam, f(i), dtype=f) for i in rollout_list], dtype=f)
+    else:
+        mx = max(rollout_list)
+        biases = np.array([np.power(f(2.) - lam, f(mx - i), dtype=f) for i in rollout_list], dtype=f)
+    inv = f(1.) / (biases + f(1e-8))
+    e = np.exp(inv - inv.max(), dtype=f)
+    return (e / e.sum(dtype=f)).astype(f)
+
+
+class LearnerBase(object):
+    """What MPGLearner and NADPLearner share (mpg_learner.py:30-64,171-178; nadp.py:29-53,78-85)."""
+
+    def __init__(self, policy_cls, args):
+        self.args = args
+        self.batch_size = self.args.replay_batch_size
+        self.policy_with_value = policy_cls(**vars(self.args))
+        self.engine = self.policy_with_value.engine
+        self.batch_data = {}
+        self.counter = 0
+        self.num_batch_reuse = self.args.num_batch_reuse
+        self.M = self.args.M
+        self.num_rollout_list_for_policy_update = list(self.args.num_rollout_list_for_policy_update)
+        self.num_rollout_list_for_q_estimation = list(self.args.num_rollout_list_for_q_estimation or [])
+        self.preprocessor = Preprocessor(self.args.obs_dim, self.args.obs_ptype, self.args.rew_ptype,
+                                         self.args.obs_scale, self.args.rew_scale, self.args.rew_shift,
+                                         gamma=self.args.gamma)
+        self.policy_gradient_timer = TimerStat()
+        self.q_gradient_timer = TimerStat()
+        self.target_timer = TimerStat()
+        self.stats = {}
+        self.info_for_buffer = {}
+        # noise of the model rollout: None -> in-kernel Philox keyed by (seed, global row, step);
+        # tests install explicit eps tensors with set_rollout_noise
+        self.noise_seed = int(getattr(self.args, 'noise_seed', 7))
+        self._noise_q = self._noise_p = None
+        self._dev = {}
+        # data parallel: each rank holds a contiguous shard of the global batch
+        self.world_size, self.rank = 1, 0
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            self.world_size, self.rank = torch.distributed.get_world_size(), torch.distributed.get_rank()
+
+    # -- reference interface ------------------------------------------------------------------------
+    def get_stats(self):
+        return self.stats
+
+    def get_info_for_buffer(self):
+        return self.info_for_buffer
+
+    def get_weights(self):
+        return self.policy_with_value.get_weights()
+
+    def set_weights(self, weights):
+        return self.policy_with_value.set_weights(weights)
+
+    def set_ppc_params(self, params):
+        self.preprocessor.set_params(params)
+
+    # -- helpers ------------------------------------------------------------------------------------
+    def set_rollout_noise(self, noise_q=None, noise_p=None):
+        """Explicit standard-normal eps, shape (n, M*B), for the Q-target / policy rollouts."""
+        self._noise_q = None if noise_q is None else self.engine.dev(noise_q)
+        self._noise_p = None if noise_p is None else self.engine.dev(noise_p)
+
+    def _upload_batch(self, batch_data):
+        # mpg_learner.py:66-72: cast to fp32; here additionally host -> device (pinned when possible)
+        names = ('batch_obs', 'batch_actions', 'batch_rewards', 'batch_obs_tp1', 'batch_dones')
+        self.batch_data = {k: np.asarray(v).astype(np.float32) for k, v in zip(names, batch_data)}
+        self._dev = {k: self.engine.dev(v) for k, v in self.batch_data.items() if k != 'batch_dones'}
+
+    @property
+    def global_rows(self):
+        return self._dev['batch_obs'].shape[0] * self.world_size
+
+    @property
+    def row_offset(self):
+        return self._dev['batch_obs'].shape[0] * self.rank
+
+    def _allreduce(self, flat):
+        if self.world_size > 1:
+            torch.distributed.all_reduce(flat, op=torch.distributed.ReduceOp.SUM)
+        return flat
+
+    def _split_to_numpy(self, flat_host, nets):
+        """flat fp32 host vector (concatenated nets) -> list of arrays in [W1,b1,W2,b2,W3,b3] order per net."""
+        out, pos = [], 0
+        a = self.args
+        for kind in nets:
+            in_dim = a.obs_dim + (a.act_dim if kind == 'q' else 0)
+            out_dim = 1 if kind == 'q' else 2 * a.act_dim
+            for shape in ((in_dim, 256), (256,), (256, 256), (256,), (256, out_dim), (out_dim,)):
+                n = int(np.prod(shape))
+                out.append(flat_host[pos:pos + n].reshape(shape))
+                pos += n
+        assert pos == flat_host.size
+        return out

@@ -98,3 +98,28 @@ def default_obs_scale(env_id, num_future_data=0):
     if env_id == 'InvertedPendulumConti-v0':
         return [0.001, 1 / 3, 0.1, 0.5]
     return [1.0] * 11
+
+
+def philox_normal(seed, rows, n_steps, global_rows=None, row_offset=0, M=1):
+    """numpy restatement of the in-kernel noise stream (csrc/common.cuh: philox4x32_10 + Box-Muller):
+    eps[t, m*rows + i] keyed by (seed, m*global_rows + row_offset + i, t). Returns (n_steps, M*rows) fp32."""
+    global_rows = rows if global_rows is None else global_rows
+    m_idx, i_idx = np.divmod(np.arange(M * rows, dtype=np.uint64), np.uint64(rows))
+    nrow = m_idx * np.uint64(global_rows) + np.uint64(row_offset) + i_idx
+    t = np.arange(n_steps, dtype=np.uint64)[:, None]
+    c0 = np.broadcast_to((nrow & np.uint64(0xFFFFFFFF))[None, :], (n_steps, M * rows)).copy()
+    c1 = np.broadcast_to((nrow >> np.uint64(32))[None, :], (n_steps, M * rows)).copy()
+    c2 = np.broadcast_to(t, (n_steps, M * rows)).copy()
+    c3 = np.zeros_like(c0)
+    k0, k1 = np.uint64(seed & 0xFFFFFFFF), np.uint64((seed >> 32) & 0xFFFFFFFF)
+    M0, M1, W0, W1, MASK = (np.uint64(v) for v in (0xD2511F53, 0xCD9E8D57, 0x9E3779B9, 0xBB67AE85, 0xFFFFFFFF))
+    for _ in range(10):
+        p0, p1 = M0 * c0, M1 * c2
+        hi0, lo0, hi1, lo1 = p0 >> np.uint64(32), p0 & MASK, p1 >> np.uint64(32), p1 & MASK
+        c0, c1, c2, c3 = hi1 ^ c1 ^ k0, lo1, hi0 ^ c3 ^ k1, lo0
+        k0, k1 = (k0 + W0) & MASK, (k1 + W1) & MASK
+    f = np.float32
+    u1 = (c0.astype(f) + f(0.5)) * f(2.3283064365386963e-10)
+    u2 = (c1.astype(f) + f(0.5)) * f(2.3283064365386963e-10)
+    u1 = np.clip(u1, f(1e-12), f(1.0))
+    return (np.sqrt(f(-2.0) * np.log(u1)) * np.cos(np.float64(2.0 * np.pi) * u2.astype(np.float64))).astype(f)

@@ -1,0 +1,350 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI) against
+  * golden vectors produced by the reference's own Python (H=256 cases), and
+  * the CPU oracle (fp64) on the same seeded inputs,
+to the north-star tolerances: rollout states / rewards <= 1e-5 relative (norm-relative per step),
+gradients <= 1e-4 relative L2.  Every test runs for each available kernel backend (fp32 FFMA and,
+when it covers the configuration, the tcgen05 tensor-core path)."""
+import numpy as np
+import pytest
+import torch
+
+from mpg_b200 import synthetic
+from mpg_b200.config import default_args
+from tests.util import load_golden, make_batch, mpg_case_inputs, nadp_case_inputs, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+TOL_STATE, TOL_GRAD = 1e-5, 1e-4
+PT, IP, IDP = 'PathTracking-v0', 'InvertedPendulumConti-v0', 'InvertedDoublePendulum-v2'
+
+
+def _learner(kind, args, weights, backend):
+    from mpg_b200.learners import MPGLearner, NADPLearner
+    from mpg_b200.policy import PolicyWithQs
+    learner = (NADPLearner if kind == 'nadp' else MPGLearner)(PolicyWithQs, args)
+    learner.set_weights(weights)
+    if backend == 'tc':
+        if not learner.engine.tc_available():
+            pytest.skip('tensor-core backend does not cover this configuration')
+        learner.engine.set_backend(1)
+    return learner
+
+
+def _flat(grads):
+    return np.concatenate([np.asarray(g, np.float64).ravel() for g in grads])
+
+
+def _split_nets(flat, sizes):
+    out, pos = [], 0
+    for s in sizes:
+        out.append(flat[pos:pos + s])
+        pos += s
+    return out
+
+
+def _unclip(g, norm, clip):
+    return g * max(norm, clip) / clip
+
+
+BACKENDS = ['ffma', 'tc']
+
+
+# ------------------------------------------------------------------------------------------------
+# golden vectors from the reference's own code (H = 256)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('backend', BACKENDS)
+def test_nadp_compute_gradient_matches_reference_golden(backend):
+    case, gold = load_golden('nadp_pt_h256')
+    args, w, batch, nq, npol = nadp_case_inputs(case)
+    learner = _learner('nadp', args, w, backend)
+    learner.set_rollout_noise(nq, npol)
+    grads = learner.compute_gradient(batch, None, None, 7)
+    st = learner.get_stats()
+    assert len(grads) == 12 and grads[0].shape == (8, 256) and grads[10].shape == (256, 4)
+    flat = _flat(grads)
+    nQ = gold['q_grad__f64'].size
+    qg, pg = flat[:nQ], flat[nQ:]
+    clip = args.gradient_clip_norm
+    # the golden stores unclipped gradients + pre-clip norms; undo the clip with the reported norm
+    assert rel_l2(_unclip(qg, st['q_gradient_norm'], clip), gold['q_grad__f64']) <= TOL_GRAD
+    assert rel_l2(_unclip(pg, st['policy_gradient_norm'], clip), gold['policy_grad__f64']) <= TOL_GRAD
+    for k in ('q_loss', 'policy_loss', 'value_mean', 'q_gradient_norm', 'policy_gradient_norm'):
+        assert rel_l2(st[k], gold[f'stat_{k}__f64']) <= 2e-5, (k, st[k], gold[f'stat_{k}__f64'])
+    # forward-only Q-target rollout (nadp.py:87-126)
+    learner.set_rollout_noise(nq, npol)
+    tgt = learner.model_rollout_for_q_estimation(learner._dev['batch_obs'], learner._dev['batch_actions'])
+    assert rel_l2(tgt.cpu().numpy(), gold['q_targets__f64']) <= TOL_STATE
+
+
+@pytest.mark.parametrize('backend', BACKENDS)
+def test_mpg_v2_compute_gradient_matches_reference_golden(backend):
+    case, gold = load_golden('mpg2_pt_h256')
+    args, w, batch, npol = mpg_case_inputs(case)
+    learner = _learner('mpg', args, w, backend)
+    learner.set_rollout_noise(None, npol)
+    grads = learner.compute_gradient(batch, None, None, case['iteration'])
+    st = learner.get_stats()
+    assert len(grads) == 18
+    flat = _flat(grads)
+    nQ = gold['q_grad1__f64'].size
+    q1, q2, pg = flat[:nQ], flat[nQ:2 * nQ], flat[2 * nQ:]
+    clip = args.gradient_clip_norm
+    assert rel_l2(learner.batch_data['batch_targets'].cpu().numpy(), gold['batch_targets__f64']) <= TOL_STATE
+    assert rel_l2(_unclip(q1, st['q_gradient_norm1'], clip), gold['q_grad1__f64']) <= TOL_GRAD
+    assert rel_l2(_unclip(q2, st['q_gradient_norm2'], clip), gold['q_grad2__f64']) <= TOL_GRAD
+    assert rel_l2(_unclip(pg, st['policy_gradient_norm'], clip), gold['policy_grad__f64']) <= TOL_GRAD
+    for k in ('value_mean', 'policy_total_loss', 'policy_gradient_norm', 'q_loss1', 'q_gradient_norm1', 'q_loss2',
+              'q_gradient_norm2'):
+        assert rel_l2(st[k], gold[f'stat_{k}__f64']) <= 2e-5, (k, st[k], gold[f'stat_{k}__f64'])
+    assert np.allclose(st['w_list'], gold['stat_w_list__f64'], rtol=1e-4)
+    assert rel_l2(st['all_losses'], gold['stat_all_losses__f64']) <= 2e-5
+
+
+# ------------------------------------------------------------------------------------------------
+# CUDA vs oracle (fp64) on seeded inputs: variants and sizes
+# ------------------------------------------------------------------------------------------------
+def _nadp_vs_oracle(env_id, B, n, M, nfd, backend, seed=0, buffer_type='normal', tol_grad=TOL_GRAD, tol_scalar=2e-5):
+    from oracle import mpg_oracle as O
+    args = default_args('NADP', env_id, replay_batch_size=B, M=M, num_future_data=nfd,
+                        num_rollout_list_for_policy_update=[n], num_rollout_list_for_q_estimation=[n],
+                        buffer_type=buffer_type)
+    w = synthetic.make_policy_with_qs_weights(100 + seed, args.obs_dim, args.act_dim, 256, double_q=False)
+    batch = make_batch(200 + seed, env_id, B, nfd)
+    rng = np.random.default_rng(300 + seed)
+    nq, npol = synthetic.make_noise(rng, n, B * M), synthetic.make_noise(rng, n, B * M)
+    learner = _learner('nadp', args, w, backend)
+    learner.set_rollout_noise(nq, npol)
+    flat = _flat(learner.compute_gradient(batch, None, None, 0))
+    st = learner.get_stats()
+    ref = O.nadp_compute_gradient(args, w, batch, nq, npol, torch.float64)
+    nQ = ref['q_grad'].size
+    clip = args.gradient_clip_norm
+    errs = dict(q=rel_l2(_unclip(flat[:nQ], st['q_gradient_norm'], clip), ref['q_grad']),
+                p=rel_l2(_unclip(flat[nQ:], st['policy_gradient_norm'], clip), ref['policy_grad']),
+                clipped=rel_l2(flat, ref['compute_gradient']),
+                q_loss=rel_l2(st['q_loss'], ref['q_loss']), policy_loss=rel_l2(st['policy_loss'], ref['policy_loss']),
+                value_mean=rel_l2(st['value_mean'], ref['value_mean']))
+    if buffer_type != 'normal':
+        errs['td'] = rel_l2(learner.get_info_for_buffer()['td_error'], ref['td_error'])
+    print(env_id, B, n, M, nfd, backend, errs)
+    assert errs['q'] <= tol_grad and errs['p'] <= tol_grad and errs['clipped'] <= tol_grad, errs
+    for k in ('q_loss', 'policy_loss', 'value_mean'):
+        assert errs[k] <= tol_scalar, errs
+    if 'td' in errs:
+        assert errs['td'] <= tol_scalar, errs
+    return learner
+
+
+@pytest.mark.parametrize('backend', BACKENDS)
+@pytest.mark.parametrize('B,n,M,nfd', [(256, 25, 1, 0), (100, 25, 1, 0), (1, 25, 1, 0), (48, 10, 2, 2), (64, 1, 1, 0),
+                                       (2048, 25, 1, 0)])
+def test_nadp_pathtracking_vs_oracle(B, n, M, nfd, backend):
+    _nadp_vs_oracle(PT, B, n, M, nfd, backend, buffer_type='priority' if B == 48 else 'normal')
+
+
+@pytest.mark.parametrize('backend', BACKENDS)
+def test_nadp_inverted_pendulum_vs_oracle(backend):
+    _nadp_vs_oracle(IP, 200, 25, 1, 0, backend)
+
+
+@pytest.mark.parametrize('backend', BACKENDS)
+def test_nadp_double_pendulum_vs_oracle(backend):
+    # the falling double pendulum amplifies fp32 rounding (two correct fp32 codes agree to ~1e-2 on n=25
+    # gradients, tests/test_oracle_golden.py): the north-star tolerance is checked on a short horizon,
+    # the full horizon against the fp32-vs-fp64 spread of the oracle itself.
+    _nadp_vs_oracle(IDP, 128, 3, 1, 0, backend)
+    _nadp_vs_oracle(IDP, 128, 25, 1, 0, backend, tol_grad=5e-2, tol_scalar=5e-3)
+
+
+@pytest.mark.parametrize('backend', BACKENDS)
+@pytest.mark.parametrize('version,rollout_list,M,nfd,deriv,ite,env_id', [
+    ('MPG-v2', [0, 25], 1, 0, False, 4000, PT),
+    ('MPG-v2', [0, 3, 25], 2, 2, False, 5000, PT),
+    ('MPG-v2', [0, 25], 1, 0, True, 2000, PT),
+    ('MPG-v1', [0, 25], 1, 0, False, 4500, PT),
+    ('MPG-v2', [25], 1, 0, False, 100, PT),
+    ('MPG-v2', [0, 25], 1, 0, False, 1500, IP),
+])
+def test_mpg_vs_oracle(version, rollout_list, M, nfd, deriv, ite, env_id, backend):
+    from oracle import mpg_oracle as O
+    B = 160
+    args = default_args(version, env_id, replay_batch_size=B, M=M, num_future_data=nfd,
+                        num_rollout_list_for_policy_update=rollout_list, deriv_interval_policy=deriv,
+                        buffer_type='priority', sample_num_in_learner=None)
+    dq = version == 'MPG-v2'
+    w = synthetic.make_policy_with_qs_weights(7, args.obs_dim, args.act_dim, 256, double_q=dq)
+    batch = make_batch(8, env_id, B, nfd)
+    npol = synthetic.make_noise(np.random.default_rng(9), max(rollout_list), B * M)
+    learner = _learner('mpg', args, w, backend)
+    learner.set_rollout_noise(None, npol)
+    flat = _flat(learner.compute_gradient(batch, None, None, ite))
+    st = learner.get_stats()
+    ref = O.mpg_compute_gradient(args, w, batch, npol, ite, torch.float64)
+    errs = dict(clipped=rel_l2(flat, ref['compute_gradient']),
+                targets=rel_l2(learner.batch_data['batch_targets'].cpu().numpy(), ref['batch_targets']),
+                td=rel_l2(learner.get_info_for_buffer()['td_error'], ref['td_error']),
+                total_loss=rel_l2(st['policy_total_loss'], ref['total_loss']),
+                value_mean=rel_l2(st['value_mean'], ref['value_mean']),
+                pnorm=rel_l2(st['policy_gradient_norm'], ref['policy_gradient_norm']),
+                q1=rel_l2(st['q_loss1'], ref['q_loss1']))
+    nQ = ref['q_grad1'].size
+    nq_nets = 2 if dq else 1
+    errs['p'] = rel_l2(_unclip(flat[nq_nets * nQ:], st['policy_gradient_norm'], args.gradient_clip_norm), ref['policy_grad'])
+    print(version, rollout_list, M, nfd, deriv, env_id, backend, errs)
+    assert errs['clipped'] <= TOL_GRAD and errs['p'] <= TOL_GRAD, errs
+    for k in ('targets', 'td', 'total_loss', 'value_mean', 'pnorm', 'q1'):
+        assert errs[k] <= 2e-5, errs
+    assert np.allclose(st['w_list'], ref['ws'], rtol=1e-4, atol=1e-7)
+    var_ref = ref['returns_var']
+    assert np.allclose(st['returns_var'], var_ref, rtol=2e-2, atol=1e-6 * max(1.0, float(np.abs(ref['minus_returns']).max()) ** 2))
+
+
+@pytest.mark.parametrize('backend', BACKENDS)
+@pytest.mark.parametrize('env_id,nfd', [(PT, 0), (PT, 2), (IP, 0), (IDP, 0)])
+def test_closed_loop_trajectories_vs_oracle(env_id, nfd, backend):
+    """States and rewards of the closed-loop rollout, per step, <= 1e-5 norm-relative (fp32)."""
+    from oracle import mpg_oracle as O
+    from mpg_b200.policy import PolicyWithQs
+    B, n = 512, 25
+    args = default_args('NADP', env_id, replay_batch_size=B, num_future_data=nfd)
+    w = synthetic.make_policy_with_qs_weights(17, args.obs_dim, args.act_dim, 256, double_q=False)
+    rng = np.random.default_rng(18)
+    obs0 = synthetic.make_obs(rng, env_id, B, nfd)
+    noise = synthetic.make_noise(rng, n, B)
+    pol = PolicyWithQs(**vars(args))
+    pol.set_weights(w)
+    e = pol.engine
+    if backend == 'tc':
+        if not e.tc_available():
+            pytest.skip('tensor-core backend does not cover this configuration')
+        e.set_backend(1)
+    ret, t_obs, t_rew, t_act = e.rollout_forward(e.dev(obs0), [n], noise=e.dev(noise), want_traj=True)
+    ro, rr, ra = O.closed_loop(args, w[1], obs0, noise, n, torch.float64)
+    worst = 0.0
+    horizon_checked = n if env_id != IDP else 4   # chaotic beyond a few steps in fp32 (see above)
+    for t in range(horizon_checked):
+        worst = max(worst, rel_l2(t_obs[t].cpu().numpy(), ro[t]), rel_l2(t_rew[t].cpu().numpy(), rr[t]))
+    worst = max(worst, rel_l2(t_act[:horizon_checked + 1].cpu().numpy(), ra[:horizon_checked + 1]))
+    print(env_id, nfd, backend, 'worst per-step rel-L2', worst)
+    assert worst <= TOL_STATE, worst
+
+
+def test_model_api_single_steps_match_reference_golden():
+    """<Env>Model.reset / rollout_out (the reference's model API) against the reference's own trajectories."""
+    from mpg_b200.envs_and_models import NAME2MODELCLS
+    from tests.util import model_case_inputs
+    for name in ('model_pt', 'model_pt_nfd2', 'model_ip', 'model_idp'):
+        case, gold = load_golden(name)
+        args, obs0, acts, noise, _ = model_case_inputs(case)
+        model = NAME2MODELCLS[case['env_id']](**vars(args))
+        model.set_noise(list(noise))
+        model.reset(obs0)
+        steps = case['n'] if 'idp' not in name else 4
+        for t in range(steps):
+            o, r = model.rollout_out(acts[t])
+            assert rel_l2(o.cpu().numpy(), gold['open_obs__f64'][t]) <= TOL_STATE, (name, t)
+            assert rel_l2(r.cpu().numpy(), gold['open_rew__f64'][t]) <= TOL_STATE, (name, t)
+
+
+@pytest.mark.parametrize('env_id', [PT, IP, IDP])
+def test_model_api_autograd_matches_oracle(env_id):
+    """d(sum of rewards + final obs)/d(actions, obs0) through 3 chained rollout_out calls."""
+    from oracle import mpg_oracle as O
+    from mpg_b200.envs_and_models import NAME2MODELCLS
+    B, n = 64, 3
+    args = default_args('NADP', env_id)
+    rng = np.random.default_rng(5)
+    obs0 = synthetic.make_obs(rng, env_id, B)
+    acts = rng.uniform(-1, 1, (n, B, args.act_dim)).astype(np.float32)
+    noise = synthetic.make_noise(rng, n, B)
+    wobs = rng.standard_normal(args.obs_dim)
+    # oracle
+    m = O.NAME2MODELCLS[env_id]()
+    a64 = torch.tensor(acts, dtype=torch.float64, requires_grad=True)
+    m.reset(torch.tensor(obs0, dtype=torch.float64))
+    loss = 0
+    for t in range(n):
+        o, r = m.rollout_out(a64[t], torch.tensor(noise[t], dtype=torch.float64))
+        loss = loss + r.sum()
+    loss = loss + (o * torch.tensor(wobs)).sum()
+    g_ref = torch.autograd.grad(loss, a64)[0].numpy()
+    # CUDA
+    model = NAME2MODELCLS[env_id](**vars(args))
+    model.set_noise(list(noise))
+    a32 = torch.tensor(acts, device='cuda', requires_grad=True)
+    model.reset(obs0)
+    loss = 0
+    for t in range(n):
+        o, r = model.rollout_out(a32[t])
+        loss = loss + r.sum()
+    loss = loss + (o * torch.tensor(wobs, device='cuda', dtype=torch.float32)).sum()
+    loss.backward()
+    assert rel_l2(a32.grad.cpu().numpy(), g_ref) <= TOL_GRAD
+
+
+def test_philox_noise_matches_numpy_restatement():
+    from mpg_b200.engine import Engine
+    args = default_args('NADP', PT)
+    e = Engine(**vars(args))
+    got = e.philox_noise(rows=300, M=2, horizon=7, noise_seed=0x1234567890, global_rows=1000, row_offset=400).cpu().numpy()
+    want = synthetic.philox_normal(0x1234567890, 300, 7, global_rows=1000, row_offset=400, M=2)
+    assert np.abs(got - want).max() < 5e-6
+    assert abs(got.mean()) < 0.05 and abs(got.std() - 1.0) < 0.05
+
+
+# ------------------------------------------------------------------------------------------------
+# size-independent properties at the bench size
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('backend', BACKENDS)
+def test_full_size_properties(backend):
+    """B = 65536, n = 25 (BASELINE config 2): run-to-run bit reproducibility, linearity of the gradient
+    in the rollout weights, shard invariance (two half batches with global scaling add up to the full batch),
+    M-tiling with identical noise equals M = 1."""
+    from mpg_b200 import _lib
+    from mpg_b200.policy import PolicyWithQs
+    B, n = 65536, 25
+    args = default_args('NADP', PT, replay_batch_size=B)
+    pol = PolicyWithQs(**vars(args))
+    pol.set_weights(synthetic.make_policy_with_qs_weights(1, args.obs_dim, args.act_dim, 256, double_q=False))
+    e = pol.engine
+    if backend == 'tc':
+        if not e.tc_available():
+            pytest.skip('tensor-core backend does not cover this configuration')
+        e.set_backend(1)
+    obs = e.dev(synthetic.make_obs(np.random.default_rng(2), PT, B))
+    kw = dict(full_bptt=True, use_philox=True, noise_seed=11)
+    g1, r1 = e.policy_grad(obs, [0, n], [0.3, 0.7], **kw)
+    g2, r2 = e.policy_grad(obs, [0, n], [0.3, 0.7], **kw)
+    assert torch.equal(g1, g2) and torch.equal(r1, r2), 'not bit-reproducible run to run'
+    assert torch.isfinite(g1).all() and torch.isfinite(r1).all()
+    ga, _ = e.policy_grad(obs, [0, n], [1.0, 0.0], **kw)
+    gb, _ = e.policy_grad(obs, [0, n], [0.0, 1.0], **kw)
+    assert rel_l2((0.3 * ga + 0.7 * gb).cpu().numpy(), g1.cpu().numpy()) <= 1e-5
+    h = B // 2
+    gl, _ = e.policy_grad(obs[:h].contiguous(), [0, n], [0.3, 0.7], global_rows=B, row_offset=0, **kw)
+    gr, _ = e.policy_grad(obs[h:].contiguous(), [0, n], [0.3, 0.7], global_rows=B, row_offset=h, **kw)
+    assert rel_l2((gl + gr).cpu().numpy(), g1.cpu().numpy()) <= 1e-5
+    # M = 2 with the same eps on both tiles == M = 1
+    Bs = 4096
+    eps = e.dev(synthetic.make_noise(np.random.default_rng(3), n, Bs))
+    gm1, rm1 = e.policy_grad(obs[:Bs].contiguous(), [n], [1.0], M=1, noise=eps, full_bptt=True)
+    gm2, rm2 = e.policy_grad(obs[:Bs].contiguous(), [n], [1.0], M=2, noise=torch.cat([eps, eps], 1).contiguous(), full_bptt=True)
+    assert rel_l2(gm2.cpu().numpy(), gm1.cpu().numpy()) <= 1e-5
+    assert torch.allclose(rm2[:, :Bs], rm1) and torch.allclose(rm2[:, Bs:], rm1)
+
+
+def test_error_paths():
+    from mpg_b200.engine import Engine
+    from mpg_b200.learners import MPGLearner
+    from mpg_b200.policy import PolicyWithQs
+    args = default_args('NADP', PT)
+    e = Engine(**vars(args))
+    obs = e.dev(synthetic.make_obs(np.random.default_rng(0), PT, 8))
+    with pytest.raises(RuntimeError, match='never set'):
+        e.policy_grad(obs, [25], [1.0])
+    with pytest.raises(NotImplementedError):
+        PolicyWithQs(**vars(default_args('NADP', PT, policy_num_hidden_units=64)))
+    bad = default_args('MPG-v2', PT)
+    bad.learner_version = 'MPG-v3'
+    with pytest.raises(ValueError):
+        MPGLearner(PolicyWithQs, bad)
