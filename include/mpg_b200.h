@@ -174,6 +174,12 @@ enum { MPG_BACKEND_FFMA = 0, MPG_BACKEND_TC = 1 };
 int mpg_set_backend(mpg_ctx* ctx, int backend);
 int mpg_get_backend(const mpg_ctx* ctx);
 
+/* Optional device timing of the dominant (rollout) kernel: when enabled, CUDA events are recorded on
+ * the caller's stream immediately around that launch; mpg_kernel_ms() waits for the last pair and
+ * returns its duration in milliseconds (<0: nothing recorded). Used by bench.py for the roofline. */
+int mpg_set_timing(mpg_ctx* ctx, int enabled);
+float mpg_kernel_ms(mpg_ctx* ctx);
+
 /* counters for bench.py: kernels launched by this handle since creation */
 uint64_t mpg_launch_count(const mpg_ctx* ctx);
 

@@ -35,6 +35,8 @@ struct mpg_ctx {
   size_t ws_bytes = 0;
   uint64_t launches = 0;
   int backend = MPG_BACKEND_FFMA;
+  int timing = 0, timed = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   char err[512];
   TcState tc;
 };
@@ -180,17 +182,20 @@ int fill_rollout_args(mpg_ctx* ctx, const mpg_rollout_params* p, RolloutArgs& a)
   }
   a.ckpt = ctx->ckpt;
   a.partial = ctx->partial;
+  a.partial_stride = (long long)ctx->partial_stride;
   return MPG_OK;
 }
 
 template <bool BWD>
 int launch_rollout(mpg_ctx* ctx, const RolloutArgs& a, int grid, cudaStream_t st) {
   const size_t smem = Smem::FLOATS * 4;
+  if (ctx->timing) cudaEventRecord(ctx->ev0, st);
   switch (ctx->cfg.env) {
     case MPG_ENV_PATH_TRACKING: rollout_kernel<MPG_ENV_PATH_TRACKING, BWD><<<grid, NT, smem, st>>>(a); break;
     case MPG_ENV_INVERTED_PENDULUM: rollout_kernel<MPG_ENV_INVERTED_PENDULUM, BWD><<<grid, NT, smem, st>>>(a); break;
     default: rollout_kernel<MPG_ENV_INVERTED_DOUBLE_PENDULUM, BWD><<<grid, NT, smem, st>>>(a); break;
   }
+  if (ctx->timing) { cudaEventRecord(ctx->ev1, st); ctx->timed = 1; }
   ctx->launches++;
   CUDA_OK(ctx, cudaGetLastError());
   return MPG_OK;
@@ -213,6 +218,23 @@ int mpg_set_backend(mpg_ctx* ctx, int backend) {
     return fail(ctx, MPG_ERR_UNSUPPORTED, "tensor-core backend does not cover this configuration%s");
   ctx->backend = backend;
   return MPG_OK;
+}
+
+int mpg_set_timing(mpg_ctx* ctx, int enabled) {
+  if (!ctx) return MPG_ERR_ARG;
+  if (enabled && !ctx->ev0) {
+    CUDA_OK(ctx, cudaEventCreate(&ctx->ev0));
+    CUDA_OK(ctx, cudaEventCreate(&ctx->ev1));
+  }
+  ctx->timing = enabled ? 1 : 0;
+  ctx->timed = 0;
+  return MPG_OK;
+}
+float mpg_kernel_ms(mpg_ctx* ctx) {
+  if (!ctx || !ctx->timed) return -1.f;
+  float ms = -1.f;
+  if (cudaEventSynchronize(ctx->ev1) != cudaSuccess || cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) != cudaSuccess) return -1.f;
+  return ms;
 }
 
 int mpg_param_count(const mpg_ctx* ctx, int net) {
@@ -298,6 +320,7 @@ void mpg_destroy(mpg_ctx* c) {
     cudaFree(c->nets[n].flat); cudaFree(c->nets[n].W1p); cudaFree(c->nets[n].W2p); cudaFree(c->nets[n].W2Tp);
   }
   cudaFree(c->ckpt); cudaFree(c->partial); cudaFree(c->loss_partial);
+  if (c->ev0) { cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); }
   tc_destroy(c->tc);
   delete c;
 }
@@ -347,13 +370,11 @@ int mpg_policy_grad(mpg_ctx* ctx, const mpg_rollout_params* p, const float* obs,
   const int ntiles = (MB + TILE_R - 1) / TILE_R;
   const int grid = ntiles < ctx->sms ? ntiles : ctx->sms;
   const GradLayout L(a.pol.in_dim, a.pol.out_dim);
-  a.partial = ctx->partial;
-  // partial stride must equal L.total for the kernel's indexing
-  CUDA_OK(ctx, cudaMemsetAsync(ctx->partial, 0, (size_t)grid * L.total * sizeof(float), st));
+  CUDA_OK(ctx, cudaMemsetAsync(ctx->partial, 0, (size_t)grid * ctx->partial_stride * sizeof(float), st));
   rc = launch_rollout<true>(ctx, a, grid, st);
   if (rc) return rc;
-  reduce_partials_kernel<<<(L.total + 255) / 256, 256, 0, st>>>(ctx->partial, L.total, grid, L.total, grad_out,
-                                                                nullptr, nullptr);
+  reduce_partials_kernel<<<(L.total + 255) / 256, 256, 0, st>>>(ctx->partial, ctx->partial_stride, grid, L.total,
+                                                                grad_out, nullptr, nullptr);
   ctx->launches++;
   CUDA_OK(ctx, cudaGetLastError());
   return MPG_OK;
@@ -405,15 +426,15 @@ int mpg_q_grad(mpg_ctx* ctx, int net, int rows, int64_t global_rows, const float
   for (int i = 0; i < MPG_MAX_OBS; ++i) a.obs_scale[i] = ctx->cfg.obs_scale[i];
   a.inv_global_rows = 1.f / (float)(global_rows > 0 ? global_rows : rows);
   a.obs = obs; a.act = act; a.target = target;
-  a.partial = ctx->partial; a.loss_partial = ctx->loss_partial;
+  a.partial = ctx->partial; a.loss_partial = ctx->loss_partial; a.partial_stride = (long long)ctx->partial_stride;
   a.q = net_dev(ctx, net);
   const int ntiles = (rows + TILE_R - 1) / TILE_R;
   const int grid = ntiles < ctx->sms ? ntiles : ctx->sms;
   const GradLayout L(a.q.in_dim, a.q.out_dim);
-  CUDA_OK(ctx, cudaMemsetAsync(ctx->partial, 0, (size_t)grid * L.total * sizeof(float), st));
+  CUDA_OK(ctx, cudaMemsetAsync(ctx->partial, 0, (size_t)grid * ctx->partial_stride * sizeof(float), st));
   q_grad_kernel<<<grid, NT, Smem::FLOATS * 4, st>>>(a);
-  reduce_partials_kernel<<<(L.total + 255) / 256, 256, 0, st>>>(ctx->partial, L.total, grid, L.total, grad_out,
-                                                                ctx->loss_partial, loss_sum_out);
+  reduce_partials_kernel<<<(L.total + 255) / 256, 256, 0, st>>>(ctx->partial, ctx->partial_stride, grid, L.total,
+                                                                grad_out, ctx->loss_partial, loss_sum_out);
   ctx->launches += 2;
   CUDA_OK(ctx, cudaGetLastError());
   return MPG_OK;

@@ -31,7 +31,8 @@ struct RolloutArgs {
   float* traj_rew;
   float* traj_act;
   float* ckpt;      // [horizon+1][M*rows][S]
-  float* partial;   // [grid][param_count(policy)]
+  float* partial;   // [grid][partial_stride]
+  long long partial_stride;   // floats, multiple of 4 (float4 accesses into the dW2 region)
   NetDev pol, q;
 };
 
@@ -58,7 +59,7 @@ __global__ void __launch_bounds__(NT, 1) rollout_kernel(const __grid_constant__ 
   const int ntiles = (MB + TILE_R - 1) / TILE_R;
   const bool rowthread = tid < TILE_R;
   const GradLayout L(a.pol.in_dim, a.pol.out_dim);
-  float* partial = a.partial + (size_t)blockIdx.x * L.total;
+  float* partial = a.partial + (size_t)blockIdx.x * a.partial_stride;
   GradAcc ga;
   ga.zero();
   const float cscale = -1.f / ((float)a.M * (float)a.global_rows);
@@ -233,7 +234,8 @@ struct QGradArgs {
   const float* obs;
   const float* act;
   const float* target;
-  float* partial;       // [grid][param_count(q)]
+  float* partial;       // [grid][partial_stride]
+  long long partial_stride;
   float* loss_partial;  // [grid]
   NetDev q;
 };
@@ -245,7 +247,7 @@ __global__ void __launch_bounds__(NT, 1) q_grad_kernel(const __grid_constant__ Q
   const int tid = threadIdx.x;
   const int ntiles = (a.rows + TILE_R - 1) / TILE_R;
   const GradLayout L(a.q.in_dim, a.q.out_dim);
-  float* partial = a.partial + (size_t)blockIdx.x * L.total;
+  float* partial = a.partial + (size_t)blockIdx.x * a.partial_stride;
   GradAcc ga;
   ga.zero();
   float loss = 0.f;

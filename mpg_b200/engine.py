@@ -109,6 +109,12 @@ class Engine:
             return True
         return False
 
+    def set_timing(self, enabled):
+        self._check(self.lib.mpg_set_timing(self.h, int(bool(enabled))))
+
+    def kernel_ms(self):
+        return float(self.lib.mpg_kernel_ms(self.h))
+
     @property
     def launch_count(self):
         return int(self.lib.mpg_launch_count(self.h))

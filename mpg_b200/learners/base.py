@@ -50,7 +50,7 @@ class LearnerBase(object):
         # tests install explicit eps tensors with set_rollout_noise
         self.noise_seed = int(getattr(self.args, 'noise_seed', 7))
         self._noise_q = self._noise_p = None
-        self._dev = {}
+        self._dev, self._pinned, self.h2d_bytes = {}, {}, 0
         # data parallel: each rank holds a contiguous shard of the global batch
         self.world_size, self.rank = 1, 0
         if torch.distributed.is_available() and torch.distributed.is_initialized():
@@ -82,7 +82,16 @@ class LearnerBase(object):
         # mpg_learner.py:66-72: cast to fp32; here additionally host -> device (pinned when possible)
         names = ('batch_obs', 'batch_actions', 'batch_rewards', 'batch_obs_tp1', 'batch_dones')
         self.batch_data = {k: np.asarray(v).astype(np.float32) for k, v in zip(names, batch_data)}
-        self._dev = {k: self.engine.dev(v) for k, v in self.batch_data.items() if k != 'batch_dones'}
+        self._dev = {}
+        for k, v in self.batch_data.items():
+            if k == 'batch_dones':  # ignored by every learner (mpg_learner.py:71)
+                continue
+            pin = self._pinned.get(k)
+            if pin is None or pin.shape != v.shape:
+                pin = self._pinned[k] = torch.empty(v.shape, dtype=torch.float32, pin_memory=True)
+            pin.numpy()[...] = v
+            self._dev[k] = pin.to(self.engine.device, non_blocking=True)
+        self.h2d_bytes = sum(t.numel() * 4 for t in self._dev.values())
 
     @property
     def global_rows(self):
