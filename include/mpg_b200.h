@@ -180,6 +180,10 @@ int mpg_get_backend(const mpg_ctx* ctx);
 int mpg_set_timing(mpg_ctx* ctx, int enabled);
 float mpg_kernel_ms(mpg_ctx* ctx);
 
+/* Self test of the tcgen05 GEMM building blocks (tests only). kind 0: Z[128x256] = X[128x256].W[256x256]^T;
+ * kind 1: Z[128x256] = X[128x16].W[16x256]; kind 2: Z[128x16] = X[128x256].W[16x256]^T. fp32 device pointers. */
+int mpg_tc_selftest(mpg_ctx* ctx, int kind, const float* X, const float* W, float* Z, int repeats, void* stream);
+
 /* counters for bench.py: kernels launched by this handle since creation */
 uint64_t mpg_launch_count(const mpg_ctx* ctx);
 

@@ -1,0 +1,302 @@
+// Warp-specialised GEMM machinery shared by the tensor-core rollout kernels.
+//
+// Roles inside one CTA (320 threads):
+//   warps 0-7  "epilogue": thread = (TMEM lane = row, 128-column half); they build the A-operand images in
+//              shared memory, read accumulators back with tcgen05.ld and run all per-row math;
+//   warp 8     "producer": one elected lane streams weight images from global/L2 into a 2-slot ring with
+//              1-D bulk async copies (TMA engine) completing on mbarriers;
+//   warp 9     "mma": one elected lane issues tcgen05.mma and commits to mbarriers.
+// The three roles execute the SAME schedule (same function, same CTA-uniform control flow) and meet only
+// through mbarriers:  a_full (epilogue -> mma: A image written), d_full (mma -> epilogue: accumulator
+// complete, A image and ring slots free), ring full[]/empty[] (producer <-> mma).
+#pragma once
+#include "tc_common.cuh"
+
+namespace mpg {
+namespace tc {
+
+constexpr int EPI_THREADS = 256;
+constexpr int CTA_THREADS = 320;
+constexpr int STAGE_BYTES = 32768;            // ring slot
+constexpr int NSLOT = 2;
+constexpr int TMEM_COLS = 512;
+constexpr int TM_Z1 = 0, TM_WORK = 256;       // TMEM column regions
+
+// shared memory map (bytes, 1024-aligned base)
+struct SmemMap {
+  static constexpr int ACT = 0;                               // activation image hi|lo: 128 KB
+  static constexpr int RING = ACT + 2 * ACT_SPLIT;            // 2 x 32 KB
+  static constexpr int PIMG = RING + NSLOT * STAGE_BYTES;     // [p|a|1] image hi|lo: 2 x 4 KB
+  static constexpr int MISC = PIMG + 8192;                    // fp32 scratch, see MiscF
+  static constexpr int MISC_BYTES = 12288;
+  static constexpr int BARS = MISC + MISC_BYTES;              // mbarriers + tmem pointer
+  static constexpr int TOTAL = BARS + 128;
+};
+
+struct Bars {
+  uint64_t full[NSLOT];
+  uint64_t empty[NSLOT];
+  uint64_t a_full;
+  uint64_t d_full;
+  uint32_t tmem_base;
+};
+
+// per-role running counters (phase tracking)
+struct Sync {
+  uint32_t stage = 0;    // ring stages produced / consumed so far
+  uint32_t a_cnt = 0;    // a_full phases seen
+  uint32_t d_cnt = 0;    // d_full phases seen
+};
+
+enum Role { ROLE_EPI = 0, ROLE_PRODUCER = 1, ROLE_MMA = 2 };
+
+// ---- producer: stream `nstages` stages of `bytes` each ------------------------------------------------
+__device__ __forceinline__ void produce(Bars* b, uint8_t* ring, Sync& s, const uint8_t* gsrc, int nstages, uint32_t bytes) {
+  for (int i = 0; i < nstages; ++i, ++s.stage) {
+    const uint32_t slot = s.stage & 1, par = (s.stage >> 1) & 1;
+    mbar_wait(&b->empty[slot], par ^ 1);
+    mbar_expect_tx(&b->full[slot], bytes);
+    bulk_g2s(ring + slot * STAGE_BYTES, gsrc + (size_t)i * bytes, bytes, &b->full[slot]);
+  }
+}
+
+// ---- mma role ----------------------------------------------------------------------------------------
+// big GEMM: D[128 x 256] = ACT[128 x 256] . Wt^T, Wt image streamed as 8 stages (n-half h, k-block kb):
+// stage = [hi: 128 rows x 128 B][lo: 128 rows x 128 B]
+__device__ __forceinline__ void mma_big(Bars* b, uint32_t act_addr, uint32_t ring_addr, Sync& s, uint32_t d_tmem) {
+  constexpr uint32_t idesc = make_idesc(128, 128, 0, 0);
+  for (int h = 0; h < 2; ++h)
+    for (int kb = 0; kb < 4; ++kb, ++s.stage) {
+      const uint32_t slot = s.stage & 1, par = (s.stage >> 1) & 1;
+      mbar_wait(&b->full[slot], par);
+      tc_fence_after();
+      const uint32_t bbase = ring_addr + slot * STAGE_BYTES;
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        const uint32_t a_hi = act_addr + kb * ACT_BLOCK + ks * 32, a_lo = a_hi + ACT_SPLIT;
+        const uint32_t b_hi = bbase + ks * 32, b_lo = b_hi + 16384;
+        const uint64_t dah = make_desc(a_hi, 16, 1024, LAYOUT_SW128), dal = make_desc(a_lo, 16, 1024, LAYOUT_SW128);
+        const uint64_t dbh = make_desc(b_hi, 16, 1024, LAYOUT_SW128), dbl = make_desc(b_lo, 16, 1024, LAYOUT_SW128);
+        const uint32_t d = d_tmem + h * 128;
+        umma_bf16(d, dah, dbh, idesc, (kb | ks) ? 1u : 0u);
+        umma_bf16(d, dal, dbh, idesc, 1u);
+        umma_bf16(d, dah, dbl, idesc, 1u);
+      }
+      umma_commit(&b->empty[slot]);
+    }
+}
+// first-layer GEMM: D[128 x 256] = P[128 x 16] . W1aug^T ; P is the INTERLEAVE image in shared memory,
+// W1aug image streamed as ONE stage = [hi: 256 rows x 32 B][lo: 256 rows x 32 B] = 16 KB
+__device__ __forceinline__ void mma_l1(Bars* b, uint32_t p_addr, uint32_t ring_addr, Sync& s, uint32_t d_tmem) {
+  constexpr uint32_t idesc = make_idesc(128, 256, 0, 0);
+  const uint32_t slot = s.stage & 1, par = (s.stage >> 1) & 1;
+  mbar_wait(&b->full[slot], par);
+  tc_fence_after();
+  const uint32_t bbase = ring_addr + slot * STAGE_BYTES;
+  const uint64_t dah = make_desc(p_addr, 128, 256, LAYOUT_NONE), dal = make_desc(p_addr + 4096, 128, 256, LAYOUT_NONE);
+  const uint64_t dbh = make_desc(bbase, 128, 256, LAYOUT_NONE), dbl = make_desc(bbase + 8192, 128, 256, LAYOUT_NONE);
+  umma_bf16(d_tmem, dah, dbh, idesc, 0u);
+  umma_bf16(d_tmem, dal, dbh, idesc, 1u);
+  umma_bf16(d_tmem, dah, dbl, idesc, 1u);
+  umma_commit(&b->empty[slot]);
+  ++s.stage;
+}
+// input-gradient GEMM: D[128 x 16] = ACT[128 x 256] . W1nat^T (W1nat: 16 rows x 256), image streamed as ONE
+// stage = [hi: 4 k-blocks x (16 rows x 128 B)][lo: same] = 16 KB
+__device__ __forceinline__ void mma_in(Bars* b, uint32_t act_addr, uint32_t ring_addr, Sync& s, uint32_t d_tmem) {
+  constexpr uint32_t idesc = make_idesc(128, 16, 0, 0);
+  const uint32_t slot = s.stage & 1, par = (s.stage >> 1) & 1;
+  mbar_wait(&b->full[slot], par);
+  tc_fence_after();
+  const uint32_t bbase = ring_addr + slot * STAGE_BYTES;
+  for (int kb = 0; kb < 4; ++kb)
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      const uint32_t a_hi = act_addr + kb * ACT_BLOCK + ks * 32, a_lo = a_hi + ACT_SPLIT;
+      const uint32_t b_hi = bbase + kb * 2048 + ks * 32, b_lo = b_hi + 8192;
+      const uint64_t dah = make_desc(a_hi, 16, 1024, LAYOUT_SW128), dal = make_desc(a_lo, 16, 1024, LAYOUT_SW128);
+      const uint64_t dbh = make_desc(b_hi, 16, 1024, LAYOUT_SW128), dbl = make_desc(b_lo, 16, 1024, LAYOUT_SW128);
+      umma_bf16(d_tmem, dah, dbh, idesc, (kb | ks) ? 1u : 0u);
+      umma_bf16(d_tmem, dal, dbh, idesc, 1u);
+      umma_bf16(d_tmem, dah, dbl, idesc, 1u);
+    }
+  umma_commit(&b->empty[slot]);
+  ++s.stage;
+}
+
+// ---- handshakes ----------------------------------------------------------------------------------------
+// epilogue side: A image (and any TMEM reads) done -> let the mma role go
+__device__ __forceinline__ void epi_publish_a(Bars* b) {
+  tc_fence_before();
+  fence_proxy_async();
+  mbar_arrive(&b->a_full);
+}
+__device__ __forceinline__ void mma_wait_a(Bars* b, Sync& s) {
+  mbar_wait(&b->a_full, s.a_cnt & 1);
+  ++s.a_cnt;
+  tc_fence_after();
+}
+__device__ __forceinline__ void mma_publish_d(Bars* b) { umma_commit(&b->d_full); }
+__device__ __forceinline__ void epi_wait_d(Bars* b, Sync& s) {
+  mbar_wait(&b->d_full, s.d_cnt & 1);
+  ++s.d_cnt;
+  tc_fence_after();
+}
+
+// One GEMM as seen by each role. kind: 0 big, 1 first layer, 2 input gradient.
+template <int ROLE>
+__device__ __forceinline__ void gemm(int kind, Bars* b, uint8_t* smem, Sync& s, const uint8_t* gimg, uint32_t d_tmem) {
+  if (ROLE == ROLE_PRODUCER) {
+    if (kind == 0) produce(b, smem + SmemMap::RING, s, gimg, 8, STAGE_BYTES);
+    else produce(b, smem + SmemMap::RING, s, gimg, 1, 16384);
+  } else if (ROLE == ROLE_MMA) {
+    mma_wait_a(b, s);
+    const uint32_t base = smem_u32(smem);
+    if (kind == 0) mma_big(b, base + SmemMap::ACT, base + SmemMap::RING, s, d_tmem);
+    else if (kind == 1) mma_l1(b, base + SmemMap::PIMG, base + SmemMap::RING, s, d_tmem);
+    else mma_in(b, base + SmemMap::ACT, base + SmemMap::RING, s, d_tmem);
+    mma_publish_d(b);
+  } else {
+    epi_publish_a(b);
+    epi_wait_d(b, s);
+  }
+}
+
+// ---- CTA prologue / epilogue -----------------------------------------------------------------------------
+__device__ __forceinline__ Bars* cta_setup(uint8_t* smem) {
+  Bars* b = reinterpret_cast<Bars*>(smem + SmemMap::BARS);
+  const int warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NSLOT; ++i) { mbar_init(&b->full[i], 1); mbar_init(&b->empty[i], 1); }
+    mbar_init(&b->a_full, EPI_THREADS);
+    mbar_init(&b->d_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 9) tmem_alloc(&b->tmem_base, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  return b;
+}
+__device__ __forceinline__ void cta_teardown(Bars* b) {
+  tc_fence_before();
+  __syncthreads();
+  if ((threadIdx.x >> 5) == 9) tmem_dealloc(b->tmem_base, TMEM_COLS);
+}
+
+// ---- global weight-image packing (run once per set_weights) ------------------------------------------------
+// big image: value(row, k) = src[row * rs + k * cs], 256 rows x 256 k -> 8 stages (h, kb) of [hi 16 KB | lo 16 KB]
+__global__ void pack_big_image(const float* __restrict__ src, int rs, int cs, uint8_t* __restrict__ img) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;   // one thread per (row, 8-element chunk): 256 x 32
+  if (idx >= 256 * 32) return;
+  const int row = idx >> 5, cc = idx & 31;
+  float x[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) x[e] = src[(size_t)row * rs + (size_t)(cc * 8 + e) * cs];
+  uint4 h, l;
+  split2(x[0], x[1], h.x, l.x); split2(x[2], x[3], h.y, l.y); split2(x[4], x[5], h.z, l.z); split2(x[6], x[7], h.w, l.w);
+  const int hh = row >> 7, rr = row & 127, kb = cc >> 3, c = cc & 7;
+  const size_t stage = (size_t)(hh * 4 + kb) * STAGE_BYTES;
+  const uint32_t off = (rr >> 3) * 1024 + (rr & 7) * 128 + ((c ^ (rr & 7)) << 4);
+  *reinterpret_cast<uint4*>(img + stage + off) = h;
+  *reinterpret_cast<uint4*>(img + stage + 16384 + off) = l;
+}
+// first-layer image: value(n, k) = k < in_dim ? W1[k][n] : (k == bias_k ? b1[n] : 0); 256 rows x 16 k,
+// INTERLEAVE K-major: [hi 8 KB | lo 8 KB]
+__global__ void pack_l1_image(const float* __restrict__ W1, const float* __restrict__ b1, int in_dim, int bias_k,
+                              uint8_t* __restrict__ img) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;   // (n, k-half): 256 x 2
+  if (idx >= 512) return;
+  const int n = idx >> 1, kh = idx & 1;
+  float x[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int k = kh * 8 + e;
+    x[e] = k < in_dim ? W1[(size_t)k * H + n] : (k == bias_k ? b1[n] : 0.f);
+  }
+  uint4 h, l;
+  split2(x[0], x[1], h.x, l.x); split2(x[2], x[3], h.y, l.y); split2(x[4], x[5], h.z, l.z); split2(x[6], x[7], h.w, l.w);
+  const uint32_t off = il_chunk_off(n, kh);
+  *reinterpret_cast<uint4*>(img + off) = h;
+  *reinterpret_cast<uint4*>(img + 8192 + off) = l;
+}
+// input-gradient image: value(i, n) = i < in_dim ? W1[i][n] : 0; 16 rows x 256 k, SW128 K-major per 64-k block:
+// [hi: 4 x 2 KB | lo: 4 x 2 KB]
+__global__ void pack_in_image(const float* __restrict__ W1, int in_dim, uint8_t* __restrict__ img) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;   // (i, chunk): 16 x 32
+  if (idx >= 512) return;
+  const int i = idx >> 5, cc = idx & 31;
+  float x[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) x[e] = i < in_dim ? W1[(size_t)i * H + cc * 8 + e] : 0.f;
+  uint4 h, l;
+  split2(x[0], x[1], h.x, l.x); split2(x[2], x[3], h.y, l.y); split2(x[4], x[5], h.z, l.z); split2(x[6], x[7], h.w, l.w);
+  const int kb = cc >> 3, c = cc & 7;
+  const uint32_t off = kb * 2048 + (i >> 3) * 1024 + (i & 7) * 128 + ((c ^ (i & 7)) << 4);
+  *reinterpret_cast<uint4*>(img + off) = h;
+  *reinterpret_cast<uint4*>(img + 8192 + off) = l;
+}
+
+// ---- self test: the three GEMM kinds against caller-provided fp32 data ---------------------------------------
+//   kind 0: Z[128 x 256] = X[128 x 256] . (image of Wt[256 x 256])^T
+//   kind 1: Z[128 x 256] = X16[128 x 16] . (first-layer image)^T
+//   kind 2: Z[128 x 16]  = X[128 x 256] . (input-gradient image)^T
+__global__ void __launch_bounds__(CTA_THREADS, 1) selftest_kernel(int kind, const float* __restrict__ X,
+                                                                 const uint8_t* __restrict__ img, float* __restrict__ Z,
+                                                                 int repeats) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // SW128 needs 1024-byte alignment
+  Bars* b = cta_setup(smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t tmem = b->tmem_base;
+  Sync s;
+  if (warp < 8) {
+    const int row = (warp & 3) * 32 + lane, hc = warp >> 2;
+    for (int rep = 0; rep < repeats; ++rep) {
+      if (kind == 1) {
+        if (hc == 0) {
+          for (int kh = 0; kh < 2; ++kh) {
+            float x[8];
+            for (int e = 0; e < 8; ++e) x[e] = X[row * 16 + kh * 8 + e];
+            uint4 h, l;
+            split2(x[0], x[1], h.x, l.x); split2(x[2], x[3], h.y, l.y); split2(x[4], x[5], h.z, l.z); split2(x[6], x[7], h.w, l.w);
+            *reinterpret_cast<uint4*>(smem + SmemMap::PIMG + il_chunk_off(row, kh)) = h;
+            *reinterpret_cast<uint4*>(smem + SmemMap::PIMG + 4096 + il_chunk_off(row, kh)) = l;
+          }
+        }
+      } else {
+        for (int cc = hc * 16; cc < hc * 16 + 16; ++cc) {
+          float x[8];
+          for (int e = 0; e < 8; ++e) x[e] = X[row * 256 + cc * 8 + e];
+          act_store8(smem + SmemMap::ACT, smem + SmemMap::ACT + ACT_SPLIT, row, cc, x);
+        }
+      }
+      gemm<ROLE_EPI>(kind, b, smem, s, img, tmem + TM_WORK);
+      const uint32_t lane_base = tmem + TM_WORK + ((uint32_t)((warp & 3) * 32) << 16);
+      if (kind == 2) {
+        if (hc == 0) {
+          float v[16];
+          tmem_ld16(lane_base, v);
+          for (int j = 0; j < 16; ++j) Z[row * 16 + j] = v[j];
+        }
+      } else {
+        for (int c0 = hc * 128; c0 < hc * 128 + 128; c0 += 32) {
+          float v[32];
+          tmem_ld32(lane_base + c0, v);
+          for (int j = 0; j < 32; ++j) Z[row * 256 + c0 + j] = v[j];
+        }
+      }
+    }
+    tc_fence_before();
+  } else if (warp == 8) {
+    if (lane == 0)
+      for (int rep = 0; rep < repeats; ++rep) gemm<ROLE_PRODUCER>(kind, b, smem, s, img, 0);
+  } else {
+    if (lane == 0)
+      for (int rep = 0; rep < repeats; ++rep) gemm<ROLE_MMA>(kind, b, smem, s, img, tmem + TM_WORK);
+  }
+  cta_teardown(b);
+}
+
+}  // namespace tc
+}  // namespace mpg

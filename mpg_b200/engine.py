@@ -109,6 +109,11 @@ class Engine:
             return True
         return False
 
+    def tc_selftest(self, kind, X, W, repeats=1):
+        Z = self.empty(128, 16 if kind == 2 else 256)
+        self._check(self.lib.mpg_tc_selftest(self.h, kind, _ptr(X), _ptr(W), _ptr(Z), repeats, self.stream))
+        return Z
+
     def set_timing(self, enabled):
         self._check(self.lib.mpg_set_timing(self.h, int(bool(enabled))))
 
