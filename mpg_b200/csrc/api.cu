@@ -374,9 +374,39 @@ int mpg_policy_grad(mpg_ctx* ctx, const mpg_rollout_params* p, const float* obs,
   a.obs = obs; a.noise = noise; a.returns_out = returns_out;
   a.noise_mode = noise ? 1 : (p->use_philox ? 2 : 0);
   const int MB = p->rows * p->M;
+  const GradLayout L(a.pol.in_dim, a.pol.out_dim);
+  if (ctx->backend == MPG_BACKEND_TC) {
+    // tensor-core path: fused rollout + BPTT (dX chain), then the split-K weight-gradient GEMMs
+    const int ntiles = (MB + tc::ACT_ROWS - 1) / tc::ACT_ROWS;
+    const int grid = ntiles < ctx->sms ? ntiles : ctx->sms;
+    tc::TcArgs ta;
+    memset(&ta, 0, sizeof(ta));
+    ta.r = a;
+    ta.pol = tc_net(ctx->tc, p->policy_net, ctx->nets[p->policy_net].flat, a.pol.in_dim, a.pol.out_dim);
+    if (a.has_q) ta.q = tc_net(ctx->tc, p->q_net, ctx->nets[p->q_net].flat, a.q.in_dim, a.q.out_dim);
+    ta.act_ckpt = ctx->tc.act_ckpt;
+    ta.store_steps = p->full_bptt ? p->horizon + 1 : 1;
+    const size_t need = (size_t)ntiles * ta.store_steps * tc::SLOT_BYTES;
+    if (!tc_ensure_store(ctx->tc, need)) return fail(ctx, MPG_ERR_CUDA, "cudaMalloc of the dW operand store failed%s");
+    ta.store = ctx->tc.store;
+    CUDA_OK(ctx, cudaMemsetAsync(ctx->partial, 0, (size_t)ctx->sms * ctx->partial_stride * sizeof(float), st));
+    if (ctx->timing) cudaEventRecord(ctx->ev0, st);
+    CUDA_OK(ctx, tc_launch_rollout<true>(ctx->cfg.env, ta, grid, st));
+    if (ctx->timing) { cudaEventRecord(ctx->ev1, st); ctx->timed = 1; }
+    tc::DwArgs da;
+    da.store = ctx->tc.store; da.nrecords = ntiles * ta.store_steps; da.has_h2 = 1;
+    da.in_dim = a.pol.in_dim; da.out_dim = a.pol.out_dim; da.act_dim = ctx->cfg.act_dim;
+    da.partial = ctx->partial; da.partial_stride = (long long)ctx->partial_stride;
+    int dgrid = 2 * da.nrecords < ctx->sms ? 2 * da.nrecords : (ctx->sms & ~1);
+    tc::tc_dw_kernel<<<dgrid, 192, 2 * tc::DW_STAGE + 128 + 1024, st>>>(da);
+    reduce_partials_kernel<<<(L.total + 255) / 256, 256, 0, st>>>(ctx->partial, ctx->partial_stride, ctx->sms, L.total,
+                                                                  grad_out, nullptr, nullptr);
+    ctx->launches += 3;
+    CUDA_OK(ctx, cudaGetLastError());
+    return MPG_OK;
+  }
   const int ntiles = (MB + TILE_R - 1) / TILE_R;
   const int grid = ntiles < ctx->sms ? ntiles : ctx->sms;
-  const GradLayout L(a.pol.in_dim, a.pol.out_dim);
   CUDA_OK(ctx, cudaMemsetAsync(ctx->partial, 0, (size_t)grid * ctx->partial_stride * sizeof(float), st));
   rc = launch_rollout<true>(ctx, a, grid, st);
   if (rc) return rc;
@@ -400,6 +430,21 @@ int mpg_rollout_forward(mpg_ctx* ctx, const mpg_rollout_params* p, const float* 
   a.traj_obs = traj_obs; a.traj_rew = traj_rew; a.traj_act = traj_act;
   a.noise_mode = noise ? 1 : (p->use_philox ? 2 : 0);
   const int MB = p->rows * p->M;
+  if (ctx->backend == MPG_BACKEND_TC) {
+    const int ntiles = (MB + tc::ACT_ROWS - 1) / tc::ACT_ROWS;
+    const int grid = ntiles < ctx->sms ? ntiles : ctx->sms;
+    tc::TcArgs ta;
+    memset(&ta, 0, sizeof(ta));
+    ta.r = a;
+    ta.pol = tc_net(ctx->tc, p->policy_net, ctx->nets[p->policy_net].flat, a.pol.in_dim, a.pol.out_dim);
+    if (a.has_q) ta.q = tc_net(ctx->tc, p->q_net, ctx->nets[p->q_net].flat, a.q.in_dim, a.q.out_dim);
+    ta.act_ckpt = ctx->tc.act_ckpt;
+    if (ctx->timing) cudaEventRecord(ctx->ev0, st);
+    CUDA_OK(ctx, tc_launch_rollout<false>(ctx->cfg.env, ta, grid, st));
+    if (ctx->timing) { cudaEventRecord(ctx->ev1, st); ctx->timed = 1; }
+    ctx->launches++;
+    return MPG_OK;
+  }
   const int ntiles = (MB + TILE_R - 1) / TILE_R;
   const int grid = ntiles < ctx->sms ? ntiles : ctx->sms;
   return launch_rollout<false>(ctx, a, grid, st);

@@ -1,0 +1,610 @@
+// Tensor-core (tcgen05) model-rollout kernels.
+//
+// tc_rollout_kernel<ENV,BWD>: one persistent CTA per SM owns a tile of 128 trajectories and walks the
+// horizon.  All 256x256 (and 16x256 / 256x16) contractions of the policy / Q MLPs run on the 5th-gen
+// tensor cores with split-bf16 operands (3 products, fp32 accumulation in TMEM); weights are streamed from
+// L2 through a shared-memory ring by the TMA engine; the per-row vehicle / pendulum dynamics, rewards,
+// output heads and adjoints stay in registers of the thread that owns the row (TMEM lane = row).
+// Backward = BPTT with recompute from the 24-byte state checkpoints.  The dX chain (what the recurrence
+// needs) is fully fused.  The weight-gradient contractions (K = rows) cannot be accumulated in place: the
+// fp32 accumulator of dW2 alone is 256 KB = all of TMEM.  Their operand tiles (h1, h2, delta1, delta2 as
+// split-bf16 images, written to shared memory anyway as UMMA operands) are bulk-stored once and consumed
+// by tc_dw_kernel, a split-K tcgen05 GEMM with MN-major operands.
+#pragma once
+#include "env_models.cuh"
+#include "rollout_kernels.cuh"
+#include "tc_gemm.cuh"
+
+namespace mpg {
+namespace tc {
+
+struct TcNet {
+  const uint8_t* big_fwd;
+  const uint8_t* big_dx;
+  const uint8_t* l1;
+  const uint8_t* in;
+  const float* W3;   // [H][out_dim] natural
+  const float* b2;
+  const float* b3;
+  int in_dim, out_dim;
+};
+
+constexpr int BIAS_K = 15;                    // column of the [p|a|1] image that carries the constant 1
+constexpr size_t SLOT_H1 = 0, SLOT_H2 = 131072, SLOT_D1 = 262144, SLOT_D2 = 393216, SLOT_P = 524288, SLOT_D3 = 532480;
+constexpr size_t SLOT_BYTES = 540672;         // one (tile, step) record of the dW operand store
+
+struct TcArgs {
+  RolloutArgs r;            // config, lists, pointers (r.pol / r.q unused here)
+  TcNet pol, q;
+  float* act_ckpt;          // [n_list][M*rows][A] actions at the list steps (for the Q input gradient)
+  uint8_t* store;           // dW operand store: [tile][step][SLOT_BYTES]
+  int store_steps;          // steps recorded per tile: horizon+1 (full BPTT) or 1 (first action only)
+};
+
+// fp32 scratch in shared memory
+struct MiscF {
+  float W3p[H * 2];
+  float b2p[H];
+  float W3q[H * 2];
+  float b2q[H];
+  float part[2 * 2 * ACT_ROWS];   // [hc][j][row]
+  float d3s[2 * ACT_ROWS];        // [j][row]
+  float wsum[8];                  // per-warp delta3 sums [warp][j]
+  float b3[4];                    // b3p[0], b3p[1], b3q[0]
+};
+static_assert(sizeof(MiscF) <= SmemMap::MISC_BYTES, "MISC region too small");
+
+constexpr int SM_D3IMG = SmemMap::TOTAL;          // delta3 image hi|lo (8 KB) appended after the base map
+constexpr int SM_TOTAL = SM_D3IMG + 8192;
+
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ float elu_fast(float x) { return x > 0.f ? x : __expf(x) - 1.f; }
+
+// z1 (TMEM, bias folded in) -> h1 image
+__device__ __forceinline__ void epi_hidden1(uint32_t tm_lane, uint8_t* act, int row, int hc) {
+  for (int c0 = hc * 128; c0 < hc * 128 + 128; c0 += 32) {
+    float v[32];
+    tmem_ld32(tm_lane + c0, v);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = elu_fast(v[i]);
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) act_store8(act, act + ACT_SPLIT, row, (c0 >> 3) + cc, v + 8 * cc);
+  }
+}
+// z2 (TMEM) + b2 -> h2 -> partial output-layer dot products; optionally also the h2 image
+template <bool STORE_IMG>
+__device__ __forceinline__ void epi_hidden2(uint32_t tm_lane, const float* b2, const float* W3, uint8_t* act, int row,
+                                            int hc, float& p0, float& p1) {
+  p0 = 0.f; p1 = 0.f;
+  for (int c0 = hc * 128; c0 < hc * 128 + 128; c0 += 32) {
+    float v[32];
+    tmem_ld32(tm_lane + c0, v);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      v[i] = elu_fast(v[i] + b2[c0 + i]);
+      const float2 w = *reinterpret_cast<const float2*>(W3 + 2 * (c0 + i));
+      p0 = fmaf(v[i], w.x, p0);
+      p1 = fmaf(v[i], w.y, p1);
+    }
+    if (STORE_IMG) {
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) act_store8(act, act + ACT_SPLIT, row, (c0 >> 3) + cc, v + 8 * cc);
+    }
+  }
+}
+// delta2 = (delta3 W3^T) * elu'(h2), h2 re-derived from z2 (TMEM) -> delta2 image
+__device__ __forceinline__ void epi_delta2(uint32_t tm_lane, const float* b2, const float* W3, float d30, float d31,
+                                           uint8_t* act, int row, int hc) {
+  for (int c0 = hc * 128; c0 < hc * 128 + 128; c0 += 32) {
+    float v[32];
+    tmem_ld32(tm_lane + c0, v);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const float z = v[i] + b2[c0 + i];
+      const float2 w = *reinterpret_cast<const float2*>(W3 + 2 * (c0 + i));
+      const float g = fmaf(d30, w.x, d31 * w.y);
+      v[i] = g * (z > 0.f ? 1.f : __expf(z));     // elu'(z) = 1 | exp(z)
+    }
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) act_store8(act, act + ACT_SPLIT, row, (c0 >> 3) + cc, v + 8 * cc);
+  }
+}
+// delta1 = g_h1 (TMEM work) * elu'(z1) (TMEM z1) -> delta1 image
+__device__ __forceinline__ void epi_delta1(uint32_t tm_work, uint32_t tm_z1, uint8_t* act, int row, int hc) {
+  for (int c0 = hc * 128; c0 < hc * 128 + 128; c0 += 16) {
+    float g[16], z[16];
+    tmem_ld16(tm_work + c0, g);
+    tmem_ld16(tm_z1 + c0, z);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) g[i] *= (z[i] > 0.f ? 1.f : __expf(z[i]));
+    act_store8(act, act + ACT_SPLIT, row, (c0 >> 3), g);
+    act_store8(act, act + ACT_SPLIT, row, (c0 >> 3) + 1, g + 8);
+  }
+}
+// [x0..x15] -> INTERLEAVE image row (hi | lo 4 KB apart)
+__device__ __forceinline__ void write_row16(uint8_t* img, int row, const float* x) {
+#pragma unroll
+  for (int kh = 0; kh < 2; ++kh) {
+    uint4 h, l;
+    split2(x[kh * 8 + 0], x[kh * 8 + 1], h.x, l.x);
+    split2(x[kh * 8 + 2], x[kh * 8 + 3], h.y, l.y);
+    split2(x[kh * 8 + 4], x[kh * 8 + 5], h.z, l.z);
+    split2(x[kh * 8 + 6], x[kh * 8 + 7], h.w, l.w);
+    *reinterpret_cast<uint4*>(img + il_chunk_off(row, kh)) = h;
+    *reinterpret_cast<uint4*>(img + 4096 + il_chunk_off(row, kh)) = l;
+  }
+}
+
+// whole-image bulk store to the dW operand store (one elected epilogue thread); the matching wait must come
+// before the shared-memory source is overwritten
+__device__ __forceinline__ void store_image(bool elected, uint8_t* gdst, const uint8_t* ssrc, uint32_t bytes) {
+  fence_proxy_async();
+  epi_bar();
+  if (elected) {
+    bulk_s2g(gdst, ssrc, bytes);
+    bulk_commit();
+  }
+}
+__device__ __forceinline__ void store_wait(bool elected) {
+  if (elected) bulk_wait_read_all();
+  epi_bar();
+}
+
+template <int ENV, bool BWD, int ROLE>
+__device__ __forceinline__ void run_rollout(const TcArgs& A, uint8_t* smem, Bars* b) {
+  using E = Env<ENV>;
+  constexpr int S = E::S, NA = E::A;
+  const RolloutArgs& a = A.r;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int row = (warp & 3) * 32 + lane, hc = (warp >> 2) & 1;
+  const bool rowthread = (ROLE == ROLE_EPI) && hc == 0;
+  const bool elected = (ROLE == ROLE_EPI) && tid == 0;
+  const int MB = a.rows * a.M;
+  const int ntiles = (MB + ACT_ROWS - 1) / ACT_ROWS;
+  MiscF* mf = reinterpret_cast<MiscF*>(smem + SmemMap::MISC);
+  uint8_t* act_img = smem + SmemMap::ACT;
+  uint8_t* p_img = smem + SmemMap::PIMG;
+  uint8_t* d3_img = smem + SM_D3IMG;
+  const uint32_t tmem = b->tmem_base;
+  const uint32_t tm_z1 = tmem + TM_Z1, tm_work = tmem + TM_WORK;
+  const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
+  const float cscale = -1.f / ((float)a.M * (float)a.global_rows);
+  const bool store_dw = BWD && A.store != nullptr;
+  Sync sy;
+  float db3acc[2] = {0.f, 0.f};
+
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int grow = tile * ACT_ROWS + row;
+    const bool valid = rowthread && grow < MB;
+    const int m_idx = valid ? grow / a.rows : 0, i_idx = valid ? grow % a.rows : 0;
+    const unsigned long long noise_row = (unsigned long long)m_idx * (unsigned long long)a.global_rows
+                                         + (unsigned long long)(a.row_offset + i_idx);
+    float s[S];
+#pragma unroll
+    for (int j = 0; j < S; ++j) s[j] = 0.f;
+    if (valid) {
+      float o[MPG_MAX_OBS];
+      for (int i = 0; i < a.obs_dim; ++i) o[i] = a.obs[(size_t)i_idx * a.obs_dim + i];
+      E::reset(o, s);
+    }
+    float rsum = 0.f, gpow = 1.f;
+
+    // [sigma*obs(s) | act | 0.. | 1] -> p image
+    auto write_pimg = [&](const float* st, const float* act_or_null) {
+      float x[16], o[MPG_MAX_OBS];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) x[i] = 0.f;
+      E::get_obs(st, o, a.nfd);
+      for (int i = 0; i < a.obs_dim; ++i) x[i] = o[i] * a.obs_scale[i];
+      if (act_or_null)
+        for (int j = 0; j < NA; ++j) x[a.obs_dim + j] = act_or_null[j];
+      x[BIAS_K] = 1.f;
+      write_row16(p_img, row, x);
+    };
+    // policy forward on the current p image: returns pre-activations of the head for the row thread
+    auto policy_forward = [&](float* zpre, bool store_h1, bool store_h2, uint8_t* slot) {
+      gemm<ROLE>(1, b, smem, sy, A.pol.l1, tm_z1);
+      if (ROLE == ROLE_EPI) {
+        epi_hidden1(tm_z1 + lane_off, act_img, row, hc);
+        if (store_h1) store_image(elected, slot + SLOT_H1, act_img, 2 * ACT_SPLIT);
+      }
+      gemm<ROLE>(0, b, smem, sy, A.pol.big_fwd, tm_work);
+      if (ROLE == ROLE_EPI) {
+        float p0, p1;
+        if (store_h2) {
+          store_wait(elected);   // h1 image has been read out (and the MMA that used it has completed)
+          epi_hidden2<true>(tm_work + lane_off, mf->b2p, mf->W3p, act_img, row, hc, p0, p1);
+          store_image(elected, slot + SLOT_H2, act_img, 2 * ACT_SPLIT);
+        } else {
+          epi_hidden2<false>(tm_work + lane_off, mf->b2p, mf->W3p, act_img, row, hc, p0, p1);
+        }
+        mf->part[(hc * 2 + 0) * ACT_ROWS + row] = p0;
+        mf->part[(hc * 2 + 1) * ACT_ROWS + row] = p1;
+        epi_bar();
+        if (rowthread) {
+#pragma unroll
+          for (int j = 0; j < NA; ++j)
+            zpre[j] = mf->b3[j] + mf->part[(0 * 2 + j) * ACT_ROWS + row] + mf->part[(1 * 2 + j) * ACT_ROWS + row];
+        }
+      }
+    };
+    // Q forward on the current [p|a|1] image: returns Q for the row thread
+    auto q_forward = [&]() -> float {
+      float qv = 0.f;
+      gemm<ROLE>(1, b, smem, sy, A.q.l1, tm_z1);
+      if (ROLE == ROLE_EPI) epi_hidden1(tm_z1 + lane_off, act_img, row, hc);
+      gemm<ROLE>(0, b, smem, sy, A.q.big_fwd, tm_work);
+      if (ROLE == ROLE_EPI) {
+        float p0, p1;
+        epi_hidden2<false>(tm_work + lane_off, mf->b2q, mf->W3q, act_img, row, hc, p0, p1);
+        mf->part[(hc * 2 + 0) * ACT_ROWS + row] = p0;
+        epi_bar();
+        if (rowthread) qv = mf->b3[2] + mf->part[0 * ACT_ROWS + row] + mf->part[2 * ACT_ROWS + row];
+      }
+      return qv;
+    };
+
+    // =========================================== forward ===========================================
+    for (int t = 0; t <= a.horizon; ++t) {
+      float act[NA];
+#pragma unroll
+      for (int j = 0; j < NA; ++j) act[j] = 0.f;
+      const bool given = (t == 0 && a.use_start_actions);
+      if (rowthread) {
+        if (BWD && valid) {
+          float* c = a.ckpt + ((size_t)t * MB + grow) * S;
+#pragma unroll
+          for (int j = 0; j < S; ++j) c[j] = s[j];
+        }
+        if (!given) write_pimg(s, nullptr);
+      }
+      if (!given) {
+        float zpre[NA];
+        policy_forward(zpre, false, false, nullptr);
+        if (rowthread)
+#pragma unroll
+          for (int j = 0; j < NA; ++j) act[j] = head_fwd(zpre[j], a.policy_out_tanh, a.action_range);
+      } else if (rowthread && valid) {
+#pragma unroll
+        for (int j = 0; j < NA; ++j) act[j] = a.start_actions[(size_t)i_idx * NA + j];
+      }
+      if (rowthread && valid && a.traj_act)
+#pragma unroll
+        for (int j = 0; j < NA; ++j) a.traj_act[((size_t)t * MB + grow) * NA + j] = act[j];
+      int kidx = -1;
+      for (int k = 0; k < a.n_list; ++k) if (a.list[k] == t) kidx = k;
+      if (kidx >= 0) {
+        float qv = 0.f;
+        if (BWD && rowthread && valid)
+#pragma unroll
+          for (int j = 0; j < NA; ++j) A.act_ckpt[((size_t)kidx * MB + grow) * NA + j] = act[j];
+        if (a.has_q) {
+          if (rowthread) write_pimg(s, act);
+          qv = q_forward();
+        }
+        if (valid && a.returns_out) a.returns_out[(size_t)kidx * MB + grow] = rsum + gpow * qv;
+      }
+      if (t < a.horizon && valid) {
+        float eps = 0.f;
+        if (E::HAS_NOISE) {
+          if (a.noise_mode == 1) eps = a.noise[(size_t)t * MB + grow];
+          else if (a.noise_mode == 2) eps = philox_normal(a.seed, noise_row, (uint32_t)t);
+        }
+        const float rew = E::step(s, act, eps, a.noise_mode != 0);
+        const float prew = (rew + a.rew_shift) * a.rew_scale;
+        rsum += gpow * prew;
+        gpow *= a.gamma;
+        if (a.traj_rew) a.traj_rew[(size_t)t * MB + grow] = prew;
+        if (a.traj_obs) {
+          float o[MPG_MAX_OBS];
+          E::get_obs(s, o, a.nfd);
+          for (int i = 0; i < a.obs_dim; ++i) a.traj_obs[((size_t)t * MB + grow) * a.obs_dim + i] = o[i];
+        }
+      }
+    }
+    // =========================================== backward ==========================================
+    if (BWD) {
+      float lam[S], snext[S];
+#pragma unroll
+      for (int j = 0; j < S; ++j) { lam[j] = 0.f; snext[j] = s[j]; }
+      for (int t = a.horizon; t >= 0; --t) {
+        float gp = 1.f;
+        for (int i = 0; i < t; ++i) gp *= a.gamma;
+        const bool want_dw = a.full_bptt || t == 0;
+        const bool rec = store_dw && want_dw;
+        uint8_t* slot = rec ? A.store + ((size_t)tile * A.store_steps + (a.full_bptt ? t : 0)) * SLOT_BYTES : nullptr;
+        float g_a[NA], g_s[S], act[NA], zpre[NA];
+#pragma unroll
+        for (int j = 0; j < NA; ++j) { g_a[j] = 0.f; act[j] = 0.f; zpre[j] = 0.f; }
+#pragma unroll
+        for (int j = 0; j < S; ++j) g_s[j] = 0.f;
+        if (rowthread && valid) {
+          const float* c = a.ckpt + ((size_t)t * MB + grow) * S;
+#pragma unroll
+          for (int j = 0; j < S; ++j) s[j] = c[j];
+        }
+        int kidx = -1;
+        for (int k = 0; k < a.n_list; ++k) if (a.list[k] == t) kidx = k;
+        // ---- Q input gradient at the list steps: upstream c w_k gamma^t on Q1(p_t, a_t) ----
+        if (kidx >= 0 && a.has_q && a.list_w[kidx] != 0.f) {
+          if (rowthread) {
+            float ak[NA];
+#pragma unroll
+            for (int j = 0; j < NA; ++j) ak[j] = valid ? A.act_ckpt[((size_t)kidx * MB + grow) * NA + j] : 0.f;
+            write_pimg(s, ak);
+          }
+          (void)q_forward();                               // z1q in tm_z1, z2q in tm_work
+          if (ROLE == ROLE_EPI) {
+            if (rowthread) mf->d3s[row] = valid ? cscale * a.list_w[kidx] * gp : 0.f;
+            epi_bar();
+            epi_delta2(tm_work + lane_off, mf->b2q, mf->W3q, mf->d3s[row], 0.f, act_img, row, hc);
+          }
+          gemm<ROLE>(0, b, smem, sy, A.q.big_dx, tm_work);  // g_h1q
+          if (ROLE == ROLE_EPI) epi_delta1(tm_work + lane_off, tm_z1 + lane_off, act_img, row, hc);
+          gemm<ROLE>(2, b, smem, sy, A.q.in, tm_z1);        // g_in -> 16 columns of the z1 region
+          if (rowthread) {
+            float gin[16];
+            tmem_ld16(tm_z1 + lane_off, gin);
+            if (valid) {
+              float go[MPG_MAX_OBS];
+              for (int i = 0; i < a.obs_dim; ++i) go[i] = gin[i] * a.obs_scale[i];
+              E::obs_grad_to_state(s, go, a.nfd, g_s);
+#pragma unroll
+              for (int j = 0; j < NA; ++j) g_a[j] += gin[a.obs_dim + j];
+            }
+          }
+        }
+        // ---- policy recompute ----
+        if (rowthread) write_pimg(s, nullptr);
+        if (ROLE == ROLE_EPI && rec) store_image(elected, slot + SLOT_P, p_img, 8192);
+        policy_forward(zpre, rec, rec, slot);
+        if (rowthread) {
+#pragma unroll
+          for (int j = 0; j < NA; ++j) act[j] = head_fwd(zpre[j], a.policy_out_tanh, a.action_range);
+          if (t < a.horizon && valid) {
+            float Wt = 0.f;
+            for (int k = 0; k < a.n_list; ++k) if (a.list[k] > t) Wt += a.list_w[k];
+            env_step_bwd<ENV>(s, act, lam, cscale * Wt * gp * a.rew_scale, g_s, g_a, snext);
+          }
+        }
+        // ---- delta3, its image, db3 ----
+        if (ROLE == ROLE_EPI) {
+          float d3[2] = {0.f, 0.f};
+          if (rowthread) {
+#pragma unroll
+            for (int j = 0; j < NA; ++j) {
+              d3[j] = valid ? g_a[j] * head_grad(zpre[j], a.policy_out_tanh, a.action_range) : 0.f;
+              mf->d3s[j * ACT_ROWS + row] = d3[j];
+            }
+            if (NA == 1) mf->d3s[ACT_ROWS + row] = 0.f;
+            if (want_dw) {
+              float x[16];
+#pragma unroll
+              for (int i = 0; i < 16; ++i) x[i] = 0.f;
+              x[0] = d3[0]; x[1] = d3[1];
+              if (rec) write_row16(d3_img, row, x);
+              float s0 = d3[0], s1 = d3[1];
+#pragma unroll
+              for (int o = 16; o > 0; o >>= 1) { s0 += __shfl_xor_sync(0xffffffffu, s0, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o); }
+              if (lane == 0) { mf->wsum[warp * 2] = s0; mf->wsum[warp * 2 + 1] = s1; }
+            }
+          }
+          if (rec) {
+            store_wait(elected);                            // previous image (h2 or h1) read out
+            store_image(elected, slot + SLOT_D3, d3_img, 8192);
+          } else {
+            epi_bar();
+          }
+          if (tid == 0 && want_dw) {
+            db3acc[0] += (mf->wsum[0] + mf->wsum[2]) + (mf->wsum[4] + mf->wsum[6]);
+            db3acc[1] += (mf->wsum[1] + mf->wsum[3]) + (mf->wsum[5] + mf->wsum[7]);
+          }
+          // ---- delta2 image ----
+          epi_delta2(tm_work + lane_off, mf->b2p, mf->W3p, mf->d3s[row], mf->d3s[ACT_ROWS + row], act_img, row, hc);
+          if (rec) store_image(elected, slot + SLOT_D2, act_img, 2 * ACT_SPLIT);
+        }
+        gemm<ROLE>(0, b, smem, sy, A.pol.big_dx, tm_work);   // g_h1
+        if (ROLE == ROLE_EPI) {
+          if (rec) store_wait(elected);                      // delta2 image read out before it is overwritten
+          epi_delta1(tm_work + lane_off, tm_z1 + lane_off, act_img, row, hc);
+          if (rec) store_image(elected, slot + SLOT_D1, act_img, 2 * ACT_SPLIT);
+        }
+        if (t > 0) {
+          gemm<ROLE>(2, b, smem, sy, A.pol.in, tm_z1);       // g_p
+          if (rowthread) {
+            float gin[16];
+            tmem_ld16(tm_z1 + lane_off, gin);
+            if (valid) {
+#pragma unroll
+              for (int j = 0; j < S; ++j) { lam[j] = g_s[j]; snext[j] = s[j]; }
+              float go[MPG_MAX_OBS];
+              for (int i = 0; i < a.obs_dim; ++i) go[i] = gin[i] * a.obs_scale[i];
+              E::obs_grad_to_state(s, go, a.nfd, lam);
+            }
+          }
+        }
+        if (ROLE == ROLE_EPI && rec) store_wait(elected);    // delta1 image read out before the next step
+      }
+    }
+  }
+  if (ROLE == ROLE_EPI) {
+    tc_fence_before();
+    if (BWD && tid == 0) {
+      const GradLayout L(A.pol.in_dim, A.pol.out_dim);
+      float* partial = a.partial + (size_t)blockIdx.x * a.partial_stride;
+      partial[L.ob3 + 0] = db3acc[0];
+      if (NA > 1) partial[L.ob3 + 1] = db3acc[1];
+    }
+    if (elected) bulk_wait_all();
+  }
+}
+
+template <int ENV, bool BWD>
+__global__ void __launch_bounds__(CTA_THREADS, 1) tc_rollout_kernel(const __grid_constant__ TcArgs A) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  MiscF* mf = reinterpret_cast<MiscF*>(smem + SmemMap::MISC);
+  for (int i = threadIdx.x; i < H; i += blockDim.x) {
+    mf->b2p[i] = A.pol.b2[i];
+    mf->W3p[2 * i] = A.pol.W3[i * A.pol.out_dim];
+    mf->W3p[2 * i + 1] = Env<ENV>::A > 1 ? A.pol.W3[i * A.pol.out_dim + 1] : 0.f;
+    if (A.r.has_q) {
+      mf->b2q[i] = A.q.b2[i];
+      mf->W3q[2 * i] = A.q.W3[i];
+      mf->W3q[2 * i + 1] = 0.f;
+    }
+  }
+  if (threadIdx.x == 0) {
+    mf->b3[0] = A.pol.b3[0];
+    mf->b3[1] = Env<ENV>::A > 1 ? A.pol.b3[1] : 0.f;
+    mf->b3[2] = A.r.has_q ? A.q.b3[0] : 0.f;
+  }
+  Bars* b = cta_setup(smem);   // contains __syncthreads()
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp < 8) run_rollout<ENV, BWD, ROLE_EPI>(A, smem, b);
+  else if (warp == 8) { if (lane == 0) run_rollout<ENV, BWD, ROLE_PRODUCER>(A, smem, b); }
+  else { if (lane == 0) run_rollout<ENV, BWD, ROLE_MMA>(A, smem, b); }
+  cta_teardown(b);
+}
+
+// =================================================================================================
+// Weight gradients from the operand store: split-K tcgen05 GEMMs with MN-major operands (K = rows).
+// CTA c owns feature half mh = c & 1 of every left operand and the records r = c>>1, c>>1 + G/2, ...
+//   D2  [128 x 256] += h1[:, mh]^T . delta2            -> dW2[k][n]
+//   Db2 [128 x 16]  += delta2[:, mh]^T . [p|1]         -> column BIAS_K = db2[n]
+//   D1  [128 x 16]  += delta1[:, mh]^T . [p|1]         -> dW1[i][n] (columns i < in_dim), db1[n] (column BIAS_K)
+//   D3  [128 x 16]  += h2[:, mh]^T . [delta3|0]        -> dW3[k][j]
+// =================================================================================================
+struct DwArgs {
+  const uint8_t* store;
+  int nrecords;            // tiles * store_steps
+  int has_h2;              // records carry h2 / delta3 images for every step (full BPTT) or only ... always with dW
+  int in_dim, out_dim, act_dim;
+  float* partial;
+  long long partial_stride;
+};
+
+constexpr int DW_ROWS = 32;                                     // rows (K) per stage
+constexpr int DW_OFF_H1 = 0, DW_OFF_D2 = 16384, DW_OFF_D1 = 49152, DW_OFF_H2 = 65536, DW_OFF_P = 81920, DW_OFF_D3 = 83968;
+constexpr int DW_STAGE = 86016;                                 // bytes per stage (84 KB)
+constexpr int DW_TM_D2 = 0, DW_TM_DB2 = 256, DW_TM_D1 = 272, DW_TM_D3 = 288;
+
+__global__ void __launch_bounds__(192, 1) tc_dw_kernel(const __grid_constant__ DwArgs A) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* stage_buf = smem;                                    // 2 x DW_STAGE
+  Bars* b = reinterpret_cast<Bars*>(smem + 2 * DW_STAGE);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NSLOT; ++i) { mbar_init(&b->full[i], 1); mbar_init(&b->empty[i], 1); }
+    mbar_init(&b->d_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 5) tmem_alloc(&b->tmem_base, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = b->tmem_base;
+  const int mh = blockIdx.x & 1, first = blockIdx.x >> 1, stride = gridDim.x >> 1;
+  const int nmine = first < A.nrecords ? (A.nrecords - first + stride - 1) / stride : 0;
+  const int nstages = nmine * (ACT_ROWS / DW_ROWS);
+
+  if (warp == 4) {
+    // ------------------------------- producer -------------------------------
+    if (lane == 0) {
+      uint32_t st = 0;
+      for (int r = first; r < A.nrecords; r += stride) {
+        const uint8_t* rec = A.store + (size_t)r * SLOT_BYTES;
+        for (int q = 0; q < ACT_ROWS / DW_ROWS; ++q, ++st) {
+          const uint32_t slot = st & 1, par = (st >> 1) & 1;
+          uint8_t* dst = stage_buf + slot * DW_STAGE;
+          mbar_wait(&b->empty[slot], par ^ 1);
+          mbar_expect_tx(&b->full[slot], DW_STAGE);
+          const size_t rowoff = (size_t)q * DW_ROWS * 128;       // 32 rows x 128 B inside a 64-feature block
+          for (int sp = 0; sp < 2; ++sp) {
+            for (int j = 0; j < 2; ++j) {   // left operands: the two 64-feature blocks of half mh
+              const size_t src = (size_t)sp * ACT_SPLIT + (size_t)(2 * mh + j) * ACT_BLOCK + rowoff;
+              bulk_g2s(dst + DW_OFF_H1 + (sp * 2 + j) * 4096, rec + SLOT_H1 + src, 4096, &b->full[slot]);
+              bulk_g2s(dst + DW_OFF_D1 + (sp * 2 + j) * 4096, rec + SLOT_D1 + src, 4096, &b->full[slot]);
+              bulk_g2s(dst + DW_OFF_H2 + (sp * 2 + j) * 4096, rec + SLOT_H2 + src, 4096, &b->full[slot]);
+            }
+            for (int j = 0; j < 4; ++j)     // right operand delta2: all four blocks
+              bulk_g2s(dst + DW_OFF_D2 + (sp * 4 + j) * 4096, rec + SLOT_D2 + (size_t)sp * ACT_SPLIT + (size_t)j * ACT_BLOCK + rowoff,
+                       4096, &b->full[slot]);
+            bulk_g2s(dst + DW_OFF_P + sp * 1024, rec + SLOT_P + (size_t)sp * 4096 + (size_t)q * 1024, 1024, &b->full[slot]);
+            bulk_g2s(dst + DW_OFF_D3 + sp * 1024, rec + SLOT_D3 + (size_t)sp * 4096 + (size_t)q * 1024, 1024, &b->full[slot]);
+          }
+        }
+      }
+    }
+  } else if (warp == 5) {
+    // ------------------------------- mma -------------------------------
+    if (lane == 0) {
+      constexpr uint32_t id256 = make_idesc(128, 256, 1, 1), id16 = make_idesc(128, 16, 1, 1);
+      const uint32_t sbase = smem_u32(stage_buf);
+      for (int st = 0; st < nstages; ++st) {
+        const uint32_t slot = st & 1, par = (st >> 1) & 1;
+        mbar_wait(&b->full[slot], par);
+        tc_fence_after();
+        const uint32_t base = sbase + slot * DW_STAGE;
+#pragma unroll
+        for (int ks = 0; ks < DW_ROWS / 16; ++ks) {
+          const uint32_t acc = (st | ks) ? 1u : 0u;
+          // left operands (MN-major SW128, M = 128 features = 2 blocks 4096 B apart, 8-row groups 1024 B apart)
+          auto L = [&](int off, int sp) { return make_desc(base + off + sp * 8192 + ks * 2048, 4096, 1024, LAYOUT_SW128); };
+          // right operand delta2 (N = 256 = 4 blocks)
+          auto R2 = [&](int sp) { return make_desc(base + DW_OFF_D2 + sp * 16384 + ks * 2048, 4096, 1024, LAYOUT_SW128); };
+          // right operands [p|1], [delta3|0] (MN-major INTERLEAVE, N = 16: halves 128 B apart (SBO), 8-row groups 256 B apart (LBO))
+          auto R16 = [&](int off, int sp) { return make_desc(base + off + sp * 1024 + ks * 512, 256, 128, LAYOUT_NONE); };
+          umma_bf16(tmem + DW_TM_D2, L(DW_OFF_H1, 0), R2(0), id256, acc);
+          umma_bf16(tmem + DW_TM_D2, L(DW_OFF_H1, 1), R2(0), id256, 1u);
+          umma_bf16(tmem + DW_TM_D2, L(DW_OFF_H1, 0), R2(1), id256, 1u);
+          // delta2 as LEFT operand for db2: its blocks 2mh, 2mh+1 inside the right-operand buffer
+          auto LD2 = [&](int sp) { return make_desc(base + DW_OFF_D2 + sp * 16384 + mh * 8192 + ks * 2048, 4096, 1024, LAYOUT_SW128); };
+          umma_bf16(tmem + DW_TM_DB2, LD2(0), R16(DW_OFF_P, 0), id16, acc);
+          umma_bf16(tmem + DW_TM_DB2, LD2(1), R16(DW_OFF_P, 0), id16, 1u);
+          umma_bf16(tmem + DW_TM_D1, L(DW_OFF_D1, 0), R16(DW_OFF_P, 0), id16, acc);
+          umma_bf16(tmem + DW_TM_D1, L(DW_OFF_D1, 1), R16(DW_OFF_P, 0), id16, 1u);
+          umma_bf16(tmem + DW_TM_D1, L(DW_OFF_D1, 0), R16(DW_OFF_P, 1), id16, 1u);
+          umma_bf16(tmem + DW_TM_D3, L(DW_OFF_H2, 0), R16(DW_OFF_D3, 0), id16, acc);
+          umma_bf16(tmem + DW_TM_D3, L(DW_OFF_H2, 1), R16(DW_OFF_D3, 0), id16, 1u);
+          umma_bf16(tmem + DW_TM_D3, L(DW_OFF_H2, 0), R16(DW_OFF_D3, 1), id16, 1u);
+        }
+        umma_commit(&b->empty[slot]);
+      }
+      umma_commit(&b->d_full);
+    }
+  } else {
+    // ------------------------------- epilogue: TMEM -> this CTA's partial gradient -------------------------------
+    const GradLayout L(A.in_dim, A.out_dim);
+    float* partial = A.partial + (size_t)blockIdx.x * A.partial_stride;
+    const int f = mh * 128 + warp * 32 + lane;                   // feature owned by this thread (TMEM lane)
+    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+    if (nstages > 0) {
+      mbar_wait(&b->d_full, 0);
+      tc_fence_after();
+      for (int c0 = 0; c0 < 256; c0 += 32) {
+        float v[32];
+        tmem_ld32(tmem + DW_TM_D2 + lane_off + c0, v);
+        float4* dst = reinterpret_cast<float4*>(partial + L.oW2 + (size_t)f * H + c0);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+      }
+      float v[16];
+      tmem_ld16(tmem + DW_TM_DB2 + lane_off, v);
+      partial[L.ob2 + f] = v[BIAS_K];
+      tmem_ld16(tmem + DW_TM_D1 + lane_off, v);
+      for (int i = 0; i < A.in_dim; ++i) partial[L.oW1 + (size_t)i * H + f] = v[i];
+      partial[L.ob1 + f] = v[BIAS_K];
+      tmem_ld16(tmem + DW_TM_D3 + lane_off, v);
+      for (int j = 0; j < A.act_dim; ++j) partial[L.oW3 + (size_t)f * A.out_dim + j] = v[j];
+    }
+    tc_fence_before();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) tmem_dealloc(tmem, TMEM_COLS);
+}
+
+}  // namespace tc
+}  // namespace mpg

@@ -1,6 +1,6 @@
 // Tensor-core (tcgen05) path: state owned by the handle, weight-image packing, launchers.
 #pragma once
-#include "tc_gemm.cuh"
+#include "tc_kernels.cuh"
 
 namespace mpg {
 
@@ -15,29 +15,44 @@ struct TcState {
   bool ready = false;
   TcNetImages nets[MPG_NUM_NETS];
   uint8_t* scratch_img = nullptr;   // self-test image
+  float* act_ckpt = nullptr;        // [MPG_MAX_LIST][max_rows][MAX_A]
+  uint8_t* store = nullptr;         // dW operand store (allocated on first use, grows)
+  size_t store_bytes = 0;
 };
+
+template <typename K>
+inline bool tc_set_smem(K kernel, int bytes) {
+  return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) == cudaSuccess;
+}
 
 inline bool tc_init(TcState& t, const mpg_config& cfg, int /*sms*/, size_t& ws_bytes) {
   if (cfg.obs_dim + cfg.act_dim + 1 > 16) return true;   // first-layer K must fit one UMMA k-step; stay on FFMA
-  auto alloc = [&](uint8_t** p, size_t n) {
+  auto alloc = [&](void** p, size_t n) {
     if (cudaMalloc(p, n) != cudaSuccess) return false;
     ws_bytes += n;
     return true;
   };
-  bool ok = alloc(&t.scratch_img, 8 * tc::STAGE_BYTES);
+  bool ok = alloc((void**)&t.scratch_img, 8 * tc::STAGE_BYTES)
+            && alloc((void**)&t.act_ckpt, (size_t)MPG_MAX_LIST * cfg.max_rows * MAX_A * sizeof(float));
   for (int n = 0; n < MPG_NUM_NETS && ok; ++n)
-    ok = alloc(&t.nets[n].big_fwd, 8 * tc::STAGE_BYTES) && alloc(&t.nets[n].big_dx, 8 * tc::STAGE_BYTES)
-         && alloc(&t.nets[n].l1, 16384) && alloc(&t.nets[n].in, 16384);
+    ok = alloc((void**)&t.nets[n].big_fwd, 8 * tc::STAGE_BYTES) && alloc((void**)&t.nets[n].big_dx, 8 * tc::STAGE_BYTES)
+         && alloc((void**)&t.nets[n].l1, 16384) && alloc((void**)&t.nets[n].in, 16384);
   if (!ok) return false;
-  if (cudaFuncSetAttribute(tc::selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SmemMap::TOTAL + 1024)
-      != cudaSuccess)
-    return false;
-  t.ready = false;   // flipped on once the rollout kernels are wired in
-  return true;
+  const int sm = tc::SM_TOTAL + 1024;
+  ok = tc_set_smem(tc::selftest_kernel, tc::SmemMap::TOTAL + 1024)
+       && tc_set_smem(tc::tc_rollout_kernel<MPG_ENV_PATH_TRACKING, true>, sm)
+       && tc_set_smem(tc::tc_rollout_kernel<MPG_ENV_PATH_TRACKING, false>, sm)
+       && tc_set_smem(tc::tc_rollout_kernel<MPG_ENV_INVERTED_PENDULUM, true>, sm)
+       && tc_set_smem(tc::tc_rollout_kernel<MPG_ENV_INVERTED_PENDULUM, false>, sm)
+       && tc_set_smem(tc::tc_rollout_kernel<MPG_ENV_INVERTED_DOUBLE_PENDULUM, true>, sm)
+       && tc_set_smem(tc::tc_rollout_kernel<MPG_ENV_INVERTED_DOUBLE_PENDULUM, false>, sm)
+       && tc_set_smem(tc::tc_dw_kernel, 2 * tc::DW_STAGE + 128 + 1024);
+  t.ready = ok;
+  return ok;
 }
 
 inline void tc_destroy(TcState& t) {
-  cudaFree(t.scratch_img);
+  cudaFree(t.scratch_img); cudaFree(t.act_ckpt); cudaFree(t.store);
   for (int n = 0; n < MPG_NUM_NETS; ++n) {
     cudaFree(t.nets[n].big_fwd); cudaFree(t.nets[n].big_dx); cudaFree(t.nets[n].l1); cudaFree(t.nets[n].in);
   }
@@ -49,9 +64,38 @@ inline bool tc_pack_weights(TcState& t, int net, const float* flat, int in_dim, 
   const GradLayout L(in_dim, out_dim);
   tc::pack_big_image<<<32, 256, 0, st>>>(flat + L.oW2, 1, H, t.nets[net].big_fwd);     // value(n,k) = W2[k][n]
   tc::pack_big_image<<<32, 256, 0, st>>>(flat + L.oW2, H, 1, t.nets[net].big_dx);      // value(k,n) = W2[k][n]
-  tc::pack_l1_image<<<2, 256, 0, st>>>(flat + L.oW1, flat + L.ob1, in_dim, 15, t.nets[net].l1);
+  tc::pack_l1_image<<<2, 256, 0, st>>>(flat + L.oW1, flat + L.ob1, in_dim, tc::BIAS_K, t.nets[net].l1);
   tc::pack_in_image<<<2, 256, 0, st>>>(flat + L.oW1, in_dim, t.nets[net].in);
   return cudaGetLastError() == cudaSuccess;
+}
+
+inline tc::TcNet tc_net(const TcState& t, int net, const float* flat, int in_dim, int out_dim) {
+  const GradLayout L(in_dim, out_dim);
+  tc::TcNet n;
+  n.big_fwd = t.nets[net].big_fwd; n.big_dx = t.nets[net].big_dx; n.l1 = t.nets[net].l1; n.in = t.nets[net].in;
+  n.W3 = flat + L.oW3; n.b2 = flat + L.ob2; n.b3 = flat + L.ob3;
+  n.in_dim = in_dim; n.out_dim = out_dim;
+  return n;
+}
+
+inline bool tc_ensure_store(TcState& t, size_t bytes) {
+  if (bytes <= t.store_bytes) return true;
+  cudaFree(t.store);
+  t.store = nullptr; t.store_bytes = 0;
+  if (cudaMalloc((void**)&t.store, bytes) != cudaSuccess) { cudaGetLastError(); return false; }
+  t.store_bytes = bytes;
+  return true;
+}
+
+template <bool BWD>
+inline cudaError_t tc_launch_rollout(int env, const tc::TcArgs& a, int grid, cudaStream_t st) {
+  const size_t smem = tc::SM_TOTAL + 1024;
+  switch (env) {
+    case MPG_ENV_PATH_TRACKING: tc::tc_rollout_kernel<MPG_ENV_PATH_TRACKING, BWD><<<grid, tc::CTA_THREADS, smem, st>>>(a); break;
+    case MPG_ENV_INVERTED_PENDULUM: tc::tc_rollout_kernel<MPG_ENV_INVERTED_PENDULUM, BWD><<<grid, tc::CTA_THREADS, smem, st>>>(a); break;
+    default: tc::tc_rollout_kernel<MPG_ENV_INVERTED_DOUBLE_PENDULUM, BWD><<<grid, tc::CTA_THREADS, smem, st>>>(a); break;
+  }
+  return cudaGetLastError();
 }
 
 // self test of one GEMM kind (see tc_gemm.cuh): W is fp32 [256 x 256] (kind 0), [16 x 256] (kinds 1, 2)
