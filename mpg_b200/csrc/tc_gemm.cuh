@@ -1,11 +1,11 @@
 // Warp-specialised GEMM machinery shared by the tensor-core rollout kernels.
 //
 // Roles inside one CTA (320 threads):
-//   warps 0-7  "epilogue": thread = (TMEM lane = row, 128-column half); they build the A-operand images in
+//   warps 0-15 "epilogue": thread = (TMEM lane = row, 64-column quarter); they build the A-operand images in
 //              shared memory, read accumulators back with tcgen05.ld and run all per-row math;
-//   warp 8     "producer": one elected lane streams weight images from global/L2 into a 2-slot ring with
+//   warp 16    "producer": one elected lane streams weight images from global/L2 into a 2-slot ring with
 //              1-D bulk async copies (TMA engine) completing on mbarriers;
-//   warp 9     "mma": one elected lane issues tcgen05.mma and commits to mbarriers.
+//   warp 17    "mma": one elected lane issues tcgen05.mma and commits to mbarriers.
 // The three roles execute the SAME schedule (same function, same CTA-uniform control flow) and meet only
 // through mbarriers:  a_full (epilogue -> mma: A image written), d_full (mma -> epilogue: accumulator
 // complete, A image and ring slots free), ring full[]/empty[] (producer <-> mma).
@@ -15,8 +15,13 @@
 namespace mpg {
 namespace tc {
 
-constexpr int EPI_THREADS = 256;
-constexpr int CTA_THREADS = 320;
+#ifndef MPG_EPI_WARPS
+#define MPG_EPI_WARPS 16
+#endif
+constexpr int EPI_WARPS = MPG_EPI_WARPS;                 // 4 per TMEM lane quadrant: each owns 64 accumulator columns
+constexpr int EPI_THREADS = EPI_WARPS * 32;
+constexpr int CTA_THREADS = EPI_THREADS + 64;  // + producer warp + mma warp
+constexpr int COLS_PER_WARP = 256 / (EPI_WARPS / 4);
 constexpr int STAGE_BYTES = 32768;            // ring slot
 constexpr int NSLOT = 2;
 constexpr int TMEM_COLS = 512;
@@ -172,7 +177,7 @@ __device__ __forceinline__ Bars* cta_setup(uint8_t* smem) {
     mbar_init(&b->d_full, 1);
     fence_barrier_init();
   }
-  if (warp == 9) tmem_alloc(&b->tmem_base, TMEM_COLS);
+  if (warp == EPI_WARPS + 1) tmem_alloc(&b->tmem_base, TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -181,7 +186,7 @@ __device__ __forceinline__ Bars* cta_setup(uint8_t* smem) {
 __device__ __forceinline__ void cta_teardown(Bars* b) {
   tc_fence_before();
   __syncthreads();
-  if ((threadIdx.x >> 5) == 9) tmem_dealloc(b->tmem_base, TMEM_COLS);
+  if ((threadIdx.x >> 5) == EPI_WARPS + 1) tmem_dealloc(b->tmem_base, TMEM_COLS);
 }
 
 // ---- global weight-image packing (run once per set_weights) ------------------------------------------------
@@ -250,8 +255,9 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) selftest_kernel(int kind, cons
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t tmem = b->tmem_base;
   Sync s;
-  if (warp < 8) {
+  if (warp < EPI_WARPS) {
     const int row = (warp & 3) * 32 + lane, hc = warp >> 2;
+    constexpr int CW = COLS_PER_WARP;
     for (int rep = 0; rep < repeats; ++rep) {
       if (kind == 1) {
         if (hc == 0) {
@@ -265,7 +271,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) selftest_kernel(int kind, cons
           }
         }
       } else {
-        for (int cc = hc * 16; cc < hc * 16 + 16; ++cc) {
+        for (int cc = hc * (CW / 8); cc < (hc + 1) * (CW / 8); ++cc) {
           float x[8];
           for (int e = 0; e < 8; ++e) x[e] = X[row * 256 + cc * 8 + e];
           act_store8(smem + SmemMap::ACT, smem + SmemMap::ACT + ACT_SPLIT, row, cc, x);
@@ -280,7 +286,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) selftest_kernel(int kind, cons
           for (int j = 0; j < 16; ++j) Z[row * 16 + j] = v[j];
         }
       } else {
-        for (int c0 = hc * 128; c0 < hc * 128 + 128; c0 += 32) {
+        for (int c0 = hc * CW; c0 < (hc + 1) * CW; c0 += 32) {
           float v[32];
           tmem_ld32(lane_base + c0, v);
           for (int j = 0; j < 32; ++j) Z[row * 256 + c0 + j] = v[j];
@@ -288,7 +294,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) selftest_kernel(int kind, cons
       }
     }
     tc_fence_before();
-  } else if (warp == 8) {
+  } else if (warp == EPI_WARPS) {
     if (lane == 0)
       for (int rep = 0; rep < repeats; ++rep) gemm<ROLE_PRODUCER>(kind, b, smem, s, img, 0);
   } else {

@@ -15,6 +15,10 @@
 #include "rollout_kernels.cuh"
 #include "tc_gemm.cuh"
 
+#ifndef MPG_EPI_INLINE
+#define MPG_EPI_INLINE __forceinline__
+#endif
+
 namespace mpg {
 namespace tc {
 
@@ -47,7 +51,7 @@ struct MiscF {
   float b2p[H];
   float W3q[H * 2];
   float b2q[H];
-  float part[2 * 2 * ACT_ROWS];   // [hc][j][row]
+  float part[4 * 2 * ACT_ROWS];   // [column quarter][j][row]
   float d3s[2 * ACT_ROWS];        // [j][row]
   float wsum[8];                  // per-warp delta3 sums [warp][j]
   float b3[4];                    // b3p[0], b3p[1], b3q[0]
@@ -57,12 +61,12 @@ static_assert(sizeof(MiscF) <= SmemMap::MISC_BYTES, "MISC region too small");
 constexpr int SM_D3IMG = SmemMap::TOTAL;          // delta3 image hi|lo (8 KB) appended after the base map
 constexpr int SM_TOTAL = SM_D3IMG + 8192;
 
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
-__device__ __forceinline__ float elu_fast(float x) { return x > 0.f ? x : __expf(x) - 1.f; }
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory"); }
+__device__ __forceinline__ float elu_fast(float x) { return x > 0.f ? x : exp_fast(x) - 1.f; }
 
 // z1 (TMEM, bias folded in) -> h1 image
-__device__ __forceinline__ void epi_hidden1(uint32_t tm_lane, uint8_t* act, int row, int hc) {
-  for (int c0 = hc * 128; c0 < hc * 128 + 128; c0 += 32) {
+__device__ MPG_EPI_INLINE void epi_hidden1(uint32_t tm_lane, uint8_t* act, int row, int hc) {
+  for (int c0 = hc * COLS_PER_WARP; c0 < (hc + 1) * COLS_PER_WARP; c0 += 32) {
     float v[32];
     tmem_ld32(tm_lane + c0, v);
 #pragma unroll
@@ -73,10 +77,10 @@ __device__ __forceinline__ void epi_hidden1(uint32_t tm_lane, uint8_t* act, int 
 }
 // z2 (TMEM) + b2 -> h2 -> partial output-layer dot products; optionally also the h2 image
 template <bool STORE_IMG>
-__device__ __forceinline__ void epi_hidden2(uint32_t tm_lane, const float* b2, const float* W3, uint8_t* act, int row,
+__device__ MPG_EPI_INLINE void epi_hidden2(uint32_t tm_lane, const float* b2, const float* W3, uint8_t* act, int row,
                                             int hc, float& p0, float& p1) {
   p0 = 0.f; p1 = 0.f;
-  for (int c0 = hc * 128; c0 < hc * 128 + 128; c0 += 32) {
+  for (int c0 = hc * COLS_PER_WARP; c0 < (hc + 1) * COLS_PER_WARP; c0 += 32) {
     float v[32];
     tmem_ld32(tm_lane + c0, v);
 #pragma unroll
@@ -93,9 +97,9 @@ __device__ __forceinline__ void epi_hidden2(uint32_t tm_lane, const float* b2, c
   }
 }
 // delta2 = (delta3 W3^T) * elu'(h2), h2 re-derived from z2 (TMEM) -> delta2 image
-__device__ __forceinline__ void epi_delta2(uint32_t tm_lane, const float* b2, const float* W3, float d30, float d31,
+__device__ MPG_EPI_INLINE void epi_delta2(uint32_t tm_lane, const float* b2, const float* W3, float d30, float d31,
                                            uint8_t* act, int row, int hc) {
-  for (int c0 = hc * 128; c0 < hc * 128 + 128; c0 += 32) {
+  for (int c0 = hc * COLS_PER_WARP; c0 < (hc + 1) * COLS_PER_WARP; c0 += 32) {
     float v[32];
     tmem_ld32(tm_lane + c0, v);
 #pragma unroll
@@ -103,20 +107,20 @@ __device__ __forceinline__ void epi_delta2(uint32_t tm_lane, const float* b2, co
       const float z = v[i] + b2[c0 + i];
       const float2 w = *reinterpret_cast<const float2*>(W3 + 2 * (c0 + i));
       const float g = fmaf(d30, w.x, d31 * w.y);
-      v[i] = g * (z > 0.f ? 1.f : __expf(z));     // elu'(z) = 1 | exp(z)
+      v[i] = g * (z > 0.f ? 1.f : exp_fast(z));   // elu'(z) = 1 | exp(z)
     }
 #pragma unroll
     for (int cc = 0; cc < 4; ++cc) act_store8(act, act + ACT_SPLIT, row, (c0 >> 3) + cc, v + 8 * cc);
   }
 }
 // delta1 = g_h1 (TMEM work) * elu'(z1) (TMEM z1) -> delta1 image
-__device__ __forceinline__ void epi_delta1(uint32_t tm_work, uint32_t tm_z1, uint8_t* act, int row, int hc) {
-  for (int c0 = hc * 128; c0 < hc * 128 + 128; c0 += 16) {
+__device__ MPG_EPI_INLINE void epi_delta1(uint32_t tm_work, uint32_t tm_z1, uint8_t* act, int row, int hc) {
+  for (int c0 = hc * COLS_PER_WARP; c0 < (hc + 1) * COLS_PER_WARP; c0 += 16) {
     float g[16], z[16];
     tmem_ld16(tm_work + c0, g);
     tmem_ld16(tm_z1 + c0, z);
 #pragma unroll
-    for (int i = 0; i < 16; ++i) g[i] *= (z[i] > 0.f ? 1.f : __expf(z[i]));
+    for (int i = 0; i < 16; ++i) g[i] *= (z[i] > 0.f ? 1.f : exp_fast(z[i]));
     act_store8(act, act + ACT_SPLIT, row, (c0 >> 3), g);
     act_store8(act, act + ACT_SPLIT, row, (c0 >> 3) + 1, g + 8);
   }
@@ -156,7 +160,7 @@ __device__ __forceinline__ void run_rollout(const TcArgs& A, uint8_t* smem, Bars
   constexpr int S = E::S, NA = E::A;
   const RolloutArgs& a = A.r;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int row = (warp & 3) * 32 + lane, hc = (warp >> 2) & 1;
+  const int row = (warp & 3) * 32 + lane, hc = (warp >> 2) & 3;   // hc: column quarter of this warp
   const bool rowthread = (ROLE == ROLE_EPI) && hc == 0;
   const bool elected = (ROLE == ROLE_EPI) && tid == 0;
   const int MB = a.rows * a.M;
@@ -224,7 +228,8 @@ __device__ __forceinline__ void run_rollout(const TcArgs& A, uint8_t* smem, Bars
         if (rowthread) {
 #pragma unroll
           for (int j = 0; j < NA; ++j)
-            zpre[j] = mf->b3[j] + mf->part[(0 * 2 + j) * ACT_ROWS + row] + mf->part[(1 * 2 + j) * ACT_ROWS + row];
+            zpre[j] = mf->b3[j] + ((mf->part[(0 * 2 + j) * ACT_ROWS + row] + mf->part[(1 * 2 + j) * ACT_ROWS + row])
+                                   + (mf->part[(2 * 2 + j) * ACT_ROWS + row] + mf->part[(3 * 2 + j) * ACT_ROWS + row]));
         }
       }
     };
@@ -239,7 +244,8 @@ __device__ __forceinline__ void run_rollout(const TcArgs& A, uint8_t* smem, Bars
         epi_hidden2<false>(tm_work + lane_off, mf->b2q, mf->W3q, act_img, row, hc, p0, p1);
         mf->part[(hc * 2 + 0) * ACT_ROWS + row] = p0;
         epi_bar();
-        if (rowthread) qv = mf->b3[2] + mf->part[0 * ACT_ROWS + row] + mf->part[2 * ACT_ROWS + row];
+        if (rowthread) qv = mf->b3[2] + ((mf->part[0 * ACT_ROWS + row] + mf->part[2 * ACT_ROWS + row])
+                                         + (mf->part[4 * ACT_ROWS + row] + mf->part[6 * ACT_ROWS + row]));
       }
       return qv;
     };
@@ -461,8 +467,8 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) tc_rollout_kernel(const __grid
   }
   Bars* b = cta_setup(smem);   // contains __syncthreads()
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (warp < 8) run_rollout<ENV, BWD, ROLE_EPI>(A, smem, b);
-  else if (warp == 8) { if (lane == 0) run_rollout<ENV, BWD, ROLE_PRODUCER>(A, smem, b); }
+  if (warp < EPI_WARPS) run_rollout<ENV, BWD, ROLE_EPI>(A, smem, b);
+  else if (warp == EPI_WARPS) { if (lane == 0) run_rollout<ENV, BWD, ROLE_PRODUCER>(A, smem, b); }
   else { if (lane == 0) run_rollout<ENV, BWD, ROLE_MMA>(A, smem, b); }
   cta_teardown(b);
 }

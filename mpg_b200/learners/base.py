@@ -4,6 +4,7 @@ import numpy as np
 import torch
 
 from ..engine import Engine  # noqa: F401  (documentation of the dependency)
+from .. import parallel
 from ..preprocessor import Preprocessor
 from ..utils.misc import TimerStat
 
@@ -52,9 +53,7 @@ class LearnerBase(object):
         self._noise_q = self._noise_p = None
         self._dev, self._pinned, self.h2d_bytes = {}, {}, 0
         # data parallel: each rank holds a contiguous shard of the global batch
-        self.world_size, self.rank = 1, 0
-        if torch.distributed.is_available() and torch.distributed.is_initialized():
-            self.world_size, self.rank = torch.distributed.get_world_size(), torch.distributed.get_rank()
+        self.world_size, self.rank = parallel.dist_info()
 
     # -- reference interface ------------------------------------------------------------------------
     def get_stats(self):
@@ -95,27 +94,14 @@ class LearnerBase(object):
 
     @property
     def global_rows(self):
-        return self._dev['batch_obs'].shape[0] * self.world_size
+        return parallel.shard_rows(self._dev['batch_obs'].shape[0], self.world_size, self.rank)[0]
 
     @property
     def row_offset(self):
-        return self._dev['batch_obs'].shape[0] * self.rank
+        return parallel.shard_rows(self._dev['batch_obs'].shape[0], self.world_size, self.rank)[1]
 
     def _allreduce(self, flat):
-        if self.world_size > 1:
-            torch.distributed.all_reduce(flat, op=torch.distributed.ReduceOp.SUM)
-        return flat
+        return parallel.allreduce_flat(flat, self.world_size)
 
     def _split_to_numpy(self, flat_host, nets):
-        """flat fp32 host vector (concatenated nets) -> list of arrays in [W1,b1,W2,b2,W3,b3] order per net."""
-        out, pos = [], 0
-        a = self.args
-        for kind in nets:
-            in_dim = a.obs_dim + (a.act_dim if kind == 'q' else 0)
-            out_dim = 1 if kind == 'q' else 2 * a.act_dim
-            for shape in ((in_dim, 256), (256,), (256, 256), (256,), (256, out_dim), (out_dim,)):
-                n = int(np.prod(shape))
-                out.append(flat_host[pos:pos + n].reshape(shape))
-                pos += n
-        assert pos == flat_host.size
-        return out
+        return parallel.split_flat(flat_host, self.args.obs_dim, self.args.act_dim, nets)
