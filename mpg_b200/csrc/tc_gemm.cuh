@@ -41,7 +41,8 @@ struct SmemMap {
 struct Bars {
   uint64_t full[NSLOT];
   uint64_t empty[NSLOT];
-  uint64_t a_full;
+  uint64_t a_full;       // [p|a|1] image written (first-layer GEMMs)
+  uint64_t a_blk[4];     // 64-feature block kb of the activation image written (K-block pipelining)
   uint64_t d_full;
   uint32_t tmem_base;
 };
@@ -50,6 +51,7 @@ struct Bars {
 struct Sync {
   uint32_t stage = 0;    // ring stages produced / consumed so far
   uint32_t a_cnt = 0;    // a_full phases seen
+  uint32_t g_cnt = 0;    // a_blk[] phases seen (GEMMs whose A operand is the activation image)
   uint32_t d_cnt = 0;    // d_full phases seen
 };
 
@@ -66,12 +68,15 @@ __device__ __forceinline__ void produce(Bars* b, uint8_t* ring, Sync& s, const u
 }
 
 // ---- mma role ----------------------------------------------------------------------------------------
-// big GEMM: D[128 x 256] = ACT[128 x 256] . Wt^T, Wt image streamed as 8 stages (n-half h, k-block kb):
-// stage = [hi: 128 rows x 128 B][lo: 128 rows x 128 B]
+// big GEMM: D[128 x 256] = ACT[128 x 256] . Wt^T, Wt image streamed as 8 stages ordered (k-block kb, n-half h):
+// stage = [hi: 128 rows x 128 B][lo: 128 rows x 128 B].  K-block kb is issued as soon as the epilogue has
+// published that 64-feature block of the activation image, so the UMMAs overlap the epilogue that produces A.
 __device__ __forceinline__ void mma_big(Bars* b, uint32_t act_addr, uint32_t ring_addr, Sync& s, uint32_t d_tmem) {
   constexpr uint32_t idesc = make_idesc(128, 128, 0, 0);
-  for (int h = 0; h < 2; ++h)
-    for (int kb = 0; kb < 4; ++kb, ++s.stage) {
+  for (int kb = 0; kb < 4; ++kb) {
+    mbar_wait(&b->a_blk[kb], s.g_cnt & 1);
+    tc_fence_after();
+    for (int h = 0; h < 2; ++h, ++s.stage) {
       const uint32_t slot = s.stage & 1, par = (s.stage >> 1) & 1;
       mbar_wait(&b->full[slot], par);
       tc_fence_after();
@@ -89,11 +94,15 @@ __device__ __forceinline__ void mma_big(Bars* b, uint32_t act_addr, uint32_t rin
       }
       umma_commit(&b->empty[slot]);
     }
+  }
+  ++s.g_cnt;
 }
 // first-layer GEMM: D[128 x 256] = P[128 x 16] . W1aug^T ; P is the INTERLEAVE image in shared memory,
 // W1aug image streamed as ONE stage = [hi: 256 rows x 32 B][lo: 256 rows x 32 B] = 16 KB
 __device__ __forceinline__ void mma_l1(Bars* b, uint32_t p_addr, uint32_t ring_addr, Sync& s, uint32_t d_tmem) {
   constexpr uint32_t idesc = make_idesc(128, 256, 0, 0);
+  mbar_wait(&b->a_full, s.a_cnt & 1);
+  ++s.a_cnt;
   const uint32_t slot = s.stage & 1, par = (s.stage >> 1) & 1;
   mbar_wait(&b->full[slot], par);
   tc_fence_after();
@@ -111,10 +120,11 @@ __device__ __forceinline__ void mma_l1(Bars* b, uint32_t p_addr, uint32_t ring_a
 __device__ __forceinline__ void mma_in(Bars* b, uint32_t act_addr, uint32_t ring_addr, Sync& s, uint32_t d_tmem) {
   constexpr uint32_t idesc = make_idesc(128, 16, 0, 0);
   const uint32_t slot = s.stage & 1, par = (s.stage >> 1) & 1;
-  mbar_wait(&b->full[slot], par);
-  tc_fence_after();
   const uint32_t bbase = ring_addr + slot * STAGE_BYTES;
-  for (int kb = 0; kb < 4; ++kb)
+  for (int kb = 0; kb < 4; ++kb) {
+    mbar_wait(&b->a_blk[kb], s.g_cnt & 1);
+    if (kb == 0) mbar_wait(&b->full[slot], par);
+    tc_fence_after();
 #pragma unroll
     for (int ks = 0; ks < 4; ++ks) {
       const uint32_t a_hi = act_addr + kb * ACT_BLOCK + ks * 32, a_lo = a_hi + ACT_SPLIT;
@@ -125,21 +135,24 @@ __device__ __forceinline__ void mma_in(Bars* b, uint32_t act_addr, uint32_t ring
       umma_bf16(d_tmem, dal, dbh, idesc, 1u);
       umma_bf16(d_tmem, dah, dbl, idesc, 1u);
     }
+  }
   umma_commit(&b->empty[slot]);
   ++s.stage;
+  ++s.g_cnt;
 }
 
 // ---- handshakes ----------------------------------------------------------------------------------------
-// epilogue side: A image (and any TMEM reads) done -> let the mma role go
+// epilogue side: [p|a|1] image (and any TMEM reads) done -> let the first-layer GEMM go
 __device__ __forceinline__ void epi_publish_a(Bars* b) {
   tc_fence_before();
   fence_proxy_async();
   mbar_arrive(&b->a_full);
 }
-__device__ __forceinline__ void mma_wait_a(Bars* b, Sync& s) {
-  mbar_wait(&b->a_full, s.a_cnt & 1);
-  ++s.a_cnt;
-  tc_fence_after();
+// epilogue side: 64-feature block kb of the activation image written by this thread
+__device__ __forceinline__ void epi_block_done(Bars* b, int kb) {
+  tc_fence_before();
+  fence_proxy_async();
+  mbar_arrive(&b->a_blk[kb]);
 }
 __device__ __forceinline__ void mma_publish_d(Bars* b) { umma_commit(&b->d_full); }
 __device__ __forceinline__ void epi_wait_d(Bars* b, Sync& s) {
@@ -148,23 +161,32 @@ __device__ __forceinline__ void epi_wait_d(Bars* b, Sync& s) {
   tc_fence_after();
 }
 
-// One GEMM as seen by each role. kind: 0 big, 1 first layer, 2 input gradient.
+// Issue side of one GEMM. kind: 0 big, 1 first layer, 2 input gradient.  Producer: stream the weight image.
+// MMA: wait for the operands (per K-block), issue, commit d_full.  Epilogue: kind 1 publishes the [p|a|1]
+// image here; kinds 0/2 publish their A blocks from inside the epilogue loops (epi_block_done).  The
+// epilogue picks the result up later with epi_wait_d.
 template <int ROLE>
-__device__ __forceinline__ void gemm(int kind, Bars* b, uint8_t* smem, Sync& s, const uint8_t* gimg, uint32_t d_tmem) {
+__device__ __forceinline__ void gemm_issue(int kind, Bars* b, uint8_t* smem, Sync& s, const uint8_t* gimg, uint32_t d_tmem) {
   if (ROLE == ROLE_PRODUCER) {
     if (kind == 0) produce(b, smem + SmemMap::RING, s, gimg, 8, STAGE_BYTES);
     else produce(b, smem + SmemMap::RING, s, gimg, 1, 16384);
   } else if (ROLE == ROLE_MMA) {
-    mma_wait_a(b, s);
     const uint32_t base = smem_u32(smem);
     if (kind == 0) mma_big(b, base + SmemMap::ACT, base + SmemMap::RING, s, d_tmem);
     else if (kind == 1) mma_l1(b, base + SmemMap::PIMG, base + SmemMap::RING, s, d_tmem);
     else mma_in(b, base + SmemMap::ACT, base + SmemMap::RING, s, d_tmem);
     mma_publish_d(b);
   } else {
-    epi_publish_a(b);
-    epi_wait_d(b, s);
+    if (kind == 1) epi_publish_a(b);
   }
+}
+// compatibility wrapper: issue + wait, A image published as a whole (self test)
+template <int ROLE>
+__device__ __forceinline__ void gemm(int kind, Bars* b, uint8_t* smem, Sync& s, const uint8_t* gimg, uint32_t d_tmem) {
+  if (ROLE == ROLE_EPI && kind != 1)
+    for (int kb = 0; kb < 4; ++kb) epi_block_done(b, kb);
+  gemm_issue<ROLE>(kind, b, smem, s, gimg, d_tmem);
+  if (ROLE == ROLE_EPI) epi_wait_d(b, s);
 }
 
 // ---- CTA prologue / epilogue -----------------------------------------------------------------------------
@@ -174,6 +196,7 @@ __device__ __forceinline__ Bars* cta_setup(uint8_t* smem) {
   if (threadIdx.x == 0) {
     for (int i = 0; i < NSLOT; ++i) { mbar_init(&b->full[i], 1); mbar_init(&b->empty[i], 1); }
     mbar_init(&b->a_full, EPI_THREADS);
+    for (int i = 0; i < 4; ++i) mbar_init(&b->a_blk[i], EPI_THREADS);
     mbar_init(&b->d_full, 1);
     fence_barrier_init();
   }
@@ -190,7 +213,7 @@ __device__ __forceinline__ void cta_teardown(Bars* b) {
 }
 
 // ---- global weight-image packing (run once per set_weights) ------------------------------------------------
-// big image: value(row, k) = src[row * rs + k * cs], 256 rows x 256 k -> 8 stages (h, kb) of [hi 16 KB | lo 16 KB]
+// big image: value(row, k) = src[row * rs + k * cs], 256 rows x 256 k -> 8 stages (kb, h) of [hi 16 KB | lo 16 KB]
 __global__ void pack_big_image(const float* __restrict__ src, int rs, int cs, uint8_t* __restrict__ img) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;   // one thread per (row, 8-element chunk): 256 x 32
   if (idx >= 256 * 32) return;
@@ -201,7 +224,7 @@ __global__ void pack_big_image(const float* __restrict__ src, int rs, int cs, ui
   uint4 h, l;
   split2(x[0], x[1], h.x, l.x); split2(x[2], x[3], h.y, l.y); split2(x[4], x[5], h.z, l.z); split2(x[6], x[7], h.w, l.w);
   const int hh = row >> 7, rr = row & 127, kb = cc >> 3, c = cc & 7;
-  const size_t stage = (size_t)(hh * 4 + kb) * STAGE_BYTES;
+  const size_t stage = (size_t)(kb * 2 + hh) * STAGE_BYTES;   // streamed in (k-block, n-half) order
   const uint32_t off = (rr >> 3) * 1024 + (rr & 7) * 128 + ((c ^ (rr & 7)) << 4);
   *reinterpret_cast<uint4*>(img + stage + off) = h;
   *reinterpret_cast<uint4*>(img + stage + 16384 + off) = l;

@@ -64,65 +64,100 @@ constexpr int SM_TOTAL = SM_D3IMG + 8192;
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory"); }
 __device__ __forceinline__ float elu_fast(float x) { return x > 0.f ? x : exp_fast(x) - 1.f; }
 
-// z1 (TMEM, bias folded in) -> h1 image
-__device__ MPG_EPI_INLINE void epi_hidden1(uint32_t tm_lane, uint8_t* act, int row, int hc) {
-  for (int c0 = hc * COLS_PER_WARP; c0 < (hc + 1) * COLS_PER_WARP; c0 += 32) {
-    float v[32];
-    tmem_ld32(tm_lane + c0, v);
+// load 8 consecutive features of row r back from a split-bf16 image (hi + lo)
+__device__ __forceinline__ void act_load8(const uint8_t* act_hi, const uint8_t* act_lo, int r, int cc, float* x) {
+  const uint32_t off = act_chunk_off(r, cc);
+  const uint4 h = *reinterpret_cast<const uint4*>(act_hi + off);
+  const uint4 l = *reinterpret_cast<const uint4*>(act_lo + off);
+  const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
 #pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = elu_fast(v[i]);
-#pragma unroll
-    for (int cc = 0; cc < 4; ++cc) act_store8(act, act + ACT_SPLIT, row, (c0 >> 3) + cc, v + 8 * cc);
+  for (int i = 0; i < 4; ++i) {
+    x[2 * i] = __uint_as_float(hw[i] << 16) + __uint_as_float(lw[i] << 16);
+    x[2 * i + 1] = __uint_as_float(hw[i] & 0xFFFF0000u) + __uint_as_float(lw[i] & 0xFFFF0000u);
   }
 }
-// z2 (TMEM) + b2 -> h2 -> partial output-layer dot products; optionally also the h2 image
-template <bool STORE_IMG>
-__device__ MPG_EPI_INLINE void epi_hidden2(uint32_t tm_lane, const float* b2, const float* W3, uint8_t* act, int row,
-                                            int hc, float& p0, float& p1) {
+
+// Block-ordered epilogues: every warp handles 16 columns of each 64-feature block kb, so that block kb of
+// the activation image is complete (and published to the MMA warp) after 1/4 of the epilogue.
+
+// z1 (TMEM, bias folded in) -> h1 image
+__device__ MPG_EPI_INLINE void epi_hidden1_blocks(Bars* b, uint32_t tm_lane, uint8_t* act, int row, int hc) {
+  for (int kb = 0; kb < 4; ++kb) {
+    const int c0 = kb * 64 + hc * 16;
+    float v[16];
+    tmem_ld16(tm_lane + c0, v);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = elu_fast(v[i]);
+    act_store8(act, act + ACT_SPLIT, row, c0 >> 3, v);
+    act_store8(act, act + ACT_SPLIT, row, (c0 >> 3) + 1, v + 8);
+    epi_block_done(b, kb);
+  }
+}
+// z2 (TMEM) + b2 -> h2 -> partial output-layer dot products (forward pass: no image needed)
+__device__ MPG_EPI_INLINE void epi_hidden2(uint32_t tm_lane, const float* b2, const float* W3, int hc, float& p0, float& p1) {
   p0 = 0.f; p1 = 0.f;
   for (int c0 = hc * COLS_PER_WARP; c0 < (hc + 1) * COLS_PER_WARP; c0 += 32) {
     float v[32];
     tmem_ld32(tm_lane + c0, v);
 #pragma unroll
     for (int i = 0; i < 32; ++i) {
+      const float h = elu_fast(v[i] + b2[c0 + i]);
+      const float2 w = *reinterpret_cast<const float2*>(W3 + 2 * (c0 + i));
+      p0 = fmaf(h, w.x, p0);
+      p1 = fmaf(h, w.y, p1);
+    }
+  }
+}
+// same, and keep h2 as an image (backward pass: delta2 and the dW3 operand are derived from it)
+__device__ MPG_EPI_INLINE void epi_hidden2_img(uint32_t tm_lane, const float* b2, const float* W3, uint8_t* act, int row,
+                                               int hc, float& p0, float& p1) {
+  p0 = 0.f; p1 = 0.f;
+  for (int kb = 0; kb < 4; ++kb) {
+    const int c0 = kb * 64 + hc * 16;
+    float v[16];
+    tmem_ld16(tm_lane + c0, v);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
       v[i] = elu_fast(v[i] + b2[c0 + i]);
       const float2 w = *reinterpret_cast<const float2*>(W3 + 2 * (c0 + i));
       p0 = fmaf(v[i], w.x, p0);
       p1 = fmaf(v[i], w.y, p1);
     }
-    if (STORE_IMG) {
-#pragma unroll
-      for (int cc = 0; cc < 4; ++cc) act_store8(act, act + ACT_SPLIT, row, (c0 >> 3) + cc, v + 8 * cc);
-    }
+    act_store8(act, act + ACT_SPLIT, row, c0 >> 3, v);
+    act_store8(act, act + ACT_SPLIT, row, (c0 >> 3) + 1, v + 8);
   }
 }
-// delta2 = (delta3 W3^T) * elu'(h2), h2 re-derived from z2 (TMEM) -> delta2 image
-__device__ MPG_EPI_INLINE void epi_delta2(uint32_t tm_lane, const float* b2, const float* W3, float d30, float d31,
-                                           uint8_t* act, int row, int hc) {
-  for (int c0 = hc * COLS_PER_WARP; c0 < (hc + 1) * COLS_PER_WARP; c0 += 32) {
-    float v[32];
-    tmem_ld32(tm_lane + c0, v);
+// delta2 = (delta3 W3^T) * elu'(h2), h2 read back from its image and overwritten in place by delta2
+__device__ MPG_EPI_INLINE void epi_delta2_blocks(Bars* b, const float* W3, float d30, float d31, uint8_t* act, int row, int hc) {
+  for (int kb = 0; kb < 4; ++kb) {
+    const int c0 = kb * 64 + hc * 16;
+    float v[16];
+    act_load8(act, act + ACT_SPLIT, row, c0 >> 3, v);
+    act_load8(act, act + ACT_SPLIT, row, (c0 >> 3) + 1, v + 8);
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      const float z = v[i] + b2[c0 + i];
+    for (int i = 0; i < 16; ++i) {
       const float2 w = *reinterpret_cast<const float2*>(W3 + 2 * (c0 + i));
       const float g = fmaf(d30, w.x, d31 * w.y);
-      v[i] = g * (z > 0.f ? 1.f : exp_fast(z));   // elu'(z) = 1 | exp(z)
+      v[i] = g * (v[i] > 0.f ? 1.f : v[i] + 1.f);     // elu'(z) expressed through the output h2
     }
-#pragma unroll
-    for (int cc = 0; cc < 4; ++cc) act_store8(act, act + ACT_SPLIT, row, (c0 >> 3) + cc, v + 8 * cc);
+    act_store8(act, act + ACT_SPLIT, row, c0 >> 3, v);
+    act_store8(act, act + ACT_SPLIT, row, (c0 >> 3) + 1, v + 8);
+    epi_block_done(b, kb);
   }
 }
 // delta1 = g_h1 (TMEM work) * elu'(z1) (TMEM z1) -> delta1 image
-__device__ MPG_EPI_INLINE void epi_delta1(uint32_t tm_work, uint32_t tm_z1, uint8_t* act, int row, int hc) {
-  for (int c0 = hc * COLS_PER_WARP; c0 < (hc + 1) * COLS_PER_WARP; c0 += 16) {
+__device__ MPG_EPI_INLINE void epi_delta1_blocks(Bars* b, bool publish, uint32_t tm_work, uint32_t tm_z1, uint8_t* act,
+                                                 int row, int hc) {
+  for (int kb = 0; kb < 4; ++kb) {
+    const int c0 = kb * 64 + hc * 16;
     float g[16], z[16];
     tmem_ld16(tm_work + c0, g);
     tmem_ld16(tm_z1 + c0, z);
 #pragma unroll
     for (int i = 0; i < 16; ++i) g[i] *= (z[i] > 0.f ? 1.f : exp_fast(z[i]));
-    act_store8(act, act + ACT_SPLIT, row, (c0 >> 3), g);
+    act_store8(act, act + ACT_SPLIT, row, c0 >> 3, g);
     act_store8(act, act + ACT_SPLIT, row, (c0 >> 3) + 1, g + 8);
+    if (publish) epi_block_done(b, kb);
   }
 }
 // [x0..x15] -> INTERLEAVE image row (hi | lo 4 KB apart)
@@ -205,22 +240,23 @@ __device__ __forceinline__ void run_rollout(const TcArgs& A, uint8_t* smem, Bars
       x[BIAS_K] = 1.f;
       write_row16(p_img, row, x);
     };
-    // policy forward on the current p image: returns pre-activations of the head for the row thread
-    auto policy_forward = [&](float* zpre, bool store_h1, bool store_h2, uint8_t* slot) {
-      gemm<ROLE>(1, b, smem, sy, A.pol.l1, tm_z1);
+    // policy forward on the current p image: returns pre-activations of the head for the row thread.
+    // The layer-2 UMMAs are issued K-block by K-block while the epilogue is still producing h1.
+    auto policy_forward = [&](float* zpre, bool bwd_pass, bool rec_, uint8_t* slot) {
+      gemm_issue<ROLE>(1, b, smem, sy, A.pol.l1, tm_z1);
+      gemm_issue<ROLE>(0, b, smem, sy, A.pol.big_fwd, tm_work);
       if (ROLE == ROLE_EPI) {
-        epi_hidden1(tm_z1 + lane_off, act_img, row, hc);
-        if (store_h1) store_image(elected, slot + SLOT_H1, act_img, 2 * ACT_SPLIT);
-      }
-      gemm<ROLE>(0, b, smem, sy, A.pol.big_fwd, tm_work);
-      if (ROLE == ROLE_EPI) {
+        epi_wait_d(b, sy);                                   // z1
+        epi_hidden1_blocks(b, tm_z1 + lane_off, act_img, row, hc);
+        if (rec_) store_image(elected, slot + SLOT_H1, act_img, 2 * ACT_SPLIT);
+        epi_wait_d(b, sy);                                   // z2 (all layer-2 UMMAs done: h1 image free)
         float p0, p1;
-        if (store_h2) {
-          store_wait(elected);   // h1 image has been read out (and the MMA that used it has completed)
-          epi_hidden2<true>(tm_work + lane_off, mf->b2p, mf->W3p, act_img, row, hc, p0, p1);
-          store_image(elected, slot + SLOT_H2, act_img, 2 * ACT_SPLIT);
+        if (bwd_pass) {
+          if (rec_) store_wait(elected);                     // h1 image has been read out
+          epi_hidden2_img(tm_work + lane_off, mf->b2p, mf->W3p, act_img, row, hc, p0, p1);
+          if (rec_) store_image(elected, slot + SLOT_H2, act_img, 2 * ACT_SPLIT);
         } else {
-          epi_hidden2<false>(tm_work + lane_off, mf->b2p, mf->W3p, act_img, row, hc, p0, p1);
+          epi_hidden2(tm_work + lane_off, mf->b2p, mf->W3p, hc, p0, p1);
         }
         mf->part[(hc * 2 + 0) * ACT_ROWS + row] = p0;
         mf->part[(hc * 2 + 1) * ACT_ROWS + row] = p1;
@@ -234,14 +270,17 @@ __device__ __forceinline__ void run_rollout(const TcArgs& A, uint8_t* smem, Bars
       }
     };
     // Q forward on the current [p|a|1] image: returns Q for the row thread
-    auto q_forward = [&]() -> float {
+    auto q_forward = [&](bool with_img) -> float {
       float qv = 0.f;
-      gemm<ROLE>(1, b, smem, sy, A.q.l1, tm_z1);
-      if (ROLE == ROLE_EPI) epi_hidden1(tm_z1 + lane_off, act_img, row, hc);
-      gemm<ROLE>(0, b, smem, sy, A.q.big_fwd, tm_work);
+      gemm_issue<ROLE>(1, b, smem, sy, A.q.l1, tm_z1);
+      gemm_issue<ROLE>(0, b, smem, sy, A.q.big_fwd, tm_work);
       if (ROLE == ROLE_EPI) {
+        epi_wait_d(b, sy);
+        epi_hidden1_blocks(b, tm_z1 + lane_off, act_img, row, hc);
+        epi_wait_d(b, sy);
         float p0, p1;
-        epi_hidden2<false>(tm_work + lane_off, mf->b2q, mf->W3q, act_img, row, hc, p0, p1);
+        if (with_img) epi_hidden2_img(tm_work + lane_off, mf->b2q, mf->W3q, act_img, row, hc, p0, p1);
+        else epi_hidden2(tm_work + lane_off, mf->b2q, mf->W3q, hc, p0, p1);
         mf->part[(hc * 2 + 0) * ACT_ROWS + row] = p0;
         epi_bar();
         if (rowthread) qv = mf->b3[2] + ((mf->part[0 * ACT_ROWS + row] + mf->part[2 * ACT_ROWS + row])
@@ -286,7 +325,7 @@ __device__ __forceinline__ void run_rollout(const TcArgs& A, uint8_t* smem, Bars
           for (int j = 0; j < NA; ++j) A.act_ckpt[((size_t)kidx * MB + grow) * NA + j] = act[j];
         if (a.has_q) {
           if (rowthread) write_pimg(s, act);
-          qv = q_forward();
+          qv = q_forward(false);
         }
         if (valid && a.returns_out) a.returns_out[(size_t)kidx * MB + grow] = rsum + gpow * qv;
       }
@@ -339,15 +378,21 @@ __device__ __forceinline__ void run_rollout(const TcArgs& A, uint8_t* smem, Bars
             for (int j = 0; j < NA; ++j) ak[j] = valid ? A.act_ckpt[((size_t)kidx * MB + grow) * NA + j] : 0.f;
             write_pimg(s, ak);
           }
-          (void)q_forward();                               // z1q in tm_z1, z2q in tm_work
+          (void)q_forward(true);                           // z1q in tm_z1, h2q image in ACT
           if (ROLE == ROLE_EPI) {
             if (rowthread) mf->d3s[row] = valid ? cscale * a.list_w[kidx] * gp : 0.f;
             epi_bar();
-            epi_delta2(tm_work + lane_off, mf->b2q, mf->W3q, mf->d3s[row], 0.f, act_img, row, hc);
           }
-          gemm<ROLE>(0, b, smem, sy, A.q.big_dx, tm_work);  // g_h1q
-          if (ROLE == ROLE_EPI) epi_delta1(tm_work + lane_off, tm_z1 + lane_off, act_img, row, hc);
-          gemm<ROLE>(2, b, smem, sy, A.q.in, tm_z1);        // g_in -> 16 columns of the z1 region
+          gemm_issue<ROLE>(0, b, smem, sy, A.q.big_dx, tm_work);  // g_h1q, K-blocks issued as delta2 blocks appear
+          if (ROLE == ROLE_EPI) {
+            epi_delta2_blocks(b, mf->W3q, mf->d3s[row], 0.f, act_img, row, hc);
+            epi_wait_d(b, sy);
+          }
+          gemm_issue<ROLE>(2, b, smem, sy, A.q.in, tm_z1);        // g_in -> 16 columns of the z1 region
+          if (ROLE == ROLE_EPI) {
+            epi_delta1_blocks(b, true, tm_work + lane_off, tm_z1 + lane_off, act_img, row, hc);
+            epi_wait_d(b, sy);
+          }
           if (rowthread) {
             float gin[16];
             tmem_ld16(tm_z1 + lane_off, gin);
@@ -363,7 +408,7 @@ __device__ __forceinline__ void run_rollout(const TcArgs& A, uint8_t* smem, Bars
         // ---- policy recompute ----
         if (rowthread) write_pimg(s, nullptr);
         if (ROLE == ROLE_EPI && rec) store_image(elected, slot + SLOT_P, p_img, 8192);
-        policy_forward(zpre, rec, rec, slot);
+        policy_forward(zpre, true, rec, slot);
         if (rowthread) {
 #pragma unroll
           for (int j = 0; j < NA; ++j) act[j] = head_fwd(zpre[j], a.policy_out_tanh, a.action_range);
@@ -405,28 +450,30 @@ __device__ __forceinline__ void run_rollout(const TcArgs& A, uint8_t* smem, Bars
             db3acc[0] += (mf->wsum[0] + mf->wsum[2]) + (mf->wsum[4] + mf->wsum[6]);
             db3acc[1] += (mf->wsum[1] + mf->wsum[3]) + (mf->wsum[5] + mf->wsum[7]);
           }
-          // ---- delta2 image ----
-          epi_delta2(tm_work + lane_off, mf->b2p, mf->W3p, mf->d3s[row], mf->d3s[ACT_ROWS + row], act_img, row, hc);
-          if (rec) store_image(elected, slot + SLOT_D2, act_img, 2 * ACT_SPLIT);
         }
-        gemm<ROLE>(0, b, smem, sy, A.pol.big_dx, tm_work);   // g_h1
+        // ---- delta2 image (in place over h2) feeding the dX UMMAs block by block ----
+        gemm_issue<ROLE>(0, b, smem, sy, A.pol.big_dx, tm_work);   // g_h1
         if (ROLE == ROLE_EPI) {
-          if (rec) store_wait(elected);                      // delta2 image read out before it is overwritten
-          epi_delta1(tm_work + lane_off, tm_z1 + lane_off, act_img, row, hc);
-          if (rec) store_image(elected, slot + SLOT_D1, act_img, 2 * ACT_SPLIT);
+          epi_delta2_blocks(b, mf->W3p, mf->d3s[row], mf->d3s[ACT_ROWS + row], act_img, row, hc);
+          if (rec) store_image(elected, slot + SLOT_D2, act_img, 2 * ACT_SPLIT);
+          epi_wait_d(b, sy);                                       // g_h1 complete, delta2 image consumed
         }
-        if (t > 0) {
-          gemm<ROLE>(2, b, smem, sy, A.pol.in, tm_z1);       // g_p
-          if (rowthread) {
-            float gin[16];
-            tmem_ld16(tm_z1 + lane_off, gin);
-            if (valid) {
+        if (t > 0) gemm_issue<ROLE>(2, b, smem, sy, A.pol.in, tm_z1);   // g_p
+        if (ROLE == ROLE_EPI) {
+          if (rec) store_wait(elected);                            // delta2 image read out before it is overwritten
+          epi_delta1_blocks(b, t > 0, tm_work + lane_off, tm_z1 + lane_off, act_img, row, hc);
+          if (rec) store_image(elected, slot + SLOT_D1, act_img, 2 * ACT_SPLIT);
+          if (t > 0) epi_wait_d(b, sy);
+        }
+        if (t > 0 && rowthread) {
+          float gin[16];
+          tmem_ld16(tm_z1 + lane_off, gin);
+          if (valid) {
 #pragma unroll
-              for (int j = 0; j < S; ++j) { lam[j] = g_s[j]; snext[j] = s[j]; }
-              float go[MPG_MAX_OBS];
-              for (int i = 0; i < a.obs_dim; ++i) go[i] = gin[i] * a.obs_scale[i];
-              E::obs_grad_to_state(s, go, a.nfd, lam);
-            }
+            for (int j = 0; j < S; ++j) { lam[j] = g_s[j]; snext[j] = s[j]; }
+            float go[MPG_MAX_OBS];
+            for (int i = 0; i < a.obs_dim; ++i) go[i] = gin[i] * a.obs_scale[i];
+            E::obs_grad_to_state(s, go, a.nfd, lam);
           }
         }
         if (ROLE == ROLE_EPI && rec) store_wait(elected);    // delta1 image read out before the next step
