@@ -184,6 +184,10 @@ float mpg_kernel_ms(mpg_ctx* ctx);
  * kind 1: Z[128x256] = X[128x16].W[16x256]; kind 2: Z[128x16] = X[128x256].W[16x256]^T. fp32 device pointers. */
 int mpg_tc_selftest(mpg_ctx* ctx, int kind, const float* X, const float* W, float* Z, int repeats, void* stream);
 
+/* Debug timeline of the tensor-core rollout kernel: when `buf` (64 int64, device) is non-NULL the next
+ * mpg_policy_grad calls record clock64() stamps of one backward step of CTA 0. */
+int mpg_set_profile_buffer(mpg_ctx* ctx, long long* buf);
+
 /* counters for bench.py: kernels launched by this handle since creation */
 uint64_t mpg_launch_count(const mpg_ctx* ctx);
 

@@ -36,6 +36,7 @@ struct mpg_ctx {
   uint64_t launches = 0;
   int backend = MPG_BACKEND_FFMA;
   int timing = 0, timed = 0;
+  long long* prof = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   char err[512];
   TcState tc;
@@ -220,6 +221,11 @@ int mpg_set_backend(mpg_ctx* ctx, int backend) {
   return MPG_OK;
 }
 
+int mpg_set_profile_buffer(mpg_ctx* ctx, long long* buf) {
+  if (!ctx) return MPG_ERR_ARG;
+  ctx->prof = buf;
+  return MPG_OK;
+}
 int mpg_set_timing(mpg_ctx* ctx, int enabled) {
   if (!ctx) return MPG_ERR_ARG;
   if (enabled && !ctx->ev0) {
@@ -389,6 +395,7 @@ int mpg_policy_grad(mpg_ctx* ctx, const mpg_rollout_params* p, const float* obs,
     const size_t need = (size_t)ntiles * ta.store_steps * tc::SLOT_BYTES;
     if (!tc_ensure_store(ctx->tc, need)) return fail(ctx, MPG_ERR_CUDA, "cudaMalloc of the dW operand store failed%s");
     ta.store = ctx->tc.store;
+    ta.prof = ctx->prof;
     CUDA_OK(ctx, cudaMemsetAsync(ctx->partial, 0, (size_t)ctx->sms * ctx->partial_stride * sizeof(float), st));
     if (ctx->timing) cudaEventRecord(ctx->ev0, st);
     CUDA_OK(ctx, tc_launch_rollout<true>(ctx->cfg.env, ta, grid, st));

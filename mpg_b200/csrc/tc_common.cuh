@@ -158,8 +158,10 @@ constexpr int ACT_SPLIT = 4 * ACT_BLOCK;      // 256 features: 64 KB per split (
 __device__ __forceinline__ uint32_t act_chunk_off(int r, int cc) {
   return (uint32_t)((cc >> 3) * ACT_BLOCK + (r >> 3) * 1024 + (r & 7) * 128 + (((cc & 7) ^ (r & 7)) << 4));
 }
-// store 8 consecutive features (fp32) of row r as hi / lo bf16 chunks
-__device__ __forceinline__ void act_store8(uint8_t* act_hi, uint8_t* act_lo, int r, int cc, const float* x) {
+// store 8 consecutive features (fp32) of row r as hi / lo bf16 chunks; when `gimg` is given the same two
+// chunks also go to the global copy of the image (dW operand store, identical layout)
+__device__ __forceinline__ void act_store8(uint8_t* act_hi, uint8_t* act_lo, int r, int cc, const float* x,
+                                           uint8_t* gimg = nullptr) {
   uint4 h, l;
   split2(x[0], x[1], h.x, l.x);
   split2(x[2], x[3], h.y, l.y);
@@ -168,6 +170,10 @@ __device__ __forceinline__ void act_store8(uint8_t* act_hi, uint8_t* act_lo, int
   const uint32_t off = act_chunk_off(r, cc);
   *reinterpret_cast<uint4*>(act_hi + off) = h;
   *reinterpret_cast<uint4*>(act_lo + off) = l;
+  if (gimg) {
+    *reinterpret_cast<uint4*>(gimg + off) = h;
+    *reinterpret_cast<uint4*>(gimg + ACT_SPLIT + off) = l;
+  }
 }
 // INTERLEAVE K-major image of R rows x 16 elements: byte offset of the 16-byte chunk (k half kh) of row r
 __device__ __forceinline__ uint32_t il_chunk_off(int r, int kh) { return (uint32_t)((r >> 3) * 256 + kh * 128 + (r & 7) * 16); }

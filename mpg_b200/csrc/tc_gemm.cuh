@@ -22,16 +22,17 @@ constexpr int EPI_WARPS = MPG_EPI_WARPS;                 // 4 per TMEM lane quad
 constexpr int EPI_THREADS = EPI_WARPS * 32;
 constexpr int CTA_THREADS = EPI_THREADS + 64;  // + producer warp + mma warp
 constexpr int COLS_PER_WARP = 256 / (EPI_WARPS / 4);
-constexpr int STAGE_BYTES = 32768;            // ring slot
-constexpr int NSLOT = 2;
+constexpr int STAGE_BYTES = 16384;            // ring slot: one split (hi or lo) of a 128-row x 64-k weight block
+constexpr int NSLOT = 4;                      // 3 loads in flight while one slot is consumed
+constexpr int BIG_IMAGE_BYTES = 16 * STAGE_BYTES;
 constexpr int TMEM_COLS = 512;
 constexpr int TM_Z1 = 0, TM_WORK = 256;       // TMEM column regions
 
 // shared memory map (bytes, 1024-aligned base)
 struct SmemMap {
   static constexpr int ACT = 0;                               // activation image hi|lo: 128 KB
-  static constexpr int RING = ACT + 2 * ACT_SPLIT;            // 2 x 32 KB
-  static constexpr int PIMG = RING + NSLOT * STAGE_BYTES;     // [p|a|1] image hi|lo: 2 x 4 KB
+  static constexpr int RING = ACT + 2 * ACT_SPLIT;            // 4 x 16 KB
+  static constexpr int PIMG = RING + NSLOT * STAGE_BYTES;     // [p|a|1] image hi|lo: 2 x 4 KB (ring = 4 x 16 KB)
   static constexpr int MISC = PIMG + 8192;                    // fp32 scratch, see MiscF
   static constexpr int MISC_BYTES = 12288;
   static constexpr int BARS = MISC + MISC_BYTES;              // mbarriers + tmem pointer
@@ -60,39 +61,62 @@ enum Role { ROLE_EPI = 0, ROLE_PRODUCER = 1, ROLE_MMA = 2 };
 // ---- producer: stream `nstages` stages of `bytes` each ------------------------------------------------
 __device__ __forceinline__ void produce(Bars* b, uint8_t* ring, Sync& s, const uint8_t* gsrc, int nstages, uint32_t bytes) {
   for (int i = 0; i < nstages; ++i, ++s.stage) {
-    const uint32_t slot = s.stage & 1, par = (s.stage >> 1) & 1;
+    const uint32_t slot = s.stage & (NSLOT - 1), par = (s.stage / NSLOT) & 1;
     mbar_wait(&b->empty[slot], par ^ 1);
     mbar_expect_tx(&b->full[slot], bytes);
     bulk_g2s(ring + slot * STAGE_BYTES, gsrc + (size_t)i * bytes, bytes, &b->full[slot]);
   }
 }
 
+// The ring is consumed in slot PAIRS (0,1) / (2,3) by the big GEMMs; single-stage GEMMs (first layer, input
+// gradient) pad their second slot with an empty stage so that every GEMM starts on an even slot and the
+// mbarrier phases of all four slots advance in lock step.
+__device__ __forceinline__ void produce_pad(Bars* b, Sync& s) {
+  const uint32_t slot = s.stage & (NSLOT - 1), par = (s.stage / NSLOT) & 1;
+  mbar_wait(&b->empty[slot], par ^ 1);
+  mbar_arrive(&b->full[slot]);
+  ++s.stage;
+}
+__device__ __forceinline__ void consume_pad(Bars* b, Sync& s) {
+  const uint32_t slot = s.stage & (NSLOT - 1), par = (s.stage / NSLOT) & 1;
+  mbar_wait(&b->full[slot], par);
+  umma_commit(&b->empty[slot]);
+  ++s.stage;
+}
+
 // ---- mma role ----------------------------------------------------------------------------------------
-// big GEMM: D[128 x 256] = ACT[128 x 256] . Wt^T, Wt image streamed as 8 stages ordered (k-block kb, n-half h):
-// stage = [hi: 128 rows x 128 B][lo: 128 rows x 128 B].  K-block kb is issued as soon as the epilogue has
-// published that 64-feature block of the activation image, so the UMMAs overlap the epilogue that produces A.
+// big GEMM: D[128 x 256] = ACT[128 x 256] . Wt^T.  The Wt image is streamed as 16 stages of 16 KB ordered
+// (k-block kb, split, n-half h); the two n-halves of a split land in ADJACENT ring slots (0,1 or 2,3), so one
+// N = 256 UMMA reads both (half the instruction count and 25 % less shared-memory operand traffic than two
+// N = 128 UMMAs).  K-block kb is issued as soon as the epilogue has published that 64-feature block of the
+// activation image, so the UMMAs overlap the epilogue that produces A.
 __device__ __forceinline__ void mma_big(Bars* b, uint32_t act_addr, uint32_t ring_addr, Sync& s, uint32_t d_tmem) {
-  constexpr uint32_t idesc = make_idesc(128, 128, 0, 0);
+  constexpr uint32_t idesc = make_idesc(128, 256, 0, 0);
   for (int kb = 0; kb < 4; ++kb) {
     mbar_wait(&b->a_blk[kb], s.g_cnt & 1);
     tc_fence_after();
-    for (int h = 0; h < 2; ++h, ++s.stage) {
-      const uint32_t slot = s.stage & 1, par = (s.stage >> 1) & 1;
+    const uint64_t dah = make_desc(act_addr + kb * ACT_BLOCK, 16, 1024, LAYOUT_SW128);
+    const uint64_t dal = make_desc(act_addr + ACT_SPLIT + kb * ACT_BLOCK, 16, 1024, LAYOUT_SW128);
+#pragma unroll
+    for (int sp = 0; sp < 2; ++sp) {
+      const uint32_t slot = s.stage & (NSLOT - 1), par = (s.stage / NSLOT) & 1;   // slot is 0 or 2
       mbar_wait(&b->full[slot], par);
+      mbar_wait(&b->full[slot + 1], par);
       tc_fence_after();
-      const uint32_t bbase = ring_addr + slot * STAGE_BYTES;
+      const uint64_t db = make_desc(ring_addr + slot * STAGE_BYTES, 16, 1024, LAYOUT_SW128);
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks) {
-        const uint32_t a_hi = act_addr + kb * ACT_BLOCK + ks * 32, a_lo = a_hi + ACT_SPLIT;
-        const uint32_t b_hi = bbase + ks * 32, b_lo = b_hi + 16384;
-        const uint64_t dah = make_desc(a_hi, 16, 1024, LAYOUT_SW128), dal = make_desc(a_lo, 16, 1024, LAYOUT_SW128);
-        const uint64_t dbh = make_desc(b_hi, 16, 1024, LAYOUT_SW128), dbl = make_desc(b_lo, 16, 1024, LAYOUT_SW128);
-        const uint32_t d = d_tmem + h * 128;
-        umma_bf16(d, dah, dbh, idesc, (kb | ks) ? 1u : 0u);
-        umma_bf16(d, dal, dbh, idesc, 1u);
-        umma_bf16(d, dah, dbl, idesc, 1u);
+        const uint64_t ko = (uint64_t)(ks * 2);          // +32 bytes along K inside the 128-byte swizzle atom
+        if (sp == 0) {
+          umma_bf16(d_tmem, dah + ko, db + ko, idesc, (kb | ks) ? 1u : 0u);   // a_hi . b_hi
+          umma_bf16(d_tmem, dal + ko, db + ko, idesc, 1u);                    // a_lo . b_hi
+        } else {
+          umma_bf16(d_tmem, dah + ko, db + ko, idesc, 1u);                    // a_hi . b_lo
+        }
       }
       umma_commit(&b->empty[slot]);
+      umma_commit(&b->empty[slot + 1]);
+      s.stage += 2;
     }
   }
   ++s.g_cnt;
@@ -103,7 +127,7 @@ __device__ __forceinline__ void mma_l1(Bars* b, uint32_t p_addr, uint32_t ring_a
   constexpr uint32_t idesc = make_idesc(128, 256, 0, 0);
   mbar_wait(&b->a_full, s.a_cnt & 1);
   ++s.a_cnt;
-  const uint32_t slot = s.stage & 1, par = (s.stage >> 1) & 1;
+  const uint32_t slot = s.stage & (NSLOT - 1), par = (s.stage / NSLOT) & 1;
   mbar_wait(&b->full[slot], par);
   tc_fence_after();
   const uint32_t bbase = ring_addr + slot * STAGE_BYTES;
@@ -114,12 +138,13 @@ __device__ __forceinline__ void mma_l1(Bars* b, uint32_t p_addr, uint32_t ring_a
   umma_bf16(d_tmem, dah, dbl, idesc, 1u);
   umma_commit(&b->empty[slot]);
   ++s.stage;
+  consume_pad(b, s);
 }
 // input-gradient GEMM: D[128 x 16] = ACT[128 x 256] . W1nat^T (W1nat: 16 rows x 256), image streamed as ONE
 // stage = [hi: 4 k-blocks x (16 rows x 128 B)][lo: same] = 16 KB
 __device__ __forceinline__ void mma_in(Bars* b, uint32_t act_addr, uint32_t ring_addr, Sync& s, uint32_t d_tmem) {
   constexpr uint32_t idesc = make_idesc(128, 16, 0, 0);
-  const uint32_t slot = s.stage & 1, par = (s.stage >> 1) & 1;
+  const uint32_t slot = s.stage & (NSLOT - 1), par = (s.stage / NSLOT) & 1;
   const uint32_t bbase = ring_addr + slot * STAGE_BYTES;
   for (int kb = 0; kb < 4; ++kb) {
     mbar_wait(&b->a_blk[kb], s.g_cnt & 1);
@@ -138,6 +163,7 @@ __device__ __forceinline__ void mma_in(Bars* b, uint32_t act_addr, uint32_t ring
   }
   umma_commit(&b->empty[slot]);
   ++s.stage;
+  consume_pad(b, s);
   ++s.g_cnt;
 }
 
@@ -168,8 +194,8 @@ __device__ __forceinline__ void epi_wait_d(Bars* b, Sync& s) {
 template <int ROLE>
 __device__ __forceinline__ void gemm_issue(int kind, Bars* b, uint8_t* smem, Sync& s, const uint8_t* gimg, uint32_t d_tmem) {
   if (ROLE == ROLE_PRODUCER) {
-    if (kind == 0) produce(b, smem + SmemMap::RING, s, gimg, 8, STAGE_BYTES);
-    else produce(b, smem + SmemMap::RING, s, gimg, 1, 16384);
+    if (kind == 0) produce(b, smem + SmemMap::RING, s, gimg, 16, STAGE_BYTES);
+    else { produce(b, smem + SmemMap::RING, s, gimg, 1, 16384); produce_pad(b, s); }
   } else if (ROLE == ROLE_MMA) {
     const uint32_t base = smem_u32(smem);
     if (kind == 0) mma_big(b, base + SmemMap::ACT, base + SmemMap::RING, s, d_tmem);
@@ -224,10 +250,10 @@ __global__ void pack_big_image(const float* __restrict__ src, int rs, int cs, ui
   uint4 h, l;
   split2(x[0], x[1], h.x, l.x); split2(x[2], x[3], h.y, l.y); split2(x[4], x[5], h.z, l.z); split2(x[6], x[7], h.w, l.w);
   const int hh = row >> 7, rr = row & 127, kb = cc >> 3, c = cc & 7;
-  const size_t stage = (size_t)(kb * 2 + hh) * STAGE_BYTES;   // streamed in (k-block, n-half) order
+  const size_t stage = (size_t)(kb * 4 + hh) * STAGE_BYTES;   // streamed in (k-block, split, n-half) order
   const uint32_t off = (rr >> 3) * 1024 + (rr & 7) * 128 + ((c ^ (rr & 7)) << 4);
   *reinterpret_cast<uint4*>(img + stage + off) = h;
-  *reinterpret_cast<uint4*>(img + stage + 16384 + off) = l;
+  *reinterpret_cast<uint4*>(img + stage + 2 * STAGE_BYTES + off) = l;
 }
 // first-layer image: value(n, k) = k < in_dim ? W1[k][n] : (k == bias_k ? b1[n] : 0); 256 rows x 16 k,
 // INTERLEAVE K-major: [hi 8 KB | lo 8 KB]

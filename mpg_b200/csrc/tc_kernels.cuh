@@ -43,6 +43,7 @@ struct TcArgs {
   float* act_ckpt;          // [n_list][M*rows][A] actions at the list steps (for the Q input gradient)
   uint8_t* store;           // dW operand store: [tile][step][SLOT_BYTES]
   int store_steps;          // steps recorded per tile: horizon+1 (full BPTT) or 1 (first action only)
+  long long* prof;          // optional: clock64 timestamps of one backward step of CTA 0 (debug / DESIGN.md timeline)
 };
 
 // fp32 scratch in shared memory
@@ -81,15 +82,15 @@ __device__ __forceinline__ void act_load8(const uint8_t* act_hi, const uint8_t* 
 // the activation image is complete (and published to the MMA warp) after 1/4 of the epilogue.
 
 // z1 (TMEM, bias folded in) -> h1 image
-__device__ MPG_EPI_INLINE void epi_hidden1_blocks(Bars* b, uint32_t tm_lane, uint8_t* act, int row, int hc) {
+__device__ MPG_EPI_INLINE void epi_hidden1_blocks(Bars* b, uint32_t tm_lane, uint8_t* act, int row, int hc, uint8_t* gimg) {
   for (int kb = 0; kb < 4; ++kb) {
     const int c0 = kb * 64 + hc * 16;
     float v[16];
     tmem_ld16(tm_lane + c0, v);
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = elu_fast(v[i]);
-    act_store8(act, act + ACT_SPLIT, row, c0 >> 3, v);
-    act_store8(act, act + ACT_SPLIT, row, (c0 >> 3) + 1, v + 8);
+    act_store8(act, act + ACT_SPLIT, row, c0 >> 3, v, gimg);
+    act_store8(act, act + ACT_SPLIT, row, (c0 >> 3) + 1, v + 8, gimg);
     epi_block_done(b, kb);
   }
 }
@@ -110,7 +111,7 @@ __device__ MPG_EPI_INLINE void epi_hidden2(uint32_t tm_lane, const float* b2, co
 }
 // same, and keep h2 as an image (backward pass: delta2 and the dW3 operand are derived from it)
 __device__ MPG_EPI_INLINE void epi_hidden2_img(uint32_t tm_lane, const float* b2, const float* W3, uint8_t* act, int row,
-                                               int hc, float& p0, float& p1) {
+                                               int hc, float& p0, float& p1, uint8_t* gimg) {
   p0 = 0.f; p1 = 0.f;
   for (int kb = 0; kb < 4; ++kb) {
     const int c0 = kb * 64 + hc * 16;
@@ -123,12 +124,13 @@ __device__ MPG_EPI_INLINE void epi_hidden2_img(uint32_t tm_lane, const float* b2
       p0 = fmaf(v[i], w.x, p0);
       p1 = fmaf(v[i], w.y, p1);
     }
-    act_store8(act, act + ACT_SPLIT, row, c0 >> 3, v);
-    act_store8(act, act + ACT_SPLIT, row, (c0 >> 3) + 1, v + 8);
+    act_store8(act, act + ACT_SPLIT, row, c0 >> 3, v, gimg);
+    act_store8(act, act + ACT_SPLIT, row, (c0 >> 3) + 1, v + 8, gimg);
   }
 }
 // delta2 = (delta3 W3^T) * elu'(h2), h2 read back from its image and overwritten in place by delta2
-__device__ MPG_EPI_INLINE void epi_delta2_blocks(Bars* b, const float* W3, float d30, float d31, uint8_t* act, int row, int hc) {
+__device__ MPG_EPI_INLINE void epi_delta2_blocks(Bars* b, const float* W3, float d30, float d31, uint8_t* act, int row, int hc,
+                                                 uint8_t* gimg) {
   for (int kb = 0; kb < 4; ++kb) {
     const int c0 = kb * 64 + hc * 16;
     float v[16];
@@ -140,14 +142,14 @@ __device__ MPG_EPI_INLINE void epi_delta2_blocks(Bars* b, const float* W3, float
       const float g = fmaf(d30, w.x, d31 * w.y);
       v[i] = g * (v[i] > 0.f ? 1.f : v[i] + 1.f);     // elu'(z) expressed through the output h2
     }
-    act_store8(act, act + ACT_SPLIT, row, c0 >> 3, v);
-    act_store8(act, act + ACT_SPLIT, row, (c0 >> 3) + 1, v + 8);
+    act_store8(act, act + ACT_SPLIT, row, c0 >> 3, v, gimg);
+    act_store8(act, act + ACT_SPLIT, row, (c0 >> 3) + 1, v + 8, gimg);
     epi_block_done(b, kb);
   }
 }
 // delta1 = g_h1 (TMEM work) * elu'(z1) (TMEM z1) -> delta1 image
 __device__ MPG_EPI_INLINE void epi_delta1_blocks(Bars* b, bool publish, uint32_t tm_work, uint32_t tm_z1, uint8_t* act,
-                                                 int row, int hc) {
+                                                 int row, int hc, uint8_t* gimg) {
   for (int kb = 0; kb < 4; ++kb) {
     const int c0 = kb * 64 + hc * 16;
     float g[16], z[16];
@@ -155,13 +157,13 @@ __device__ MPG_EPI_INLINE void epi_delta1_blocks(Bars* b, bool publish, uint32_t
     tmem_ld16(tm_z1 + c0, z);
 #pragma unroll
     for (int i = 0; i < 16; ++i) g[i] *= (z[i] > 0.f ? 1.f : exp_fast(z[i]));
-    act_store8(act, act + ACT_SPLIT, row, c0 >> 3, g);
-    act_store8(act, act + ACT_SPLIT, row, (c0 >> 3) + 1, g + 8);
+    act_store8(act, act + ACT_SPLIT, row, c0 >> 3, g, gimg);
+    act_store8(act, act + ACT_SPLIT, row, (c0 >> 3) + 1, g + 8, gimg);
     if (publish) epi_block_done(b, kb);
   }
 }
 // [x0..x15] -> INTERLEAVE image row (hi | lo 4 KB apart)
-__device__ __forceinline__ void write_row16(uint8_t* img, int row, const float* x) {
+__device__ __forceinline__ void write_row16(uint8_t* img, int row, const float* x, uint8_t* gimg = nullptr) {
 #pragma unroll
   for (int kh = 0; kh < 2; ++kh) {
     uint4 h, l;
@@ -169,8 +171,14 @@ __device__ __forceinline__ void write_row16(uint8_t* img, int row, const float* 
     split2(x[kh * 8 + 2], x[kh * 8 + 3], h.y, l.y);
     split2(x[kh * 8 + 4], x[kh * 8 + 5], h.z, l.z);
     split2(x[kh * 8 + 6], x[kh * 8 + 7], h.w, l.w);
-    *reinterpret_cast<uint4*>(img + il_chunk_off(row, kh)) = h;
-    *reinterpret_cast<uint4*>(img + 4096 + il_chunk_off(row, kh)) = l;
+    if (img) {
+      *reinterpret_cast<uint4*>(img + il_chunk_off(row, kh)) = h;
+      *reinterpret_cast<uint4*>(img + 4096 + il_chunk_off(row, kh)) = l;
+    }
+    if (gimg) {
+      *reinterpret_cast<uint4*>(gimg + il_chunk_off(row, kh)) = h;
+      *reinterpret_cast<uint4*>(gimg + 4096 + il_chunk_off(row, kh)) = l;
+    }
   }
 }
 
@@ -211,6 +219,11 @@ __device__ __forceinline__ void run_rollout(const TcArgs& A, uint8_t* smem, Bars
   const bool store_dw = BWD && A.store != nullptr;
   Sync sy;
   float db3acc[2] = {0.f, 0.f};
+  int prof_t = -1;   // step being traced
+  auto stamp = [&](int id) {
+    if (A.prof && blockIdx.x == 0 && prof_t >= 0 && ((ROLE == ROLE_EPI && tid == 0) || ROLE == ROLE_MMA))
+      A.prof[(ROLE == ROLE_MMA ? 32 : 0) + id] = clock64();
+  };
 
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int grow = tile * ACT_ROWS + row;
@@ -229,7 +242,7 @@ __device__ __forceinline__ void run_rollout(const TcArgs& A, uint8_t* smem, Bars
     float rsum = 0.f, gpow = 1.f;
 
     // [sigma*obs(s) | act | 0.. | 1] -> p image
-    auto write_pimg = [&](const float* st, const float* act_or_null) {
+    auto write_pimg = [&](const float* st, const float* act_or_null, uint8_t* gimg = nullptr) {
       float x[16], o[MPG_MAX_OBS];
 #pragma unroll
       for (int i = 0; i < 16; ++i) x[i] = 0.f;
@@ -238,26 +251,34 @@ __device__ __forceinline__ void run_rollout(const TcArgs& A, uint8_t* smem, Bars
       if (act_or_null)
         for (int j = 0; j < NA; ++j) x[a.obs_dim + j] = act_or_null[j];
       x[BIAS_K] = 1.f;
-      write_row16(p_img, row, x);
+      write_row16(p_img, row, x, gimg);
     };
     // policy forward on the current p image: returns pre-activations of the head for the row thread.
     // The layer-2 UMMAs are issued K-block by K-block while the epilogue is still producing h1.
     auto policy_forward = [&](float* zpre, bool bwd_pass, bool rec_, uint8_t* slot) {
+      if (ROLE == ROLE_MMA && bwd_pass) stamp(0);
       gemm_issue<ROLE>(1, b, smem, sy, A.pol.l1, tm_z1);
+      if (ROLE == ROLE_MMA && bwd_pass) stamp(1);
       gemm_issue<ROLE>(0, b, smem, sy, A.pol.big_fwd, tm_work);
+      if (ROLE == ROLE_MMA && bwd_pass) stamp(2);
       if (ROLE == ROLE_EPI) {
         epi_wait_d(b, sy);                                   // z1
-        epi_hidden1_blocks(b, tm_z1 + lane_off, act_img, row, hc);
+        if (bwd_pass) stamp(2);
+        if (rec_) store_wait(elected);                       // previous step's delta1 image has been read out
+        epi_hidden1_blocks(b, tm_z1 + lane_off, act_img, row, hc, nullptr);
+        if (bwd_pass) stamp(3);
         if (rec_) store_image(elected, slot + SLOT_H1, act_img, 2 * ACT_SPLIT);
         epi_wait_d(b, sy);                                   // z2 (all layer-2 UMMAs done: h1 image free)
+        if (bwd_pass) stamp(4);
         float p0, p1;
         if (bwd_pass) {
           if (rec_) store_wait(elected);                     // h1 image has been read out
-          epi_hidden2_img(tm_work + lane_off, mf->b2p, mf->W3p, act_img, row, hc, p0, p1);
+          epi_hidden2_img(tm_work + lane_off, mf->b2p, mf->W3p, act_img, row, hc, p0, p1, nullptr);
           if (rec_) store_image(elected, slot + SLOT_H2, act_img, 2 * ACT_SPLIT);
         } else {
           epi_hidden2(tm_work + lane_off, mf->b2p, mf->W3p, hc, p0, p1);
         }
+        if (bwd_pass) stamp(5);
         mf->part[(hc * 2 + 0) * ACT_ROWS + row] = p0;
         mf->part[(hc * 2 + 1) * ACT_ROWS + row] = p1;
         epi_bar();
@@ -276,10 +297,10 @@ __device__ __forceinline__ void run_rollout(const TcArgs& A, uint8_t* smem, Bars
       gemm_issue<ROLE>(0, b, smem, sy, A.q.big_fwd, tm_work);
       if (ROLE == ROLE_EPI) {
         epi_wait_d(b, sy);
-        epi_hidden1_blocks(b, tm_z1 + lane_off, act_img, row, hc);
+        epi_hidden1_blocks(b, tm_z1 + lane_off, act_img, row, hc, nullptr);
         epi_wait_d(b, sy);
         float p0, p1;
-        if (with_img) epi_hidden2_img(tm_work + lane_off, mf->b2q, mf->W3q, act_img, row, hc, p0, p1);
+        if (with_img) epi_hidden2_img(tm_work + lane_off, mf->b2q, mf->W3q, act_img, row, hc, p0, p1, nullptr);
         else epi_hidden2(tm_work + lane_off, mf->b2q, mf->W3q, hc, p0, p1);
         mf->part[(hc * 2 + 0) * ACT_ROWS + row] = p0;
         epi_bar();
@@ -357,6 +378,8 @@ __device__ __forceinline__ void run_rollout(const TcArgs& A, uint8_t* smem, Bars
         for (int i = 0; i < t; ++i) gp *= a.gamma;
         const bool want_dw = a.full_bptt || t == 0;
         const bool rec = store_dw && want_dw;
+        prof_t = (tile == (int)blockIdx.x && t == a.horizon - 1) ? t : -1;
+        stamp(0);
         uint8_t* slot = rec ? A.store + ((size_t)tile * A.store_steps + (a.full_bptt ? t : 0)) * SLOT_BYTES : nullptr;
         float g_a[NA], g_s[S], act[NA], zpre[NA];
 #pragma unroll
@@ -372,6 +395,7 @@ __device__ __forceinline__ void run_rollout(const TcArgs& A, uint8_t* smem, Bars
         for (int k = 0; k < a.n_list; ++k) if (a.list[k] == t) kidx = k;
         // ---- Q input gradient at the list steps: upstream c w_k gamma^t on Q1(p_t, a_t) ----
         if (kidx >= 0 && a.has_q && a.list_w[kidx] != 0.f) {
+          if (ROLE == ROLE_EPI && store_dw) store_wait(elected);   // the previous step's delta1 store still reads ACT
           if (rowthread) {
             float ak[NA];
 #pragma unroll
@@ -385,12 +409,12 @@ __device__ __forceinline__ void run_rollout(const TcArgs& A, uint8_t* smem, Bars
           }
           gemm_issue<ROLE>(0, b, smem, sy, A.q.big_dx, tm_work);  // g_h1q, K-blocks issued as delta2 blocks appear
           if (ROLE == ROLE_EPI) {
-            epi_delta2_blocks(b, mf->W3q, mf->d3s[row], 0.f, act_img, row, hc);
+            epi_delta2_blocks(b, mf->W3q, mf->d3s[row], 0.f, act_img, row, hc, nullptr);
             epi_wait_d(b, sy);
           }
           gemm_issue<ROLE>(2, b, smem, sy, A.q.in, tm_z1);        // g_in -> 16 columns of the z1 region
           if (ROLE == ROLE_EPI) {
-            epi_delta1_blocks(b, true, tm_work + lane_off, tm_z1 + lane_off, act_img, row, hc);
+            epi_delta1_blocks(b, true, tm_work + lane_off, tm_z1 + lane_off, act_img, row, hc, nullptr);
             epi_wait_d(b, sy);
           }
           if (rowthread) {
@@ -406,8 +430,7 @@ __device__ __forceinline__ void run_rollout(const TcArgs& A, uint8_t* smem, Bars
           }
         }
         // ---- policy recompute ----
-        if (rowthread) write_pimg(s, nullptr);
-        if (ROLE == ROLE_EPI && rec) store_image(elected, slot + SLOT_P, p_img, 8192);
+        if (rowthread) write_pimg(s, nullptr, rec ? slot + SLOT_P : nullptr);
         policy_forward(zpre, true, rec, slot);
         if (rowthread) {
 #pragma unroll
@@ -433,37 +456,40 @@ __device__ __forceinline__ void run_rollout(const TcArgs& A, uint8_t* smem, Bars
 #pragma unroll
               for (int i = 0; i < 16; ++i) x[i] = 0.f;
               x[0] = d3[0]; x[1] = d3[1];
-              if (rec) write_row16(d3_img, row, x);
+              if (rec) write_row16(nullptr, row, x, slot + SLOT_D3);
               float s0 = d3[0], s1 = d3[1];
 #pragma unroll
               for (int o = 16; o > 0; o >>= 1) { s0 += __shfl_xor_sync(0xffffffffu, s0, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o); }
               if (lane == 0) { mf->wsum[warp * 2] = s0; mf->wsum[warp * 2 + 1] = s1; }
             }
           }
-          if (rec) {
-            store_wait(elected);                            // previous image (h2 or h1) read out
-            store_image(elected, slot + SLOT_D3, d3_img, 8192);
-          } else {
-            epi_bar();
-          }
+          if (rec) store_wait(elected);                     // h2 image read out before delta2 overwrites it (has epi_bar)
+          else epi_bar();
           if (tid == 0 && want_dw) {
             db3acc[0] += (mf->wsum[0] + mf->wsum[2]) + (mf->wsum[4] + mf->wsum[6]);
             db3acc[1] += (mf->wsum[1] + mf->wsum[3]) + (mf->wsum[5] + mf->wsum[7]);
           }
         }
         // ---- delta2 image (in place over h2) feeding the dX UMMAs block by block ----
+        if (ROLE == ROLE_MMA) stamp(3);
         gemm_issue<ROLE>(0, b, smem, sy, A.pol.big_dx, tm_work);   // g_h1
+        if (ROLE == ROLE_MMA) stamp(4);
         if (ROLE == ROLE_EPI) {
-          epi_delta2_blocks(b, mf->W3p, mf->d3s[row], mf->d3s[ACT_ROWS + row], act_img, row, hc);
+          stamp(6);
+          epi_delta2_blocks(b, mf->W3p, mf->d3s[row], mf->d3s[ACT_ROWS + row], act_img, row, hc, nullptr);
+          stamp(7);
           if (rec) store_image(elected, slot + SLOT_D2, act_img, 2 * ACT_SPLIT);
           epi_wait_d(b, sy);                                       // g_h1 complete, delta2 image consumed
+          stamp(8);
         }
         if (t > 0) gemm_issue<ROLE>(2, b, smem, sy, A.pol.in, tm_z1);   // g_p
         if (ROLE == ROLE_EPI) {
           if (rec) store_wait(elected);                            // delta2 image read out before it is overwritten
-          epi_delta1_blocks(b, t > 0, tm_work + lane_off, tm_z1 + lane_off, act_img, row, hc);
+          epi_delta1_blocks(b, t > 0, tm_work + lane_off, tm_z1 + lane_off, act_img, row, hc, nullptr);
+          stamp(9);
           if (rec) store_image(elected, slot + SLOT_D1, act_img, 2 * ACT_SPLIT);
           if (t > 0) epi_wait_d(b, sy);
+          stamp(10);
         }
         if (t > 0 && rowthread) {
           float gin[16];
@@ -476,19 +502,19 @@ __device__ __forceinline__ void run_rollout(const TcArgs& A, uint8_t* smem, Bars
             E::obs_grad_to_state(s, go, a.nfd, lam);
           }
         }
-        if (ROLE == ROLE_EPI && rec) store_wait(elected);    // delta1 image read out before the next step
+        stamp(11);
       }
     }
   }
   if (ROLE == ROLE_EPI) {
     tc_fence_before();
+    if (elected) bulk_wait_all();
     if (BWD && tid == 0) {
       const GradLayout L(A.pol.in_dim, A.pol.out_dim);
       float* partial = a.partial + (size_t)blockIdx.x * a.partial_stride;
       partial[L.ob3 + 0] = db3acc[0];
       if (NA > 1) partial[L.ob3 + 1] = db3acc[1];
     }
-    if (elected) bulk_wait_all();
   }
 }
 

@@ -32,10 +32,10 @@ inline bool tc_init(TcState& t, const mpg_config& cfg, int /*sms*/, size_t& ws_b
     ws_bytes += n;
     return true;
   };
-  bool ok = alloc((void**)&t.scratch_img, 8 * tc::STAGE_BYTES)
+  bool ok = alloc((void**)&t.scratch_img, tc::BIG_IMAGE_BYTES)
             && alloc((void**)&t.act_ckpt, (size_t)MPG_MAX_LIST * cfg.max_rows * MAX_A * sizeof(float));
   for (int n = 0; n < MPG_NUM_NETS && ok; ++n)
-    ok = alloc((void**)&t.nets[n].big_fwd, 8 * tc::STAGE_BYTES) && alloc((void**)&t.nets[n].big_dx, 8 * tc::STAGE_BYTES)
+    ok = alloc((void**)&t.nets[n].big_fwd, tc::BIG_IMAGE_BYTES) && alloc((void**)&t.nets[n].big_dx, tc::BIG_IMAGE_BYTES)
          && alloc((void**)&t.nets[n].l1, 16384) && alloc((void**)&t.nets[n].in, 16384);
   if (!ok) return false;
   const int sm = tc::SM_TOTAL + 1024;

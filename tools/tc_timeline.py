@@ -1,0 +1,21 @@
+import sys, ctypes, numpy as np, torch
+sys.path.insert(0,'.')
+from mpg_b200 import synthetic, _lib
+from mpg_b200.config import default_args
+from mpg_b200.policy import PolicyWithQs
+B=65536
+args=default_args('NADP','PathTracking-v0',replay_batch_size=B)
+pol=PolicyWithQs(**vars(args)); pol.set_weights(synthetic.make_policy_with_qs_weights(1,6,2,256,double_q=False))
+e=pol.engine; e.set_backend(1)
+obs=e.dev(synthetic.make_obs(np.random.default_rng(2),'PathTracking-v0',B))
+buf=torch.zeros(64,dtype=torch.int64,device='cuda')
+for full in (1,0):
+    e.lib.mpg_set_profile_buffer(e.h, ctypes.c_void_p(buf.data_ptr()))
+    for _ in range(3): e.policy_grad(obs,[0,25],[0.0,1.0],full_bptt=bool(full),use_philox=True)
+    torch.cuda.synchronize()
+    t=buf.cpu().numpy()
+    ep=t[:12]-t[0]; mm=t[32:37]-t[0]
+    names=['start','-','z1 ready','E1 done','z2 ready','E2 done','d3 ready','Ed2 done','g_h1 ready','Ed1 done','g_p ready','step end']
+    print('full_bptt',full)
+    for i,n in enumerate(names): print(f'  epi {n:12s} {ep[i]:8d}')
+    print('  mma: fwd-start',mm[0],'l1-issued',mm[1],'big-fwd-done-issue',mm[2],'dx-start',mm[3],'dx-issued',mm[4])
