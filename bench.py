@@ -275,9 +275,24 @@ def main():
     peak_tf = float(peaks.get('bf16_tflops_sustained', 1400.0))
     sm_mhz = (clocks or {}).get('sm_mhz') or 1965.0
     ffma_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
+    traffic = None   # dram__bytes_read.sum + dram__bytes_write.sum of the same kernel, one ncu --set full capture
+    prof = os.path.join(ROOT, 'profiles', 'r1_tc_rollout_kernel_ncu_full.csv' if backend == 'tc' else
+                        'r1_ffma_rollout_kernel_ncu_full.csv')
+    try:
+        mult = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
+        tot = 0.0
+        for line in open(prof):
+            c = line.strip().split(',')
+            if c[0] in ('dram__bytes_read.sum', 'dram__bytes_write.sum'):
+                tot += float(c[2]) * mult[c[1]]
+        traffic = tot * (rows / float(ROWS_PER_GPU)) if tot > 0 else None
+    except Exception:
+        traffic = None
     roofline = {
         'bound': 'tensor', 'achieved': achieved_tf, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': achieved_tf / peak_tf,
-        'traffic': None,
+        'traffic': traffic,
+        'traffic_note': 'bytes per launch from profiles/ (ncu --set full of the same kernel at B=65536); algorithmic '
+                        'bytes are 56 B/state-step = 92 MB; the tc path adds the dW operand store (4 KB/state-step)',
         'kernel': 'rollout_kernel<PathTracking,BWD> (fused forward rollout + BPTT, %s backend)' % backend,
         'kernel_ms': k_ms, 'algorithmic_flop_per_state_step': FLOP_PER_STATE_STEP,
         'peak_source': ('MEASURED_PEAKS.json bf16_tflops_sustained (of measured)' if peaks else 'fallback 1.4 PFLOP/s (of fallback)'),

@@ -159,6 +159,16 @@ int mpg_compute_rewards(mpg_ctx* ctx, int rows, const float* state, const float*
                         void* stream);
 int mpg_state_dim(const mpg_ctx* ctx);
 
+/* ---- optimiser step on device-resident weights --------------------- */
+/* One Keras-Adam step on the flat weights of `net` (PolicyWithQs.apply_gradients, policy.py:123-156; keras
+ * OptimizerV2 Adam: m = b1 m + (1-b1) g, v = b2 v + (1-b2) g^2, w -= lr sqrt(1-b2^t)/(1-b1^t) m / (sqrt(v) + eps)).
+ *   grad: flat gradient in Keras order (device);  lr: already-decayed learning rate (PolynomialDecay is evaluated
+ *   by the caller);  step: t = optimizer.iterations + 1.  Kernel-layout copies of the weights are re-packed. */
+int mpg_adam_step(mpg_ctx* ctx, int net, const float* grad, float lr, int64_t step, float beta1, float beta2, float eps,
+                  void* stream);
+/* Polyak target update (policy.py:158-171): dst = tau * src + (1 - tau) * dst, then re-pack dst */
+int mpg_polyak_update(mpg_ctx* ctx, int src_net, int dst_net, float tau, void* stream);
+
 /* ---- tf.clip_by_global_norm (mpg_learner.py:415-431, nadp.py:220-225) --------------------- */
 /* in place over one net's flat gradient; norm_out[0] = pre-clip global norm */
 int mpg_clip_global_norm(mpg_ctx* ctx, float* grad, int n, float clip, float* norm_out, void* stream);

@@ -17,7 +17,7 @@ SYMBOLS = [
     'mpg_returns_tile_mean', 'mpg_q_grad', 'mpg_policy_forward', 'mpg_q_forward', 'mpg_q_target', 'mpg_td_error',
     'mpg_model_reset', 'mpg_model_step', 'mpg_model_step_bwd', 'mpg_compute_rewards', 'mpg_state_dim',
     'mpg_clip_global_norm', 'mpg_philox_noise', 'mpg_launch_count', 'mpg_set_backend', 'mpg_get_backend',
-    'mpg_set_timing', 'mpg_kernel_ms', 'mpg_tc_selftest', 'mpg_set_profile_buffer',
+    'mpg_set_timing', 'mpg_kernel_ms', 'mpg_tc_selftest', 'mpg_set_profile_buffer', 'mpg_adam_step', 'mpg_polyak_update',
 ]
 
 
@@ -85,6 +85,8 @@ def load():
         'mpg_kernel_ms': (f32, [vp]),
         'mpg_tc_selftest': (i32, [vp, i32, vp, vp, vp, i32, vp]),
         'mpg_set_profile_buffer': (i32, [vp, vp]),
+        'mpg_adam_step': (i32, [vp, i32, vp, f32, i64, f32, f32, f32, vp]),
+        'mpg_polyak_update': (i32, [vp, i32, i32, f32, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)  # AttributeError if the header and the library ever diverge

@@ -16,6 +16,8 @@ struct NetStore {
   float* W1p = nullptr;
   float* W2p = nullptr;
   float* W2Tp = nullptr;
+  float* adam_m = nullptr;   // Adam moments (allocated on the first optimiser step)
+  float* adam_v = nullptr;
   int in_dim = 0, out_dim = 0;
   bool set = false;
 };
@@ -75,6 +77,22 @@ __global__ void pack_kernel(const float* __restrict__ flat, int in_dim, int out_
   W2p[idx] = flat[L.oW2 + k * H + c];
   W2Tp[idx] = flat[L.oW2 + c * H + k];   // W2T[n=k][col c] = W2[c][k]
   if (k < in_dim) W1p[idx] = flat[L.oW1 + k * H + c];
+}
+
+__global__ void adam_kernel(float* __restrict__ w, float* __restrict__ m, float* __restrict__ v, const float* __restrict__ g,
+                            int n, float lr_t, float b1, float b2, float eps) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float gi = g[i];
+  const float mi = b1 * m[i] + (1.f - b1) * gi;
+  const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+  m[i] = mi; v[i] = vi;
+  w[i] -= lr_t * mi / (sqrtf(vi) + eps);
+}
+
+__global__ void polyak_kernel(float* __restrict__ dst, const float* __restrict__ src, int n, float tau) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = tau * src[i] + (1.f - tau) * dst[i];
 }
 
 __global__ void reduce_partials_kernel(const float* __restrict__ partial, size_t stride, int nparts, int n,
@@ -331,6 +349,7 @@ void mpg_destroy(mpg_ctx* c) {
   if (!c) return;
   for (int n = 0; n < MPG_NUM_NETS; ++n) {
     cudaFree(c->nets[n].flat); cudaFree(c->nets[n].W1p); cudaFree(c->nets[n].W2p); cudaFree(c->nets[n].W2Tp);
+    cudaFree(c->nets[n].adam_m); cudaFree(c->nets[n].adam_v);
   }
   cudaFree(c->ckpt); cudaFree(c->partial); cudaFree(c->loss_partial);
   if (c->ev0) { cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); }
@@ -355,6 +374,51 @@ int mpg_set_weights(mpg_ctx* ctx, int net, const float* const w[6], void* stream
   ns.set = true;
   return tc_pack_weights(ctx->tc, net, ns.flat, ns.in_dim, ns.out_dim, st) ? MPG_OK
                                                                            : fail(ctx, MPG_ERR_CUDA, "tc weight pack failed%s");
+}
+
+static int repack(mpg_ctx* ctx, int net, cudaStream_t st) {
+  NetStore& ns = ctx->nets[net];
+  pack_kernel<<<(H * H + 255) / 256, 256, 0, st>>>(ns.flat, ns.in_dim, ns.out_dim, ns.W1p, ns.W2p, ns.W2Tp);
+  ctx->launches++;
+  CUDA_OK(ctx, cudaGetLastError());
+  return tc_pack_weights(ctx->tc, net, ns.flat, ns.in_dim, ns.out_dim, st) ? MPG_OK
+                                                                           : fail(ctx, MPG_ERR_CUDA, "tc weight pack failed%s");
+}
+
+int mpg_adam_step(mpg_ctx* ctx, int net, const float* grad, float lr, int64_t step, float beta1, float beta2, float eps,
+                  void* stream) {
+  if (!ctx || !grad || step < 1) return fail(ctx, MPG_ERR_ARG, "bad argument to mpg_adam_step%s");
+  int rc = check_net(ctx, net);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  NetStore& ns = ctx->nets[net];
+  const int n = GradLayout(ns.in_dim, ns.out_dim).total;
+  if (!ns.adam_m) {
+    CUDA_OK(ctx, cudaMalloc(&ns.adam_m, n * sizeof(float)));
+    CUDA_OK(ctx, cudaMalloc(&ns.adam_v, n * sizeof(float)));
+    CUDA_OK(ctx, cudaMemsetAsync(ns.adam_m, 0, n * sizeof(float), st));
+    CUDA_OK(ctx, cudaMemsetAsync(ns.adam_v, 0, n * sizeof(float), st));
+  }
+  const double t = (double)step;
+  const float lr_t = (float)((double)lr * sqrt(1.0 - pow((double)beta2, t)) / (1.0 - pow((double)beta1, t)));
+  adam_kernel<<<(n + 255) / 256, 256, 0, st>>>(ns.flat, ns.adam_m, ns.adam_v, grad, n, lr_t, beta1, beta2, eps);
+  ctx->launches++;
+  CUDA_OK(ctx, cudaGetLastError());
+  return repack(ctx, net, st);
+}
+
+int mpg_polyak_update(mpg_ctx* ctx, int src_net, int dst_net, float tau, void* stream) {
+  int rc = check_net(ctx, src_net);
+  if (!rc) rc = check_net(ctx, dst_net);
+  if (rc) return rc;
+  NetStore &a = ctx->nets[src_net], &d = ctx->nets[dst_net];
+  if (a.in_dim != d.in_dim || a.out_dim != d.out_dim) return fail(ctx, MPG_ERR_ARG, "polyak: nets differ in shape%s");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int n = GradLayout(a.in_dim, a.out_dim).total;
+  polyak_kernel<<<(n + 255) / 256, 256, 0, st>>>(d.flat, a.flat, n, tau);
+  ctx->launches++;
+  CUDA_OK(ctx, cudaGetLastError());
+  return repack(ctx, dst_net, st);
 }
 
 int mpg_get_weights(mpg_ctx* ctx, int net, float* const w[6], void* stream) {

@@ -75,7 +75,7 @@ class Engine:
         if rows <= self.cfg.max_rows and horizon <= self.cfg.max_horizon:
             return
         backend = self.backend
-        saved = dict(self._weights)
+        saved = {net: self.get_net_weights(net) for net in self._weights}   # Adam moments are reset by a re-create
         self.close()
         self.cfg.max_rows = max(int(rows), self.cfg.max_rows)
         self.cfg.max_horizon = max(int(horizon), self.cfg.max_horizon)
@@ -145,7 +145,17 @@ class Engine:
         self._weights[net] = ts
 
     def get_net_weights(self, net):
-        return [t.detach().cpu().numpy() for t in self._weights[net]]
+        """Current weights of `net` read back from the handle (they change under mpg_adam_step / polyak)."""
+        ts = [torch.empty_like(t) for t in self._weights[net]]
+        arr = (ctypes.c_void_p * 6)(*[t.data_ptr() for t in ts])
+        self._check(self.lib.mpg_get_weights(self.h, net, arr, self.stream))
+        return [t.cpu().numpy() for t in ts]
+
+    def adam_step(self, net, grad, lr, step, beta1=0.9, beta2=0.999, eps=1e-7):
+        self._check(self.lib.mpg_adam_step(self.h, net, _ptr(grad), float(lr), int(step), beta1, beta2, eps, self.stream))
+
+    def polyak_update(self, src_net, dst_net, tau):
+        self._check(self.lib.mpg_polyak_update(self.h, src_net, dst_net, float(tau), self.stream))
 
     # ------------------------------------------------------------------ rollouts
     def _params(self, rows, M, horizon, rollout_list, list_w, full_bptt, q_net, policy_net, global_rows, row_offset,

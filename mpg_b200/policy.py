@@ -5,7 +5,8 @@ Kept: constructor keywords, get_weights / set_weights nested-list format
 (models + target_models, each [W1,b1,W2,b2,W3,b3] with Keras (in,out) kernels, policy.py:112-121),
 compute_action / compute_mode / compute_target_action / compute_Q1 / compute_Q2 / compute_Q1_target /
 compute_Q2_target on RAW-scaled ("processed") observations exactly like the reference.
-Not built here: Adam / Polyak target update / checkpoints -> apply_gradients raises.
+apply_gradients (policy.py:123-171) runs on the device-resident weights: Keras-Adam with PolynomialDecay
+learning rates, delayed policy update and Polyak targets. Checkpoints are not built.
 """
 import numpy as np
 import torch
@@ -33,6 +34,9 @@ class PolicyWithQs(object):
         self.policy_only, self.double_Q, self.target = policy_only, double_Q, target
         self.tau, self.delay_update, self.action_range = tau, delay_update, action_range
         self.deterministic_policy = True
+        self.value_lr_schedule = kwargs.get('value_lr_schedule') or [8e-5, 100000, 8e-6]
+        self.policy_lr_schedule = kwargs.get('policy_lr_schedule') or [3e-5, 100000, 3e-6]
+        self.opt_iterations = {}   # per-optimizer step counters (keras optimizer.iterations)
         rows = int(kwargs.get('replay_batch_size', 256)) * int(kwargs.get('M', 1))
         lists = list(kwargs.get('num_rollout_list_for_policy_update') or [25]) + \
             list(kwargs.get('num_rollout_list_for_q_estimation') or [])
@@ -73,9 +77,38 @@ class PolicyWithQs(object):
         for i, w in enumerate(weights):
             self.engine.set_net_weights(slots[i], w)
 
+    @staticmethod
+    def polynomial_decay(schedule, step):
+        """keras PolynomialDecay(initial, decay_steps, end), power 1, no cycle."""
+        init, decay_steps, end = schedule
+        frac = min(float(step), float(decay_steps)) / float(decay_steps)
+        return (init - end) * (1.0 - frac) + end
+
+    def _adam(self, slot, schedule, flat_grad):
+        it = self.opt_iterations.get(slot, 0)
+        self.engine.adam_step(slot, flat_grad, self.polynomial_decay(schedule, it), it + 1)
+        self.opt_iterations[slot] = it + 1
+
     def apply_gradients(self, iteration, grads):
-        raise NotImplementedError('optimiser step (Adam + Polyak targets, policy.py:123-171) is outside the hot path '
-                                  'of this build: SURVEY.md 8(f) next #2')
+        """PolicyWithQs.apply_gradients (policy.py:123-156). `grads`: the list compute_gradient returns (numpy,
+        Q1[,Q2],policy x [W1,b1,W2,b2,W3,b3]) or one flat device tensor in the same order (no host round trip)."""
+        e = self.engine
+        if isinstance(grads, torch.Tensor):
+            flat = grads.to(e.device, torch.float32).contiguous()
+        else:
+            flat = e.dev(np.concatenate([np.asarray(g, np.float32).ravel() for g in grads]))
+        q_slots = [s for s in self.model_slots if s != _lib.NET_POLICY]
+        pos = 0
+        for s in q_slots:                              # Q nets: every call
+            n = e.param_count(s)
+            self._adam(s, self.value_lr_schedule, flat[pos:pos + n])
+            pos += n
+        npol = e.param_count(_lib.NET_POLICY)
+        if self.policy_only or iteration % self.delay_update == 0:
+            self._adam(_lib.NET_POLICY, self.policy_lr_schedule, flat[pos:pos + npol])
+            if self.target_slots and not self.policy_only:
+                for src, dst in zip(self.model_slots, self.target_slots):   # update_*_target (policy.py:158-171)
+                    e.polyak_update(src, dst, self.tau)
 
     # -- forward passes (policy.py:173-241) --------------------------------------------------------
     def _raw(self, processed_obs):

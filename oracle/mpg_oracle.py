@@ -426,3 +426,52 @@ def open_loop(args, obs0, acts, noise, dtype=torch.float64):
         o_l.append(o)
         r_l.append(r)
     return torch.stack(o_l).numpy(), torch.stack(r_l).numpy()
+
+
+# ----------------------------------------------------------------------------------------------
+# optimiser step: PolicyWithQs.apply_gradients, policy.py:123-171
+# ----------------------------------------------------------------------------------------------
+def polynomial_decay(schedule, step):
+    """keras PolynomialDecay(initial, decay_steps, end), power 1, no cycle."""
+    init, decay_steps, end = schedule
+    frac = min(float(step), float(decay_steps)) / float(decay_steps)
+    return (init - end) * (1.0 - frac) + end
+
+
+class AdamState:
+    """keras OptimizerV2 Adam for one net: b1 0.9, b2 0.999, eps 1e-7 (the algorithm lives in un-vendored,
+    un-pinned TensorFlow 2.x; restated from its published definition)."""
+
+    def __init__(self, schedule):
+        self.schedule, self.iterations, self.m, self.v = schedule, 0, None, None
+
+    def apply(self, weights, grads):
+        t = self.iterations + 1
+        lr = polynomial_decay(self.schedule, self.iterations)
+        lr_t = lr * math.sqrt(1.0 - 0.999 ** t) / (1.0 - 0.9 ** t)
+        if self.m is None:
+            self.m = [np.zeros_like(w) for w in weights]
+            self.v = [np.zeros_like(w) for w in weights]
+        out = []
+        for i, (w, g) in enumerate(zip(weights, grads)):
+            self.m[i] = 0.9 * self.m[i] + (1.0 - 0.9) * g
+            self.v[i] = 0.999 * self.v[i] + (1.0 - 0.999) * g * g
+            out.append(w - lr_t * self.m[i] / (np.sqrt(self.v[i]) + 1e-7))
+        self.iterations = t
+        return out
+
+
+def apply_gradients(weights, states, iteration, grads, double_q, delay_update, tau, dtype=np.float64):
+    """weights: get_weights() order (models + targets); states: dict name -> AdamState; grads: flat list in
+    compute_gradient order. Returns the new weights list (policy.py:123-171, target=True)."""
+    w = [[np.asarray(a, dtype) for a in net] for net in weights]
+    g = [np.asarray(a, dtype) for a in grads]
+    nq = 2 if double_q else 1
+    for i in range(nq):
+        w[i] = states[f'Q{i + 1}'].apply(w[i], g[6 * i: 6 * i + 6])
+    if iteration % delay_update == 0:
+        w[nq] = states['policy'].apply(w[nq], g[6 * nq: 6 * nq + 6])
+        nm = nq + 1
+        for i in range(nm):
+            w[nm + i] = [tau * s_ + (1.0 - tau) * t_ for s_, t_ in zip(w[i], w[nm + i])]
+    return w

@@ -77,6 +77,17 @@ class Variable:
     def shape(self):
         return tuple(self.value.shape)
 
+    # arithmetic used by the Polyak target updates (policy.py:158-171): tau * source + (1 - tau) * target
+    def __mul__(self, o):
+        return self.value.detach() * o
+
+    __rmul__ = __mul__
+
+    def __add__(self, o):
+        return self.value.detach() + o
+
+    __radd__ = __add__
+
 
 # make `tensor.numpy()` legal on tensors that carry grad history (TF eager tensors allow it)
 _orig_numpy = torch.Tensor.numpy
@@ -220,17 +231,38 @@ class _KerasModel:
             v.assign(w)
 
 
+class _PolynomialDecay:
+    """tf.keras.optimizers.schedules.PolynomialDecay(initial_learning_rate, decay_steps, end_learning_rate),
+    power = 1, cycle = False (published Keras semantics; TF itself is not installable here)."""
+
+    def __init__(self, initial, decay_steps, end=0.0001, power=1.0):
+        self.initial, self.decay_steps, self.end, self.power = initial, decay_steps, end, power
+
+    def __call__(self, step):
+        frac = min(float(step), float(self.decay_steps)) / float(self.decay_steps)
+        return (self.initial - self.end) * (1.0 - frac) ** self.power + self.end
+
+
 class _Adam:
+    """tf.keras.optimizers.Adam (OptimizerV2, TF 2.2-2.4): beta_1 0.9, beta_2 0.999, epsilon 1e-7, no amsgrad.
+    lr_t = lr(iterations) * sqrt(1 - b2^t) / (1 - b1^t), t = iterations + 1;
+    m = b1 m + (1-b1) g; v = b2 v + (1-b2) g^2; var -= lr_t * m / (sqrt(v) + eps)."""
+
     def __init__(self, lr=None, name=None):
-        self._name = name
+        self._name, self.lr, self.iterations, self.slots = name, lr, 0, {}
 
     def apply_gradients(self, gv):
-        raise NotImplementedError('optimiser step is outside the hot path (SURVEY 8(f) #2)')
-
-
-class _PolynomialDecay:
-    def __init__(self, *a):
-        self.args = a
+        t = self.iterations + 1
+        lr = self.lr(self.iterations) if callable(self.lr) else self.lr
+        lr_t = lr * np.sqrt(1.0 - 0.999 ** t) / (1.0 - 0.9 ** t)
+        for g, var in gv:
+            g = _t(g).detach()
+            m, v = self.slots.get(id(var), (torch.zeros_like(g), torch.zeros_like(g)))
+            m = 0.9 * m + (1.0 - 0.9) * g
+            v = 0.999 * v + (1.0 - 0.999) * g * g
+            self.slots[id(var)] = (m, v)
+            var.assign(var.value.detach() - lr_t * m / (torch.sqrt(v) + 1e-7))
+        self.iterations = t
 
 
 class _Normal:

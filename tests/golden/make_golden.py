@@ -199,6 +199,22 @@ def run_model(case):
     return out
 
 
+def run_apply_gradients(case):
+    """PolicyWithQs.apply_gradients (policy.py:123-171) for several iterations on seeded gradients."""
+    from policy import PolicyWithQs
+    H = case['H']
+    args = default_args(case['version'], PT, value_num_hidden_units=H, policy_num_hidden_units=H)
+    dq = case['version'] == 'MPG-v2'
+    pol = PolicyWithQs(**vars(args))
+    pol.set_weights(synthetic.make_policy_with_qs_weights(case['wseed'], args.obs_dim, args.act_dim, H, double_q=dq))
+    rng = np.random.default_rng(case['gseed'])
+    for it in range(case['iters']):
+        grads = [rng.standard_normal(np.shape(a)).astype(np.float32) * 0.1
+                 for net in pol.get_weights()[: (3 if dq else 2)] for a in net]
+        pol.apply_gradients(it, grads)
+    return {'weights': np.concatenate([np.asarray(a, np.float64).ravel() for net in pol.get_weights() for a in net])}
+
+
 def run_weights_rule(case):
     """MPGLearner.rule_based_weights (mpg_learner.py:384-399) at several iterations."""
     from learners.mpg_learner import MPGLearner
@@ -236,10 +252,12 @@ CASES = {
     'model_pt_nfd2': dict(fn='model', env_id=PT, B=32, H=64, n=25, nfd=2, wseed=111, bseed=112, nseed=113),
     'model_ip': dict(fn='model', env_id=IP, B=32, H=64, n=25, nfd=0, wseed=121, bseed=122, nseed=123),
     'model_idp': dict(fn='model', env_id=IDP, B=32, H=64, n=25, nfd=0, wseed=131, bseed=132, nseed=133),
+    'apply_grads_v2_h64': dict(fn='apply', version='MPG-v2', H=64, iters=5, wseed=141, gseed=142),
+    'apply_grads_nadp_h64': dict(fn='apply', version='NADP', H=64, iters=4, wseed=151, gseed=152),
     'rule_weights': dict(fn='rule', rollout_list=[0, 25], iterations=[0, 2000, 4000, 4500, 5000, 9000, 27000]),
     'rule_weights3': dict(fn='rule', rollout_list=[0, 3, 25], iterations=[0, 3000, 4500, 6000, 12000]),
 }
-FNS = dict(nadp=run_nadp, mpg=run_mpg, model=run_model, rule=run_weights_rule)
+FNS = dict(nadp=run_nadp, mpg=run_mpg, model=run_model, rule=run_weights_rule, apply=run_apply_gradients)
 
 
 def extract_mpc_fixture():

@@ -353,3 +353,34 @@ def test_error_paths():
     bad.learner_version = 'MPG-v3'
     with pytest.raises(ValueError):
         MPGLearner(PolicyWithQs, bad)
+
+
+@pytest.mark.parametrize('version', ['MPG-v2', 'NADP'])
+def test_apply_gradients_on_device_matches_oracle(version):
+    """SURVEY 8(f) next #2: Keras-Adam + delayed policy update + Polyak targets on the device-resident weights."""
+    from oracle import mpg_oracle as O
+    from mpg_b200.policy import PolicyWithQs
+    dq = version == 'MPG-v2'
+    args = default_args(version, PT)
+    w0 = synthetic.make_policy_with_qs_weights(31, args.obs_dim, args.act_dim, 256, double_q=dq)
+    pol = PolicyWithQs(**vars(args))
+    pol.set_weights(w0)
+    states = {'Q1': O.AdamState(args.value_lr_schedule), 'Q2': O.AdamState(args.value_lr_schedule),
+              'policy': O.AdamState(args.policy_lr_schedule)}
+    w = w0
+    rng = np.random.default_rng(32)
+    for it in range(5):
+        grads = [rng.standard_normal(np.shape(a)).astype(np.float32) * 0.1 for net in w0[: (3 if dq else 2)] for a in net]
+        pol.apply_gradients(it, grads if it % 2 == 0 else torch.tensor(np.concatenate([g.ravel() for g in grads]), device='cuda'))
+        w = O.apply_gradients(w, states, it, grads, dq, args.delay_update, args.tau)
+    got = pol.get_weights()
+    for net_g, net_r in zip(got, w):
+        for a, b in zip(net_g, net_r):
+            assert a.shape == np.shape(b)
+            assert rel_l2(a, b) <= 2e-6
+    # the updated weights are what the kernels now use
+    obs = synthetic.make_obs(np.random.default_rng(1), PT, 64)
+    act = pol.compute_mode(obs * np.asarray(args.obs_scale, np.float32)).cpu().numpy()
+    ref = O.policy_action([O.to_t(x, torch.float64) for x in w[2 if dq else 1]],
+                          O.to_t(obs * np.asarray(args.obs_scale), torch.float64), 'tanh', None).numpy()
+    assert rel_l2(act, ref) <= 1e-5

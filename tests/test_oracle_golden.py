@@ -114,3 +114,22 @@ def test_f_xu_against_recorded_env_transitions():
         for c in (0, 1, 2):
             err = np.abs(got[:, c] - obs[1:, c]).max() / np.abs(obs[1:, c]).max()
             assert err < 5e-5, (c, err)
+
+
+@pytest.mark.parametrize('name', ['apply_grads_v2_h64', 'apply_grads_nadp_h64'])
+def test_apply_gradients_oracle_matches_reference(name):
+    """Adam / delayed policy update / Polyak targets (policy.py:123-171) against the reference's own control flow."""
+    from mpg_b200 import synthetic
+    from mpg_b200.config import default_args
+    case, gold = load_golden(name)
+    H, dq = case['H'], case['version'] == 'MPG-v2'
+    args = default_args(case['version'], 'PathTracking-v0', value_num_hidden_units=H, policy_num_hidden_units=H)
+    w = synthetic.make_policy_with_qs_weights(case['wseed'], args.obs_dim, args.act_dim, H, double_q=dq)
+    states = {'Q1': O.AdamState(args.value_lr_schedule), 'Q2': O.AdamState(args.value_lr_schedule),
+              'policy': O.AdamState(args.policy_lr_schedule)}
+    rng = np.random.default_rng(case['gseed'])
+    for it in range(case['iters']):
+        grads = [rng.standard_normal(np.shape(a)).astype(np.float32) * 0.1 for net in w[: (3 if dq else 2)] for a in net]
+        w = O.apply_gradients(w, states, it, grads, dq, args.delay_update, args.tau)
+    got = np.concatenate([np.asarray(a, np.float64).ravel() for net in w for a in net])
+    assert rel_l2(got, gold['weights__f64']) <= 2e-7
