@@ -201,6 +201,25 @@ int mpg_set_profile_buffer(mpg_ctx* ctx, long long* buf);
 /* counters for bench.py: kernels launched by this handle since creation */
 uint64_t mpg_launch_count(const mpg_ctx* ctx);
 
+/* ---- GPU prioritized replay ------------------------------------------ */
+/* PrioritizedReplayBuffer (buffer.py:94-189) over sum/min segment trees (utils/segment_tree.py:13-151). */
+typedef struct mpg_replay mpg_replay;
+int mpg_replay_create(int capacity, int obs_dim, int act_dim, double alpha, double beta, mpg_replay** out);
+void mpg_replay_destroy(mpg_replay* rb);
+const char* mpg_replay_last_error(const mpg_replay* rb);
+int mpg_replay_size(const mpg_replay* rb);
+/* add n transitions (device pointers); priorities NULL -> current max priority (buffer.py:128-136) */
+int mpg_replay_add(mpg_replay* rb, int n, const float* obs, const float* act, const float* rew, const float* obs_tp1,
+                   const float* done, const float* priorities, void* stream);
+/* proportional sampling (buffer.py:138-165): u = n uniforms in [0,1); writes indices, importance weights
+ * (may be NULL) and the gathered transitions */
+int mpg_replay_sample(mpg_replay* rb, int n, const float* u, int32_t* idx_out, float* weights_out, float* obs_out,
+                      float* act_out, float* rew_out, float* obs_tp1_out, float* done_out, void* stream);
+/* update_priorities (buffer.py:167-189); priorities must be > 0 (callers pass |td| + eps) */
+int mpg_replay_update_priorities(mpg_replay* rb, int n, const int32_t* idx, const float* priorities, void* stream);
+/* root of the sum / min trees and the running max priority (synchronises the stream) */
+int mpg_replay_tree_stats(mpg_replay* rb, double* sum_out, double* min_out, double* max_priority_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -18,6 +18,8 @@ SYMBOLS = [
     'mpg_model_reset', 'mpg_model_step', 'mpg_model_step_bwd', 'mpg_compute_rewards', 'mpg_state_dim',
     'mpg_clip_global_norm', 'mpg_philox_noise', 'mpg_launch_count', 'mpg_set_backend', 'mpg_get_backend',
     'mpg_set_timing', 'mpg_kernel_ms', 'mpg_tc_selftest', 'mpg_set_profile_buffer', 'mpg_adam_step', 'mpg_polyak_update',
+    'mpg_replay_create', 'mpg_replay_destroy', 'mpg_replay_last_error', 'mpg_replay_size', 'mpg_replay_add',
+    'mpg_replay_sample', 'mpg_replay_update_priorities', 'mpg_replay_tree_stats',
 ]
 
 
@@ -87,6 +89,14 @@ def load():
         'mpg_set_profile_buffer': (i32, [vp, vp]),
         'mpg_adam_step': (i32, [vp, i32, vp, f32, i64, f32, f32, f32, vp]),
         'mpg_polyak_update': (i32, [vp, i32, i32, f32, vp]),
+        'mpg_replay_create': (i32, [i32, i32, i32, ctypes.c_double, ctypes.c_double, P(vp)]),
+        'mpg_replay_destroy': (None, [vp]),
+        'mpg_replay_last_error': (ctypes.c_char_p, [vp]),
+        'mpg_replay_size': (i32, [vp]),
+        'mpg_replay_add': (i32, [vp, i32, vp, vp, vp, vp, vp, vp, vp]),
+        'mpg_replay_sample': (i32, [vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+        'mpg_replay_update_priorities': (i32, [vp, i32, vp, vp, vp]),
+        'mpg_replay_tree_stats': (i32, [vp, P(ctypes.c_double), P(ctypes.c_double), P(ctypes.c_double), vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)  # AttributeError if the header and the library ever diverge

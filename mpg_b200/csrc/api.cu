@@ -3,9 +3,11 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <vector>
 
 #include "rollout_kernels.cuh"
 #include "tc_rollout.cuh"
+#include "replay.cuh"
 
 using namespace mpg;
 
@@ -694,6 +696,126 @@ int mpg_philox_noise(mpg_ctx* ctx, const mpg_rollout_params* p, float* out, void
                                                                                         p->rows, p->M, p->horizon, out);
   ctx->launches++;
   CUDA_OK(ctx, cudaGetLastError());
+  return MPG_OK;
+}
+
+}  // extern "C"
+
+// =====================================================================================================
+// prioritized replay
+// =====================================================================================================
+struct mpg_replay {
+  int capacity = 0, obs_dim = 0, act_dim = 0, size = 0, next_idx = 0;
+  double alpha = 0.6, beta = 0.4;
+  float *obs = nullptr, *act = nullptr, *rew = nullptr, *obs1 = nullptr, *done = nullptr;
+  double *sum_tree = nullptr, *min_tree = nullptr, *max_prio = nullptr;
+  int* owner = nullptr;
+  char err[256];
+};
+
+namespace {
+thread_local char g_replay_err[256] = "";
+int rfail(mpg_replay* rb, int code, const char* msg) {
+  snprintf(rb ? rb->err : g_replay_err, 256, "%s", msg);
+  return code;
+}
+#define RB_CUDA(rb, expr)                                                          \
+  do {                                                                             \
+    cudaError_t e__ = (expr);                                                      \
+    if (e__ != cudaSuccess) return rfail(rb, MPG_ERR_CUDA, cudaGetErrorString(e__)); \
+  } while (0)
+
+int rebuild_tree(mpg_replay* rb, cudaStream_t st) {
+  int first = rb->capacity / 2;
+  for (; first > 512; first >>= 1) replay_level_kernel<<<(first + 255) / 256, 256, 0, st>>>(first, rb->sum_tree, rb->min_tree);
+  if (first >= 1) replay_top_kernel<<<1, 512, 0, st>>>(first, rb->sum_tree, rb->min_tree);
+  RB_CUDA(rb, cudaGetLastError());
+  return MPG_OK;
+}
+}  // namespace
+
+extern "C" {
+
+const char* mpg_replay_last_error(const mpg_replay* rb) { return rb ? rb->err : g_replay_err; }
+int mpg_replay_size(const mpg_replay* rb) { return rb ? rb->size : -1; }
+
+int mpg_replay_create(int capacity, int obs_dim, int act_dim, double alpha, double beta, mpg_replay** out) {
+  if (!out || capacity <= 0 || obs_dim <= 0 || act_dim <= 0 || !(alpha > 0)) return rfail(nullptr, MPG_ERR_ARG, "bad replay config (alpha must be > 0)");
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return rfail(nullptr, MPG_ERR_CUDA, "no CUDA device: mpg_b200 has no CPU fallback");
+  mpg_replay* rb = new (std::nothrow) mpg_replay();
+  if (!rb) return rfail(nullptr, MPG_ERR_ARG, "out of host memory");
+  rb->err[0] = 0;
+  int cap = 1;
+  while (cap < capacity) cap *= 2;                       // it_capacity (buffer.py:119-121)
+  rb->capacity = cap; rb->obs_dim = obs_dim; rb->act_dim = act_dim; rb->alpha = alpha; rb->beta = beta;
+  bool ok = cudaMalloc(&rb->obs, (size_t)cap * obs_dim * 4) == cudaSuccess && cudaMalloc(&rb->obs1, (size_t)cap * obs_dim * 4) == cudaSuccess
+            && cudaMalloc(&rb->act, (size_t)cap * act_dim * 4) == cudaSuccess && cudaMalloc(&rb->rew, (size_t)cap * 4) == cudaSuccess
+            && cudaMalloc(&rb->done, (size_t)cap * 4) == cudaSuccess && cudaMalloc(&rb->sum_tree, (size_t)2 * cap * 8) == cudaSuccess
+            && cudaMalloc(&rb->min_tree, (size_t)2 * cap * 8) == cudaSuccess && cudaMalloc(&rb->max_prio, 8) == cudaSuccess
+            && cudaMalloc(&rb->owner, (size_t)cap * 4) == cudaSuccess;
+  if (!ok) { mpg_replay_destroy(rb); return rfail(nullptr, MPG_ERR_CUDA, "cudaMalloc of the replay storage failed"); }
+  cudaMemset(rb->sum_tree, 0, (size_t)2 * cap * 8);
+  std::vector<double> inf((size_t)2 * cap, INFINITY);     // neutral element of the min tree
+  cudaMemcpy(rb->min_tree, inf.data(), inf.size() * 8, cudaMemcpyHostToDevice);
+  const double one = 1.0;                                 // _max_priority = 1.0 (buffer.py:125)
+  cudaMemcpy(rb->max_prio, &one, 8, cudaMemcpyHostToDevice);
+  cudaMemset(rb->owner, 0xFF, (size_t)cap * 4);
+  *out = rb;
+  return MPG_OK;
+}
+
+void mpg_replay_destroy(mpg_replay* rb) {
+  if (!rb) return;
+  cudaFree(rb->obs); cudaFree(rb->obs1); cudaFree(rb->act); cudaFree(rb->rew); cudaFree(rb->done);
+  cudaFree(rb->sum_tree); cudaFree(rb->min_tree); cudaFree(rb->max_prio); cudaFree(rb->owner);
+  delete rb;
+}
+
+int mpg_replay_add(mpg_replay* rb, int n, const float* obs, const float* act, const float* rew, const float* obs_tp1,
+                   const float* done, const float* priorities, void* stream) {
+  if (!rb || n <= 0 || !obs || !act || !rew || !obs_tp1) return rfail(rb, MPG_ERR_ARG, "bad argument to mpg_replay_add");
+  if (n > rb->capacity) return rfail(rb, MPG_ERR_ARG, "more transitions than the buffer capacity in one add");
+  cudaStream_t st = (cudaStream_t)stream;
+  replay_write_kernel<<<(n + 127) / 128, 128, 0, st>>>(n, rb->capacity, rb->next_idx, rb->obs_dim, rb->act_dim, obs, act, rew,
+                                                        obs_tp1, done, priorities, rb->max_prio, rb->alpha, rb->obs, rb->act,
+                                                        rb->rew, rb->obs1, rb->done, rb->sum_tree, rb->min_tree);
+  rb->next_idx = (rb->next_idx + n) % rb->capacity;
+  rb->size = rb->size + n < rb->capacity ? rb->size + n : rb->capacity;
+  return rebuild_tree(rb, st);
+}
+
+int mpg_replay_sample(mpg_replay* rb, int n, const float* u, int32_t* idx_out, float* weights_out, float* obs_out,
+                      float* act_out, float* rew_out, float* obs_tp1_out, float* done_out, void* stream) {
+  if (!rb || n <= 0 || !u || !idx_out || !obs_out || !act_out || !rew_out || !obs_tp1_out || !done_out)
+    return rfail(rb, MPG_ERR_ARG, "bad argument to mpg_replay_sample");
+  if (rb->size == 0) return rfail(rb, MPG_ERR_STATE, "sampling from an empty replay buffer");
+  replay_sample_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+      n, rb->capacity, rb->size, rb->obs_dim, rb->act_dim, rb->beta, u, rb->sum_tree, rb->min_tree, rb->obs, rb->act, rb->rew,
+      rb->obs1, rb->done, idx_out, weights_out, obs_out, act_out, rew_out, obs_tp1_out, done_out);
+  RB_CUDA(rb, cudaGetLastError());
+  return MPG_OK;
+}
+
+int mpg_replay_update_priorities(mpg_replay* rb, int n, const int32_t* idx, const float* priorities, void* stream) {
+  if (!rb || n <= 0 || !idx || !priorities) return rfail(rb, MPG_ERR_ARG, "bad argument to mpg_replay_update_priorities");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int g = (n + 127) / 128;
+  replay_owner_kernel<<<g, 128, 0, st>>>(n, idx, rb->owner);
+  replay_set_prio_kernel<<<g, 128, 0, st>>>(n, rb->capacity, idx, priorities, rb->alpha, rb->owner, rb->sum_tree, rb->min_tree);
+  replay_owner_reset_kernel<<<g, 128, 0, st>>>(n, idx, rb->owner);
+  replay_max_prio_kernel<<<1, 256, 0, st>>>(n, priorities, rb->max_prio);
+  return rebuild_tree(rb, st);
+}
+
+int mpg_replay_tree_stats(mpg_replay* rb, double* sum_out, double* min_out, double* max_priority_out, void* stream) {
+  if (!rb) return MPG_ERR_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (sum_out) RB_CUDA(rb, cudaMemcpyAsync(sum_out, rb->sum_tree + 1, 8, cudaMemcpyDeviceToHost, st));
+  if (min_out) RB_CUDA(rb, cudaMemcpyAsync(min_out, rb->min_tree + 1, 8, cudaMemcpyDeviceToHost, st));
+  if (max_priority_out) RB_CUDA(rb, cudaMemcpyAsync(max_priority_out, rb->max_prio, 8, cudaMemcpyDeviceToHost, st));
+  RB_CUDA(rb, cudaStreamSynchronize(st));
   return MPG_OK;
 }
 

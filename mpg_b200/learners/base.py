@@ -80,6 +80,12 @@ class LearnerBase(object):
     def _upload_batch(self, batch_data):
         # mpg_learner.py:66-72: cast to fp32; here additionally host -> device (pinned when possible)
         names = ('batch_obs', 'batch_actions', 'batch_rewards', 'batch_obs_tp1', 'batch_dones')
+        if isinstance(batch_data[0], torch.Tensor):
+            # device-resident replay (mpg_b200.buffer.*.replay_device): no host round trip
+            self.batch_data = {k: v for k, v in zip(names, batch_data)}
+            self._dev = {k: self.engine.dev(v) for k, v in self.batch_data.items() if k != 'batch_dones'}
+            self.h2d_bytes = 0
+            return
         self.batch_data = {k: np.asarray(v).astype(np.float32) for k, v in zip(names, batch_data)}
         self._dev = {}
         for k, v in self.batch_data.items():

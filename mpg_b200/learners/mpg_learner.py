@@ -46,7 +46,8 @@ class MPGLearner(LearnerBase):
 
     def compute_td_error(self):  # mpg_learner.py:136-144
         d = self._dev
-        return self.engine.td_error(d['batch_obs'], d['batch_actions'], d['batch_rewards'], d['batch_obs_tp1']).cpu().numpy()
+        td = self.engine.td_error(d['batch_obs'], d['batch_actions'], d['batch_rewards'], d['batch_obs_tp1'])
+        return td if isinstance(self.batch_data['batch_obs'], torch.Tensor) else td.cpu().numpy()
 
     def rule_based_weights(self, ite, total_ite, eta):
         return rule_based_weights(ite, total_ite, eta, self.num_rollout_list_for_policy_update)

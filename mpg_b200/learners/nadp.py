@@ -24,7 +24,8 @@ class NADPLearner(LearnerBase):
 
     def compute_td_error(self):  # nadp.py:67-76
         d = self._dev
-        return self.engine.td_error(d['batch_obs'], d['batch_actions'], d['batch_rewards'], d['batch_obs_tp1']).cpu().numpy()
+        td = self.engine.td_error(d['batch_obs'], d['batch_actions'], d['batch_rewards'], d['batch_obs_tp1'])
+        return td if isinstance(self.batch_data['batch_obs'], torch.Tensor) else td.cpu().numpy()
 
     def model_rollout_for_q_estimation(self, mb_obs, mb_actions):
         """nadp.py:87-126: forward-only rollout from the replay (obs, action) with the online policy and

@@ -215,6 +215,46 @@ def run_apply_gradients(case):
     return {'weights': np.concatenate([np.asarray(a, np.float64).ravel() for net in pol.get_weights() for a in net])}
 
 
+def run_replay(case):
+    """The reference's own PrioritizedReplayBuffer / segment trees (pure Python, imported unmodified) driven through
+    add(weight=None), find_prefixsum_idx on explicit masses, sample_with_weights_and_idxes and update_priorities.
+    args.alpha / args.size are supplied because the reference's parsers never define them (SURVEY.md 2 #10)."""
+    from argparse import Namespace
+    from buffer import PrioritizedReplayBuffer
+    rng = np.random.default_rng(case['seed'])
+    cap, n0, n1, ns = case['capacity'], case['n_add0'], case['n_add1'], case['n_sample']
+    args = Namespace(max_buffer_size=cap, replay_starts=1, replay_batch_size=ns, alpha=0.6, size=cap, replay_alpha=0.6,
+                     replay_beta=0.4, buffer_log_interval=10 ** 9)
+    rb = PrioritizedReplayBuffer(args, 0)
+    out = {}
+
+    def add(n):
+        for _ in range(n):
+            o, a = rng.standard_normal(6).astype(np.float32), rng.standard_normal(2).astype(np.float32)
+            rb.add(o, a, np.float32(rng.standard_normal()), o + 1, np.float32(0.0), None)
+
+    def draw(tag):
+        u = rng.random(ns).astype(np.float32)
+        total = rb._it_sum.sum()
+        idx = np.array([rb._it_sum.find_prefixsum_idx(float(x) * total) for x in u], np.int32)
+        smp = rb.sample_with_weights_and_idxes(idx)
+        out[f'u_{tag}'], out[f'idx_{tag}'], out[f'w_{tag}'] = u, idx, np.asarray(smp[5], np.float64)
+        out[f'rew_{tag}'], out[f'obs_{tag}'] = np.asarray(smp[2], np.float32), np.asarray(smp[0], np.float32)
+        out[f'sum_{tag}'], out[f'min_{tag}'] = np.float64(total), np.float64(rb._it_min.min())
+
+    add(n0)
+    draw('a')
+    upd_idx = rng.integers(0, n0, case['n_update']).astype(np.int32)
+    upd_pr = (np.abs(rng.standard_normal(case['n_update'])) + 1e-3).astype(np.float32)
+    rb.update_priorities(upd_idx, [float(p) for p in upd_pr])
+    out['upd_idx'], out['upd_pr'] = upd_idx, upd_pr
+    draw('b')
+    add(n1)          # wraps around the ring when n0 + n1 > capacity; new entries take the running max priority
+    draw('c')
+    out['max_priority'] = np.float64(rb._max_priority)
+    return out
+
+
 def run_weights_rule(case):
     """MPGLearner.rule_based_weights (mpg_learner.py:384-399) at several iterations."""
     from learners.mpg_learner import MPGLearner
@@ -254,10 +294,12 @@ CASES = {
     'model_idp': dict(fn='model', env_id=IDP, B=32, H=64, n=25, nfd=0, wseed=131, bseed=132, nseed=133),
     'apply_grads_v2_h64': dict(fn='apply', version='MPG-v2', H=64, iters=5, wseed=141, gseed=142),
     'apply_grads_nadp_h64': dict(fn='apply', version='NADP', H=64, iters=4, wseed=151, gseed=152),
+    'replay': dict(fn='replay', capacity=64, n_add0=40, n_add1=40, n_sample=128, n_update=50, seed=161),
     'rule_weights': dict(fn='rule', rollout_list=[0, 25], iterations=[0, 2000, 4000, 4500, 5000, 9000, 27000]),
     'rule_weights3': dict(fn='rule', rollout_list=[0, 3, 25], iterations=[0, 3000, 4500, 6000, 12000]),
 }
-FNS = dict(nadp=run_nadp, mpg=run_mpg, model=run_model, rule=run_weights_rule, apply=run_apply_gradients)
+FNS = dict(nadp=run_nadp, mpg=run_mpg, model=run_model, rule=run_weights_rule, apply=run_apply_gradients,
+           replay=run_replay)
 
 
 def extract_mpc_fixture():
