@@ -92,6 +92,20 @@ __global__ void adam_kernel(float* __restrict__ w, float* __restrict__ m, float*
   w[i] -= lr_t * mi / (sqrtf(vi) + eps);
 }
 
+// loss_sum = sum_i 0.5 (q_i - target_i)^2, fixed-order single-block reduction
+__global__ void sq_err_kernel(const float* __restrict__ q, const float* __restrict__ target, int n, float* __restrict__ out) {
+  __shared__ float red[1024];
+  float s = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) { const float d = q[i] - target[i]; s = fmaf(0.5f * d, d, s); }
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[0] = red[0];
+}
+
 __global__ void polyak_kernel(float* __restrict__ dst, const float* __restrict__ src, int n, float tau) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) dst[i] = tau * src[i] + (1.f - tau) * dst[i];
@@ -545,6 +559,47 @@ int mpg_q_grad(mpg_ctx* ctx, int net, int rows, int64_t global_rows, const float
   int rc = check_net(ctx, net);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
+  if (ctx->backend == MPG_BACKEND_TC && rows <= ctx->cfg.max_rows) {
+    // tensor-core path: the rollout kernel in regression mode (horizon 0, given actions) + the dW kernel
+    const mpg_config& c = ctx->cfg;
+    const int qin = c.obs_dim + c.act_dim;
+    tc::TcArgs ta;
+    memset(&ta, 0, sizeof(ta));
+    RolloutArgs& r = ta.r;
+    r.obs_dim = c.obs_dim; r.act_dim = c.act_dim; r.nfd = c.num_future_data; r.policy_out_tanh = c.policy_out_tanh;
+    r.action_range = c.action_range;
+    for (int i = 0; i < MPG_MAX_OBS; ++i) r.obs_scale[i] = c.obs_scale[i];
+    r.rew_scale = c.rew_scale; r.rew_shift = c.rew_shift; r.gamma = c.gamma;
+    r.rows = rows; r.M = 1; r.horizon = 0; r.n_list = 1; r.list[0] = 0; r.list_w[0] = 1.f;
+    r.full_bptt = 1; r.has_q = 1; r.use_start_actions = 1; r.noise_mode = 0;
+    r.global_rows = global_rows > 0 ? global_rows : rows;
+    r.obs = obs; r.start_actions = act; r.returns_out = ctx->tc.qtmp; r.ckpt = ctx->ckpt;
+    r.partial = ctx->partial; r.partial_stride = (long long)ctx->partial_stride;
+    ta.q = tc_net(ctx->tc, net, ctx->nets[net].flat, qin, 1);
+    ta.pol = ta.q;   // unused in regression mode (actions are given, the policy part is skipped); fixes the gradient layout
+    ta.act_ckpt = ctx->tc.act_ckpt;
+    ta.q_regress = 1; ta.q_target = target; ta.q_inv_rows = 1.f / (float)r.global_rows;
+    const int ntiles = (rows + tc::ACT_ROWS - 1) / tc::ACT_ROWS;
+    const int grid = ntiles < ctx->sms ? ntiles : ctx->sms;
+    ta.store_steps = 1;
+    if (!tc_ensure_store(ctx->tc, (size_t)ntiles * tc::SLOT_BYTES)) return fail(ctx, MPG_ERR_CUDA, "cudaMalloc of the dW operand store failed%s");
+    ta.store = ctx->tc.store;
+    CUDA_OK(ctx, cudaMemsetAsync(ctx->partial, 0, (size_t)ctx->sms * ctx->partial_stride * sizeof(float), st));
+    CUDA_OK(ctx, tc_launch_rollout<true>(c.env, ta, grid, st));
+    tc::DwArgs da;
+    da.store = ctx->tc.store; da.nrecords = ntiles; da.has_h2 = 1;
+    da.in_dim = qin; da.out_dim = 1; da.act_dim = 1;
+    da.partial = ctx->partial; da.partial_stride = (long long)ctx->partial_stride;
+    const int dgrid = 2 * da.nrecords < ctx->sms ? 2 * da.nrecords : (ctx->sms & ~1);
+    tc::tc_dw_kernel<<<dgrid, 192, 2 * tc::DW_STAGE + 128 + 1024, st>>>(da);
+    const GradLayout L(qin, 1);
+    reduce_partials_kernel<<<(L.total + 255) / 256, 256, 0, st>>>(ctx->partial, ctx->partial_stride, ctx->sms, L.total,
+                                                                  grad_out, nullptr, nullptr);
+    if (loss_sum_out) sq_err_kernel<<<1, 1024, 0, st>>>(ctx->tc.qtmp, target, rows, loss_sum_out);
+    ctx->launches += 4;
+    CUDA_OK(ctx, cudaGetLastError());
+    return MPG_OK;
+  }
   QGradArgs a;
   memset(&a, 0, sizeof(a));
   a.obs_dim = ctx->cfg.obs_dim; a.act_dim = ctx->cfg.act_dim; a.rows = rows;

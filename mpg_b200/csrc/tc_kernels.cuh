@@ -43,6 +43,10 @@ struct TcArgs {
   float* act_ckpt;          // [n_list][M*rows][A] actions at the list steps (for the Q input gradient)
   uint8_t* store;           // dW operand store: [tile][step][SLOT_BYTES]
   int store_steps;          // steps recorded per tile: horizon+1 (full BPTT) or 1 (first action only)
+  int q_regress;            // 1: Q regression gradient (q_forward_and_backward): horizon 0, given actions,
+                            //    upstream (Q - target) / B_global, dW operands of the Q net recorded, no policy part
+  const float* q_target;    // (rows) regression targets
+  float q_inv_rows;         // 1 / B_global
   long long* prof;          // optional: clock64 timestamps of one backward step of CTA 0 (debug / DESIGN.md timeline)
 };
 
@@ -291,17 +295,23 @@ __device__ __forceinline__ void run_rollout(const TcArgs& A, uint8_t* smem, Bars
       }
     };
     // Q forward on the current [p|a|1] image: returns Q for the row thread
-    auto q_forward = [&](bool with_img) -> float {
+    auto q_forward = [&](bool with_img, uint8_t* qslot) -> float {
       float qv = 0.f;
       gemm_issue<ROLE>(1, b, smem, sy, A.q.l1, tm_z1);
       gemm_issue<ROLE>(0, b, smem, sy, A.q.big_fwd, tm_work);
       if (ROLE == ROLE_EPI) {
         epi_wait_d(b, sy);
         epi_hidden1_blocks(b, tm_z1 + lane_off, act_img, row, hc, nullptr);
+        if (qslot) store_image(elected, qslot + SLOT_H1, act_img, 2 * ACT_SPLIT);
         epi_wait_d(b, sy);
         float p0, p1;
-        if (with_img) epi_hidden2_img(tm_work + lane_off, mf->b2q, mf->W3q, act_img, row, hc, p0, p1, nullptr);
-        else epi_hidden2(tm_work + lane_off, mf->b2q, mf->W3q, hc, p0, p1);
+        if (with_img) {
+          if (qslot) store_wait(elected);
+          epi_hidden2_img(tm_work + lane_off, mf->b2q, mf->W3q, act_img, row, hc, p0, p1, nullptr);
+          if (qslot) store_image(elected, qslot + SLOT_H2, act_img, 2 * ACT_SPLIT);
+        } else {
+          epi_hidden2(tm_work + lane_off, mf->b2q, mf->W3q, hc, p0, p1);
+        }
         mf->part[(hc * 2 + 0) * ACT_ROWS + row] = p0;
         epi_bar();
         if (rowthread) qv = mf->b3[2] + ((mf->part[0 * ACT_ROWS + row] + mf->part[2 * ACT_ROWS + row])
@@ -346,7 +356,7 @@ __device__ __forceinline__ void run_rollout(const TcArgs& A, uint8_t* smem, Bars
           for (int j = 0; j < NA; ++j) A.act_ckpt[((size_t)kidx * MB + grow) * NA + j] = act[j];
         if (a.has_q) {
           if (rowthread) write_pimg(s, act);
-          qv = q_forward(false);
+          qv = q_forward(false, nullptr);
         }
         if (valid && a.returns_out) a.returns_out[(size_t)kidx * MB + grow] = rsum + gpow * qv;
       }
@@ -394,30 +404,51 @@ __device__ __forceinline__ void run_rollout(const TcArgs& A, uint8_t* smem, Bars
         int kidx = -1;
         for (int k = 0; k < a.n_list; ++k) if (a.list[k] == t) kidx = k;
         // ---- Q input gradient at the list steps: upstream c w_k gamma^t on Q1(p_t, a_t) ----
-        if (kidx >= 0 && a.has_q && a.list_w[kidx] != 0.f) {
+        if (kidx >= 0 && a.has_q && (a.list_w[kidx] != 0.f || A.q_regress)) {
+          uint8_t* qslot = (A.q_regress && store_dw) ? A.store + (size_t)tile * SLOT_BYTES : nullptr;
           if (ROLE == ROLE_EPI && store_dw) store_wait(elected);   // the previous step's delta1 store still reads ACT
           if (rowthread) {
             float ak[NA];
 #pragma unroll
             for (int j = 0; j < NA; ++j) ak[j] = valid ? A.act_ckpt[((size_t)kidx * MB + grow) * NA + j] : 0.f;
-            write_pimg(s, ak);
+            write_pimg(s, ak, qslot ? qslot + SLOT_P : nullptr);
           }
-          (void)q_forward(true);                           // z1q in tm_z1, h2q image in ACT
+          const float qv = q_forward(true, qslot);         // z1q in tm_z1, h2q image in ACT
           if (ROLE == ROLE_EPI) {
-            if (rowthread) mf->d3s[row] = valid ? cscale * a.list_w[kidx] * gp : 0.f;
-            epi_bar();
+            if (rowthread) {
+              // upstream on Q: policy loss c w_k gamma^t, or the regression residual (Q - target) / B_global
+              const float up = !valid ? 0.f : (A.q_regress ? (qv - A.q_target[i_idx]) * A.q_inv_rows : cscale * a.list_w[kidx] * gp);
+              mf->d3s[row] = up;
+              if (A.q_regress) {
+                float x[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) x[i] = 0.f;
+                x[0] = up;
+                if (qslot) write_row16(nullptr, row, x, qslot + SLOT_D3);
+                float s0 = up;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+                if (lane == 0) mf->wsum[warp * 2] = s0;
+              }
+            }
+            if (qslot) store_wait(elected);                // h2q image read out before delta2 overwrites it (has epi_bar)
+            else epi_bar();
+            if (A.q_regress && tid == 0) db3acc[0] += (mf->wsum[0] + mf->wsum[2]) + (mf->wsum[4] + mf->wsum[6]);
           }
           gemm_issue<ROLE>(0, b, smem, sy, A.q.big_dx, tm_work);  // g_h1q, K-blocks issued as delta2 blocks appear
           if (ROLE == ROLE_EPI) {
             epi_delta2_blocks(b, mf->W3q, mf->d3s[row], 0.f, act_img, row, hc, nullptr);
+            if (qslot) store_image(elected, qslot + SLOT_D2, act_img, 2 * ACT_SPLIT);
             epi_wait_d(b, sy);
           }
-          gemm_issue<ROLE>(2, b, smem, sy, A.q.in, tm_z1);        // g_in -> 16 columns of the z1 region
+          if (!A.q_regress) gemm_issue<ROLE>(2, b, smem, sy, A.q.in, tm_z1);   // g_in -> 16 columns of the z1 region
           if (ROLE == ROLE_EPI) {
-            epi_delta1_blocks(b, true, tm_work + lane_off, tm_z1 + lane_off, act_img, row, hc, nullptr);
-            epi_wait_d(b, sy);
+            if (qslot) store_wait(elected);
+            epi_delta1_blocks(b, !A.q_regress, tm_work + lane_off, tm_z1 + lane_off, act_img, row, hc, nullptr);
+            if (qslot) store_image(elected, qslot + SLOT_D1, act_img, 2 * ACT_SPLIT);
+            if (!A.q_regress) epi_wait_d(b, sy);
           }
-          if (rowthread) {
+          if (rowthread && !A.q_regress) {
             float gin[16];
             tmem_ld16(tm_z1 + lane_off, gin);
             if (valid) {
@@ -429,6 +460,7 @@ __device__ __forceinline__ void run_rollout(const TcArgs& A, uint8_t* smem, Bars
             }
           }
         }
+        if (A.q_regress) continue;   // Q regression: no policy part
         // ---- policy recompute ----
         if (rowthread) write_pimg(s, nullptr, rec ? slot + SLOT_P : nullptr);
         policy_forward(zpre, true, rec, slot);

@@ -136,7 +136,7 @@ def _nadp_vs_oracle(env_id, B, n, M, nfd, backend, seed=0, buffer_type='normal',
 
 
 @pytest.mark.parametrize('backend', BACKENDS)
-@pytest.mark.parametrize('B,n,M,nfd', [(256, 25, 1, 0), (100, 25, 1, 0), (1, 25, 1, 0), (48, 10, 2, 2), (64, 1, 1, 0),
+@pytest.mark.parametrize('B,n,M,nfd', [(256, 25, 1, 0), (100, 25, 1, 0), (1, 25, 1, 0), (48, 10, 2, 2), (64, 1, 1, 0), (300, 0, 1, 0),
                                        (2048, 25, 1, 0)])
 def test_nadp_pathtracking_vs_oracle(B, n, M, nfd, backend):
     # split-bf16 contractions carry ~5e-6 relative error per GEMM; a batch of ONE row has no averaging and
