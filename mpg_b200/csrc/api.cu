@@ -35,6 +35,7 @@ struct mpg_ctx {
   float* ckpt = nullptr;
   float* partial = nullptr;
   float* loss_partial = nullptr;
+  float* stats_part = nullptr;   // [MPG_MAX_LIST][RS_BLOCKS][2]
   size_t partial_stride = 0;
   size_t ws_bytes = 0;
   uint64_t launches = 0;
@@ -143,13 +144,17 @@ __global__ void clip_kernel(float* __restrict__ g, int n, float clip, float* __r
   if (threadIdx.x == 0 && norm_out) norm_out[0] = norm;
 }
 
-// returns (n_list, M*rows) -> tile mean (n_list, rows) and/or sums over rows of mean, mean^2
+// returns (n_list, M*rows) -> tile mean (n_list, rows) and/or sums over rows of mean, mean^2.
+// Two stages so that 64K-row batches do not serialise on one block: grid (n_list, RS_BLOCKS) partial sums in a
+// fixed slice order, then one block per k adds the RS_BLOCKS partials in index order (deterministic).
+constexpr int RS_BLOCKS = 64;
 __global__ void returns_stats_kernel(const float* __restrict__ ret, int n_list, int rows, int M,
-                                     float* __restrict__ mean_out, float* __restrict__ stats_out) {
+                                     float* __restrict__ mean_out, float* __restrict__ part) {
   __shared__ float red[2][256];
-  const int k = blockIdx.x;
+  const int k = blockIdx.x, blk = blockIdx.y;
+  const int per = (rows + RS_BLOCKS - 1) / RS_BLOCKS, lo = blk * per, hi = min(rows, lo + per);
   float s1 = 0.f, s2 = 0.f;
-  for (int i = threadIdx.x; i < rows; i += blockDim.x) {
+  for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) {
     float m = 0.f;
     for (int t = 0; t < M; ++t) m += ret[(size_t)k * M * rows + (size_t)t * rows + i];
     m /= (float)M;
@@ -162,7 +167,14 @@ __global__ void returns_stats_kernel(const float* __restrict__ ret, int n_list, 
     if (threadIdx.x < o) { red[0][threadIdx.x] += red[0][threadIdx.x + o]; red[1][threadIdx.x] += red[1][threadIdx.x + o]; }
     __syncthreads();
   }
-  if (threadIdx.x == 0 && stats_out) { stats_out[k] = red[0][0]; stats_out[n_list + k] = red[1][0]; }
+  if (threadIdx.x == 0 && part) { part[(k * RS_BLOCKS + blk) * 2] = red[0][0]; part[(k * RS_BLOCKS + blk) * 2 + 1] = red[1][0]; }
+}
+__global__ void returns_stats_final_kernel(const float* __restrict__ part, int n_list, float* __restrict__ stats_out) {
+  const int k = threadIdx.x;
+  if (k >= n_list) return;
+  float s1 = 0.f, s2 = 0.f;
+  for (int b = 0; b < RS_BLOCKS; ++b) { s1 += part[(k * RS_BLOCKS + b) * 2]; s2 += part[(k * RS_BLOCKS + b) * 2 + 1]; }
+  stats_out[k] = s1; stats_out[n_list + k] = s2;
 }
 
 __global__ void philox_noise_kernel(unsigned long long seed, long long global_rows, long long row_offset, int rows,
@@ -336,7 +348,8 @@ int mpg_create(const mpg_config* cfg, mpg_ctx** out) {
   }
   c->partial_stride = (maxP + 3) & ~size_t(3);
   ok = ok && alloc(&c->ckpt, (size_t)(cfg->max_horizon + 1) * cfg->max_rows * c->S)
-       && alloc(&c->partial, (size_t)c->sms * c->partial_stride) && alloc(&c->loss_partial, c->sms);
+       && alloc(&c->partial, (size_t)c->sms * c->partial_stride) && alloc(&c->loss_partial, c->sms)
+       && alloc(&c->stats_part, (size_t)MPG_MAX_LIST * 64 * 2);
   if (ok) ok = tc_init(c->tc, c->cfg, c->sms, c->ws_bytes);
   if (!ok) {
     snprintf(g_create_err, 512, "cudaMalloc of the workspace failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -367,7 +380,7 @@ void mpg_destroy(mpg_ctx* c) {
     cudaFree(c->nets[n].flat); cudaFree(c->nets[n].W1p); cudaFree(c->nets[n].W2p); cudaFree(c->nets[n].W2Tp);
     cudaFree(c->nets[n].adam_m); cudaFree(c->nets[n].adam_v);
   }
-  cudaFree(c->ckpt); cudaFree(c->partial); cudaFree(c->loss_partial);
+  cudaFree(c->ckpt); cudaFree(c->partial); cudaFree(c->loss_partial); cudaFree(c->stats_part);
   if (c->ev0) { cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); }
   tc_destroy(c->tc);
   delete c;
@@ -539,15 +552,17 @@ int mpg_rollout_forward(mpg_ctx* ctx, const mpg_rollout_params* p, const float* 
 
 int mpg_returns_stats(mpg_ctx* ctx, const float* returns, int n_list, int rows, int M, float* out, void* stream) {
   if (!ctx || !returns || !out || n_list <= 0) return fail(ctx, MPG_ERR_ARG, "bad argument to mpg_returns_stats%s");
-  returns_stats_kernel<<<n_list, 256, 0, (cudaStream_t)stream>>>(returns, n_list, rows, M, nullptr, out);
-  ctx->launches++;
+  if (n_list > MPG_MAX_LIST) return fail(ctx, MPG_ERR_ARG, "n_list too large%s");
+  returns_stats_kernel<<<dim3(n_list, RS_BLOCKS), 256, 0, (cudaStream_t)stream>>>(returns, n_list, rows, M, nullptr, ctx->stats_part);
+  returns_stats_final_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(ctx->stats_part, n_list, out);
+  ctx->launches += 2;
   CUDA_OK(ctx, cudaGetLastError());
   return MPG_OK;
 }
 
 int mpg_returns_tile_mean(mpg_ctx* ctx, const float* returns, int n_list, int rows, int M, float* out, void* stream) {
   if (!ctx || !returns || !out || n_list <= 0) return fail(ctx, MPG_ERR_ARG, "bad argument to mpg_returns_tile_mean%s");
-  returns_stats_kernel<<<n_list, 256, 0, (cudaStream_t)stream>>>(returns, n_list, rows, M, out, nullptr);
+  returns_stats_kernel<<<dim3(n_list, RS_BLOCKS), 256, 0, (cudaStream_t)stream>>>(returns, n_list, rows, M, out, nullptr);
   ctx->launches++;
   CUDA_OK(ctx, cudaGetLastError());
   return MPG_OK;

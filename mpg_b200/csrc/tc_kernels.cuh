@@ -380,9 +380,9 @@ __device__ __forceinline__ void run_rollout(const TcArgs& A, uint8_t* smem, Bars
     }
     // =========================================== backward ==========================================
     if (BWD) {
-      float lam[S], snext[S];
+      float lam[S], snext[S], spre[S];
 #pragma unroll
-      for (int j = 0; j < S; ++j) { lam[j] = 0.f; snext[j] = s[j]; }
+      for (int j = 0; j < S; ++j) { lam[j] = 0.f; snext[j] = s[j]; spre[j] = s[j]; }   // s == s_horizon here
       for (int t = a.horizon; t >= 0; --t) {
         float gp = 1.f;
         for (int i = 0; i < t; ++i) gp *= a.gamma;
@@ -397,9 +397,15 @@ __device__ __forceinline__ void run_rollout(const TcArgs& A, uint8_t* smem, Bars
 #pragma unroll
         for (int j = 0; j < S; ++j) g_s[j] = 0.f;
         if (rowthread && valid) {
-          const float* c = a.ckpt + ((size_t)t * MB + grow) * S;
+          // s_t was prefetched during the previous iteration; issue the loads of s_{t-1} now so that their
+          // global-memory latency hides behind this step
 #pragma unroll
-          for (int j = 0; j < S; ++j) s[j] = c[j];
+          for (int j = 0; j < S; ++j) s[j] = spre[j];
+          if (t > 0) {
+            const float* c = a.ckpt + ((size_t)(t - 1) * MB + grow) * S;
+#pragma unroll
+            for (int j = 0; j < S; ++j) spre[j] = c[j];
+          }
         }
         int kidx = -1;
         for (int k = 0; k < a.n_list; ++k) if (a.list[k] == t) kidx = k;

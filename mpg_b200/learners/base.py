@@ -86,7 +86,7 @@ class LearnerBase(object):
             self._dev = {k: self.engine.dev(v) for k, v in self.batch_data.items() if k != 'batch_dones'}
             self.h2d_bytes = 0
             return
-        self.batch_data = {k: np.asarray(v).astype(np.float32) for k, v in zip(names, batch_data)}
+        self.batch_data = {k: np.asarray(v, dtype=np.float32) for k, v in zip(names, batch_data)}   # mpg_learner.py:66-72
         self._dev = {}
         for k, v in self.batch_data.items():
             if k == 'batch_dones':  # ignored by every learner (mpg_learner.py:71)

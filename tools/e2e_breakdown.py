@@ -1,0 +1,28 @@
+"""Where one NADPLearner.compute_gradient (B = 65536, host numpy in / out) spends its time."""
+import os, sys, time
+import numpy as np, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from mpg_b200 import synthetic
+from mpg_b200.config import default_args
+from mpg_b200.learners import NADPLearner
+from mpg_b200.policy import PolicyWithQs
+import bench
+B = 65536
+args = default_args('NADP', 'PathTracking-v0', replay_batch_size=B)
+L = NADPLearner(PolicyWithQs, args)
+L.set_weights(synthetic.make_policy_with_qs_weights(0, 6, 2, 256, double_q=False))
+L.engine.set_backend(1)
+batch = bench.make_inputs(B)
+for _ in range(3): L.compute_gradient(batch, None, None, 0)
+def t(fn, n=10):
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    for _ in range(n): r = fn()
+    torch.cuda.synchronize(); return (time.perf_counter() - t0) / n * 1e3
+print('compute_gradient        %.3f ms' % t(lambda: L.compute_gradient(batch, None, None, 0)))
+print('  upload (H2D, pinned)   %.3f ms' % t(lambda: L._upload_batch(batch)))
+o, a = L._dev['batch_obs'], L._dev['batch_actions']
+print('  q_forward_and_backward %.3f ms' % t(lambda: L.q_forward_and_backward(o, a)))
+print('    rollout for q target %.3f ms' % t(lambda: L.model_rollout_for_q_estimation(o, a)))
+print('  policy_fwd_and_bwd     %.3f ms' % t(lambda: L.policy_forward_and_backward(o)))
+g = torch.zeros(136965 + 10, device='cuda')
+print('  clip x2 + D2H          %.3f ms' % t(lambda: (L.engine.clip_global_norm(g[:68353], 3.0), L.engine.clip_global_norm(g[68353:136965], 3.0), g.cpu().numpy())))
