@@ -174,6 +174,9 @@ class Engine:
                     noise=None, use_philox=False, noise_seed=0, global_rows=None, row_offset=0, want_returns=True):
         """-> (flat unclipped gradient (P,), returns (n_list, M*rows) or None)."""
         rows, horizon = obs.shape[0], max(rollout_list)
+        if self.backend == BACKEND_TC and full_bptt and rows * M > self.MAX_TC_FULL_BPTT_ROWS:
+            return self._policy_grad_chunked(obs, rollout_list, list_w, M, q_net, policy_net, noise, use_philox,
+                                             noise_seed, global_rows, row_offset, want_returns)
         self.ensure_capacity(rows * M, horizon)
         p = self._params(rows, M, horizon, rollout_list, list_w, full_bptt, q_net, policy_net, global_rows, row_offset,
                          noise_seed, use_philox)
@@ -181,6 +184,32 @@ class Engine:
         ret = self.empty(len(rollout_list), M * rows) if want_returns else None
         self._check(self.lib.mpg_policy_grad(self.h, ctypes.byref(p), _ptr(obs), _ptr(noise), _ptr(grad), _ptr(ret),
                                              self.stream))
+        return grad, ret
+
+    # The tensor-core full-BPTT path records 110 KB of dW operands per row: bound it per call.
+    MAX_TC_FULL_BPTT_ROWS = 131072
+
+    def _policy_grad_chunked(self, obs, rollout_list, list_w, M, q_net, policy_net, noise, use_philox, noise_seed,
+                             global_rows, row_offset, want_returns):
+        """Row chunks of one call: every chunk is scaled by 1/(M*global_rows) and keyed by its global row offset,
+        so the chunk gradients simply add up (the same property the multi-GPU shards rely on)."""
+        rows = obs.shape[0]
+        per = self.MAX_TC_FULL_BPTT_ROWS // M
+        grad, rets = None, []
+        for lo in range(0, rows, per):
+            hi = min(rows, lo + per)
+            nz = None
+            if noise is not None:   # (n, M*rows): columns m*rows + [lo, hi) of every tile
+                nz = torch.cat([noise[:, m * rows + lo: m * rows + hi] for m in range(M)], 1).contiguous()
+            g, r = self.policy_grad(obs[lo:hi].contiguous(), rollout_list, list_w, M=M, full_bptt=True, q_net=q_net,
+                                    policy_net=policy_net, noise=nz, use_philox=use_philox, noise_seed=noise_seed,
+                                    global_rows=global_rows or rows, row_offset=row_offset + lo, want_returns=want_returns)
+            grad = g if grad is None else grad.add_(g)
+            rets.append(r)
+        ret = None
+        if want_returns:   # back to the (n_list, M*rows) layout: tile m of all chunks, then tile m+1, ...
+            ret = torch.cat([torch.cat([r[:, m * (r.shape[1] // M):(m + 1) * (r.shape[1] // M)] for r in rets], 1)
+                             for m in range(M)], 1).contiguous()
         return grad, ret
 
     def rollout_forward(self, obs, rollout_list, M=1, q_net=_lib.NET_Q1, policy_net=_lib.NET_POLICY, start_actions=None,

@@ -384,3 +384,27 @@ def test_apply_gradients_on_device_matches_oracle(version):
     ref = O.policy_action([O.to_t(x, torch.float64) for x in w[2 if dq else 1]],
                           O.to_t(obs * np.asarray(args.obs_scale), torch.float64), 'tanh', None).numpy()
     assert rel_l2(act, ref) <= 1e-5
+
+
+def test_tc_full_bptt_row_chunking_matches_single_call():
+    """Engine.policy_grad splits big full-BPTT tensor-core calls into row chunks; chunked == unchunked."""
+    from mpg_b200.policy import PolicyWithQs
+    B, n, M = 700, 6, 2
+    args = default_args('NADP', PT, replay_batch_size=B, M=M)
+    pol = PolicyWithQs(**vars(args))
+    pol.set_weights(synthetic.make_policy_with_qs_weights(1, args.obs_dim, args.act_dim, 256, double_q=False))
+    e = pol.engine
+    if not e.tc_available():
+        pytest.skip('tensor-core backend does not cover this configuration')
+    e.set_backend(1)
+    obs = e.dev(synthetic.make_obs(np.random.default_rng(2), PT, B))
+    noise = e.dev(synthetic.make_noise(np.random.default_rng(3), n, B * M))
+    g0, r0 = e.policy_grad(obs, [0, n], [0.2, 0.8], M=M, noise=noise, full_bptt=True)
+    e.MAX_TC_FULL_BPTT_ROWS = 512          # force 3 chunks of 256 base rows
+    g1, r1 = e.policy_grad(obs, [0, n], [0.2, 0.8], M=M, noise=noise, full_bptt=True)
+    assert torch.allclose(r0, r1, rtol=0, atol=0)
+    assert rel_l2(g1.cpu().numpy(), g0.cpu().numpy()) <= 1e-5
+    gp0, _ = e.policy_grad(obs, [n], [1.0], M=M, use_philox=True, noise_seed=5, full_bptt=True)
+    e.MAX_TC_FULL_BPTT_ROWS = 131072
+    gp1, _ = e.policy_grad(obs, [n], [1.0], M=M, use_philox=True, noise_seed=5, full_bptt=True)
+    assert rel_l2(gp0.cpu().numpy(), gp1.cpu().numpy()) <= 1e-5
