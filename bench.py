@@ -29,6 +29,8 @@ import torch
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# stdout carries exactly ONE JSON line: NCCL prints its version banner / debug lines on stdout, send them to stderr
+os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
 
 from mpg_b200 import synthetic  # noqa: E402
 from mpg_b200.config import default_args  # noqa: E402
@@ -81,6 +83,17 @@ class ClockSampler:
                                        '-lms', '100', '-i', str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
+
+    def wait_first_sample(self, timeout=5.0):
+        """nvidia-smi needs up to a second to start on an 8-GPU box: do not begin before it is sampling."""
+        t0 = time.time()
+        while self.p is not None and time.time() - t0 < timeout:
+            try:
+                if os.path.getsize(self.f.name) > 0:
+                    return
+            except OSError:
+                return
+            time.sleep(0.05)
 
     def stop(self):
         out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[])
@@ -211,11 +224,13 @@ def main():
         torch.cuda.synchronize()
 
     # ---------------- device-resident metric ----------------
+    sampler = ClockSampler(local_rank) if rank == 0 else None   # runs through warm-up, timed region and e2e loop
+    if sampler:
+        sampler.wait_first_sample()
     for _ in range(opts.warmup):
         device_step()
     e.set_timing(True)
     barrier()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
     l0 = e.launch_count
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(opts.steps)]
     kernel_ms = []
@@ -235,7 +250,6 @@ def main():
         torch.cuda.synchronize()
         kernel_ms.append(e.kernel_ms())
     kernel_ms = [k for k in kernel_ms if k is not None and k > 0]
-    clocks = sampler.stop() if sampler else None
     e.set_timing(False)
     total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device='cuda')
     if world > 1:
@@ -259,6 +273,7 @@ def main():
     e2e_s = float(e2e_s.item())
     d2h = int(sum(g.nbytes for g in grads)) + 4 * 8
     e2e_value = rows * world * N_STEPS / e2e_s
+    clocks = sampler.stop() if sampler else None
 
     if rank != 0:
         if world > 1:
