@@ -33,7 +33,11 @@ typedef struct mpg_ctx mpg_ctx;
 enum {
   MPG_ENV_PATH_TRACKING = 0,            /* 'PathTracking-v0'            path_tracking_env.py:245-297 */
   MPG_ENV_INVERTED_PENDULUM = 1,        /* 'InvertedPendulumConti-v0'   inverted_pendulum_model.py:77-97 */
-  MPG_ENV_INVERTED_DOUBLE_PENDULUM = 2  /* 'InvertedDoublePendulum-v2'  inverted_double_pendulum_model.py:103-144 */
+  MPG_ENV_INVERTED_DOUBLE_PENDULUM = 2, /* 'InvertedDoublePendulum-v2'  inverted_double_pendulum_model.py:103-144 */
+  /* the REAL PathTracking environment (PathTrackingEnv, path_tracking_env.py:356-487: 200 Hz x 20 sub-steps, reference
+   * path projection). Forward only: as mpg_config.env it backs mpg_model_reset / mpg_env_step (state_dim 8); inside a
+   * PathTracking handle it is selected per call with mpg_rollout_params.real_env (MPG-v1 n-step targets). */
+  MPG_ENV_PATH_TRACKING_REAL = 3
 };
 
 /* network slots: PolicyWithQs.models + target_models (policy.py:72-89) */
@@ -81,7 +85,7 @@ typedef struct {
   int64_t row_offset;        /* first global row of this shard (keys the noise stream) */
   uint64_t noise_seed;       /* Philox key when `noise` is NULL */
   int32_t use_philox;        /* 1: in-kernel Philox4x32-10 N(0,1); 0: read `noise` (NULL noise + 0 => no noise) */
-  int32_t reserved;
+  int32_t real_env;          /* 1: roll the REAL PathTracking env instead of the model (forward-only calls, PathTracking handles) */
 } mpg_rollout_params;
 
 /* ---- lifetime ---------------------------------------------------------------------------- */
@@ -143,6 +147,15 @@ int mpg_q_target(mpg_ctx* ctx, int double_q, int rows, const float* rew, const f
 /* compute_td_error (mpg_learner.py:136-144, nadp.py:67-76) */
 int mpg_td_error(mpg_ctx* ctx, int rows, const float* obs, const float* act, const float* rew, const float* obs_tp1,
                  float* td_out, void* stream);
+
+/* Bootstrap on top of a partial return (compute_n_step_target, mpg_learner.py:153-169):
+ * out = base + coef * Q1_target(sigma o, pi_target(sigma o)); base (rows) e.g. sum_t gamma^t rho r_t, coef = gamma^T */
+int mpg_q_bootstrap(mpg_ctx* ctx, int rows, const float* base, float coef, const float* obs, float* out, void* stream);
+
+/* One step of the REAL environment (handles created with env = MPG_ENV_PATH_TRACKING_REAL):
+ * PathTrackingEnv.step (path_tracking_env.py:456-472). done_out (int32, may be NULL) = judge_done (:474-487). */
+int mpg_env_step(mpg_ctx* ctx, int rows, const float* state_in, const float* action, float* state_out, float* obs_out,
+                 float* rew_out, int32_t* done_out, void* stream);
 
 /* ---- single model step: <Env>Model.rollout_out ------------------------------------------- */
 /* state (rows, state_dim) in/out; obs_out (rows, obs_dim); rew_out (rows) RAW reward.

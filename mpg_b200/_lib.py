@@ -7,7 +7,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get('MPG_B200_LIB', os.path.join(_HERE, 'libmpg_b200.so'))  # override: kernel-variant A/B runs
 
 MAX_OBS, MAX_LIST = 16, 8
-ENV_IDS = {'PathTracking-v0': 0, 'InvertedPendulumConti-v0': 1, 'InvertedDoublePendulum-v2': 2}
+ENV_IDS = {'PathTracking-v0': 0, 'InvertedPendulumConti-v0': 1, 'InvertedDoublePendulum-v2': 2,
+           'PathTracking-v0-real': 3}   # the ground-truth PathTrackingEnv (forward only)
 NET_Q1, NET_Q2, NET_POLICY, NET_Q1_TARGET, NET_Q2_TARGET, NET_POLICY_TARGET = range(6)
 
 # every symbol include/mpg_b200.h declares (tests check that the library exports all of them)
@@ -19,7 +20,7 @@ SYMBOLS = [
     'mpg_clip_global_norm', 'mpg_philox_noise', 'mpg_launch_count', 'mpg_set_backend', 'mpg_get_backend',
     'mpg_set_timing', 'mpg_kernel_ms', 'mpg_tc_selftest', 'mpg_set_profile_buffer', 'mpg_adam_step', 'mpg_polyak_update',
     'mpg_replay_create', 'mpg_replay_destroy', 'mpg_replay_last_error', 'mpg_replay_size', 'mpg_replay_add',
-    'mpg_replay_sample', 'mpg_replay_update_priorities', 'mpg_replay_tree_stats',
+    'mpg_replay_sample', 'mpg_replay_update_priorities', 'mpg_replay_tree_stats', 'mpg_q_bootstrap', 'mpg_env_step',
 ]
 
 
@@ -36,7 +37,7 @@ class RolloutParams(ctypes.Structure):
                 ('n_list', ctypes.c_int32), ('list', ctypes.c_int32 * MAX_LIST), ('list_w', ctypes.c_float * MAX_LIST),
                 ('full_bptt', ctypes.c_int32), ('q_net', ctypes.c_int32), ('policy_net', ctypes.c_int32),
                 ('global_rows', ctypes.c_int64), ('row_offset', ctypes.c_int64), ('noise_seed', ctypes.c_uint64),
-                ('use_philox', ctypes.c_int32), ('reserved', ctypes.c_int32)]
+                ('use_philox', ctypes.c_int32), ('real_env', ctypes.c_int32)]
 
 
 _lib = None
@@ -89,6 +90,8 @@ def load():
         'mpg_set_profile_buffer': (i32, [vp, vp]),
         'mpg_adam_step': (i32, [vp, i32, vp, f32, i64, f32, f32, f32, vp]),
         'mpg_polyak_update': (i32, [vp, i32, i32, f32, vp]),
+        'mpg_q_bootstrap': (i32, [vp, i32, vp, f32, vp, vp, vp]),
+        'mpg_env_step': (i32, [vp, i32, vp, vp, vp, vp, vp, vp, vp]),
         'mpg_replay_create': (i32, [i32, i32, i32, ctypes.c_double, ctypes.c_double, P(vp)]),
         'mpg_replay_destroy': (None, [vp]),
         'mpg_replay_last_error': (ctypes.c_char_p, [vp]),

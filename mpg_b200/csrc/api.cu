@@ -234,10 +234,14 @@ int fill_rollout_args(mpg_ctx* ctx, const mpg_rollout_params* p, RolloutArgs& a)
 }
 
 template <bool BWD>
-int launch_rollout(mpg_ctx* ctx, const RolloutArgs& a, int grid, cudaStream_t st) {
+int launch_rollout(mpg_ctx* ctx, const RolloutArgs& a, int grid, cudaStream_t st, int env) {
   const size_t smem = Smem::FLOATS * 4;
   if (ctx->timing) cudaEventRecord(ctx->ev0, st);
-  switch (ctx->cfg.env) {
+  if (env == MPG_ENV_PATH_TRACKING_REAL) {
+    if (BWD) return fail(ctx, MPG_ERR_UNSUPPORTED, "the real environment is forward only%s");
+    rollout_kernel<MPG_ENV_PATH_TRACKING_REAL, false><<<grid, NT, smem, st>>>(a);
+  } else
+  switch (env) {
     case MPG_ENV_PATH_TRACKING: rollout_kernel<MPG_ENV_PATH_TRACKING, BWD><<<grid, NT, smem, st>>>(a); break;
     case MPG_ENV_INVERTED_PENDULUM: rollout_kernel<MPG_ENV_INVERTED_PENDULUM, BWD><<<grid, NT, smem, st>>>(a); break;
     default: rollout_kernel<MPG_ENV_INVERTED_DOUBLE_PENDULUM, BWD><<<grid, NT, smem, st>>>(a); break;
@@ -308,10 +312,10 @@ int mpg_create(const mpg_config* cfg, mpg_ctx** out) {
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
     return fail(nullptr, MPG_ERR_CUDA, "no CUDA device: mpg_b200 has no CPU fallback%s");
   if (cfg->hidden != H) return fail(nullptr, MPG_ERR_UNSUPPORTED, "only hidden = 256 (2 hidden layers) is built%s");
-  if (cfg->env < 0 || cfg->env > 2) return fail(nullptr, MPG_ERR_ARG, "unknown env%s");
-  static const int SD[3] = {6, 4, 6}, AD[3] = {2, 1, 1};
+  if (cfg->env < 0 || cfg->env > 3) return fail(nullptr, MPG_ERR_ARG, "unknown env%s");
+  static const int SD[4] = {6, 4, 6, 8}, AD[4] = {2, 1, 1, 2};
   if (cfg->act_dim != AD[cfg->env]) return fail(nullptr, MPG_ERR_ARG, "act_dim does not match env%s");
-  const int want_obs = cfg->env == 0 ? 6 + cfg->num_future_data : (cfg->env == 1 ? 4 : 11);
+  const int want_obs = (cfg->env == 0 || cfg->env == 3) ? 6 + cfg->num_future_data : (cfg->env == 1 ? 4 : 11);
   if (cfg->obs_dim != want_obs || cfg->obs_dim > MPG_MAX_OBS) return fail(nullptr, MPG_ERR_ARG, "obs_dim does not match env%s");
   if (cfg->max_rows <= 0 || cfg->max_horizon < 0) return fail(nullptr, MPG_ERR_ARG, "bad capacity%s");
   mpg_ctx* c = new (std::nothrow) mpg_ctx();
@@ -363,6 +367,7 @@ int mpg_create(const mpg_config* cfg, mpg_ctx** out) {
   rc |= set_smem(c, rollout_kernel<MPG_ENV_INVERTED_PENDULUM, false>);
   rc |= set_smem(c, rollout_kernel<MPG_ENV_INVERTED_DOUBLE_PENDULUM, true>);
   rc |= set_smem(c, rollout_kernel<MPG_ENV_INVERTED_DOUBLE_PENDULUM, false>);
+  rc |= set_smem(c, rollout_kernel<MPG_ENV_PATH_TRACKING_REAL, false>);
   rc |= set_smem(c, q_grad_kernel);
   rc |= set_smem(c, eval_kernel);
   if (rc) {
@@ -466,6 +471,7 @@ int mpg_get_weights(mpg_ctx* ctx, int net, float* const w[6], void* stream) {
 int mpg_policy_grad(mpg_ctx* ctx, const mpg_rollout_params* p, const float* obs, const float* noise, float* grad_out,
                     float* returns_out, void* stream) {
   if (!ctx || !p || !obs || !grad_out) return fail(ctx, MPG_ERR_ARG, "null argument to mpg_policy_grad%s");
+  if (p->real_env || ctx->cfg.env == MPG_ENV_PATH_TRACKING_REAL) return fail(ctx, MPG_ERR_UNSUPPORTED, "the real environment is forward only%s");
   cudaStream_t st = (cudaStream_t)stream;
   RolloutArgs a;
   int rc = fill_rollout_args(ctx, p, a);
@@ -508,7 +514,7 @@ int mpg_policy_grad(mpg_ctx* ctx, const mpg_rollout_params* p, const float* obs,
   const int ntiles = (MB + TILE_R - 1) / TILE_R;
   const int grid = ntiles < ctx->sms ? ntiles : ctx->sms;
   CUDA_OK(ctx, cudaMemsetAsync(ctx->partial, 0, (size_t)grid * ctx->partial_stride * sizeof(float), st));
-  rc = launch_rollout<true>(ctx, a, grid, st);
+  rc = launch_rollout<true>(ctx, a, grid, st, ctx->cfg.env);
   if (rc) return rc;
   reduce_partials_kernel<<<(L.total + 255) / 256, 256, 0, st>>>(ctx->partial, ctx->partial_stride, grid, L.total,
                                                                 grad_out, nullptr, nullptr);
@@ -530,6 +536,12 @@ int mpg_rollout_forward(mpg_ctx* ctx, const mpg_rollout_params* p, const float* 
   a.traj_obs = traj_obs; a.traj_rew = traj_rew; a.traj_act = traj_act;
   a.noise_mode = noise ? 1 : (p->use_philox ? 2 : 0);
   const int MB = p->rows * p->M;
+  int env = ctx->cfg.env;
+  if (p->real_env) {
+    if (ctx->cfg.env != MPG_ENV_PATH_TRACKING && ctx->cfg.env != MPG_ENV_PATH_TRACKING_REAL)
+      return fail(ctx, MPG_ERR_UNSUPPORTED, "real_env rollouts exist for PathTracking only (the pendulum ground truth is mujoco)%s");
+    env = MPG_ENV_PATH_TRACKING_REAL;
+  }
   if (ctx->backend == MPG_BACKEND_TC) {
     const int ntiles = (MB + tc::ACT_ROWS - 1) / tc::ACT_ROWS;
     const int grid = ntiles < ctx->sms ? ntiles : ctx->sms;
@@ -540,14 +552,14 @@ int mpg_rollout_forward(mpg_ctx* ctx, const mpg_rollout_params* p, const float* 
     if (a.has_q) ta.q = tc_net(ctx->tc, p->q_net, ctx->nets[p->q_net].flat, a.q.in_dim, a.q.out_dim);
     ta.act_ckpt = ctx->tc.act_ckpt;
     if (ctx->timing) cudaEventRecord(ctx->ev0, st);
-    CUDA_OK(ctx, tc_launch_rollout<false>(ctx->cfg.env, ta, grid, st));
+    CUDA_OK(ctx, tc_launch_rollout<false>(env, ta, grid, st));
     if (ctx->timing) { cudaEventRecord(ctx->ev1, st); ctx->timed = 1; }
     ctx->launches++;
     return MPG_OK;
   }
   const int ntiles = (MB + TILE_R - 1) / TILE_R;
   const int grid = ntiles < ctx->sms ? ntiles : ctx->sms;
-  return launch_rollout<false>(ctx, a, grid, st);
+  return launch_rollout<false>(ctx, a, grid, st, env);
 }
 
 int mpg_returns_stats(mpg_ctx* ctx, const float* returns, int n_list, int rows, int M, float* out, void* stream) {
@@ -638,7 +650,8 @@ int mpg_q_grad(mpg_ctx* ctx, int net, int rows, int64_t global_rows, const float
 static int launch_eval(mpg_ctx* ctx, EvalArgs& a, void* stream) {
   const mpg_config& c = ctx->cfg;
   a.obs_dim = c.obs_dim; a.act_dim = c.act_dim; a.policy_out_tanh = c.policy_out_tanh;
-  a.action_range = c.action_range; a.rew_scale = c.rew_scale; a.rew_shift = c.rew_shift; a.gamma = c.gamma;
+  a.action_range = c.action_range; a.rew_scale = c.rew_scale; a.rew_shift = c.rew_shift;
+  if (a.mode != 4) a.gamma = c.gamma;   // mode 4 carries its own coefficient (gamma^T)
   for (int i = 0; i < MPG_MAX_OBS; ++i) a.obs_scale[i] = c.obs_scale[i];
   const int ntiles = (a.rows + TILE_R - 1) / TILE_R;
   const int grid = ntiles < ctx->sms ? ntiles : ctx->sms;
@@ -683,6 +696,19 @@ int mpg_q_target(mpg_ctx* ctx, int double_q, int rows, const float* rew, const f
   return launch_eval(ctx, a, stream);
 }
 
+int mpg_q_bootstrap(mpg_ctx* ctx, int rows, const float* base, float coef, const float* obs, float* out, void* stream) {
+  if (!ctx || !base || !obs || !out || rows <= 0) return fail(ctx, MPG_ERR_ARG, "bad argument to mpg_q_bootstrap%s");
+  int rc = check_net(ctx, MPG_NET_POLICY_TARGET);
+  if (!rc) rc = check_net(ctx, MPG_NET_Q1_TARGET);
+  if (rc) return rc;
+  EvalArgs a;
+  memset(&a, 0, sizeof(a));
+  a.mode = 4; a.rows = rows; a.obs = obs; a.rew = base; a.out = out; a.gamma = coef;
+  a.net0 = net_dev(ctx, MPG_NET_POLICY_TARGET); a.net1 = net_dev(ctx, MPG_NET_Q1_TARGET);
+  rc = launch_eval(ctx, a, stream);
+  return rc;
+}
+
 int mpg_td_error(mpg_ctx* ctx, int rows, const float* obs, const float* act, const float* rew, const float* obs_tp1,
                  float* td_out, void* stream) {
   if (!ctx || !obs || !act || !rew || !obs_tp1 || !td_out || rows <= 0) return fail(ctx, MPG_ERR_ARG, "bad argument to mpg_td_error%s");
@@ -701,6 +727,7 @@ int mpg_td_error(mpg_ctx* ctx, int rows, const float* obs, const float* act, con
   switch ((ctx)->cfg.env) {                                               \
     case MPG_ENV_PATH_TRACKING: { constexpr int EV = MPG_ENV_PATH_TRACKING; CALL; } break; \
     case MPG_ENV_INVERTED_PENDULUM: { constexpr int EV = MPG_ENV_INVERTED_PENDULUM; CALL; } break; \
+    case MPG_ENV_PATH_TRACKING_REAL: { constexpr int EV = MPG_ENV_PATH_TRACKING_REAL; CALL; } break; \
     default: { constexpr int EV = MPG_ENV_INVERTED_DOUBLE_PENDULUM; CALL; } break; \
   }
 
@@ -729,6 +756,7 @@ int mpg_model_step_bwd(mpg_ctx* ctx, int rows, const float* state_in, const floa
                        float* g_action, void* stream) {
   if (!ctx || !state_in || !action || !g_state_in || !g_action || rows <= 0)
     return fail(ctx, MPG_ERR_ARG, "bad argument to mpg_model_step_bwd%s");
+  if (ctx->cfg.env == MPG_ENV_PATH_TRACKING_REAL) return fail(ctx, MPG_ERR_UNSUPPORTED, "the real environment is forward only%s");
   cudaStream_t st = (cudaStream_t)stream;
   ENV_SWITCH(ctx, (model_step_bwd_kernel<EV><<<(rows + 127) / 128, 128, 0, st>>>(
                       rows, ctx->cfg.obs_dim, ctx->cfg.num_future_data, state_in, action, eps, g_obs_out, g_rew_out,
@@ -738,10 +766,22 @@ int mpg_model_step_bwd(mpg_ctx* ctx, int rows, const float* state_in, const floa
   return MPG_OK;
 }
 
+int mpg_env_step(mpg_ctx* ctx, int rows, const float* state_in, const float* action, float* state_out, float* obs_out,
+                 float* rew_out, int32_t* done_out, void* stream) {
+  if (!ctx || !state_in || !action || !state_out || rows <= 0) return fail(ctx, MPG_ERR_ARG, "bad argument to mpg_env_step%s");
+  if (ctx->cfg.env != MPG_ENV_PATH_TRACKING_REAL) return fail(ctx, MPG_ERR_STATE, "mpg_env_step needs a handle created with MPG_ENV_PATH_TRACKING_REAL%s");
+  env_step_kernel<<<(rows + 127) / 128, 128, 0, (cudaStream_t)stream>>>(rows, ctx->cfg.obs_dim, ctx->cfg.num_future_data, state_in,
+                                                                        action, state_out, obs_out, rew_out, done_out);
+  ctx->launches++;
+  CUDA_OK(ctx, cudaGetLastError());
+  return MPG_OK;
+}
+
 int mpg_compute_rewards(mpg_ctx* ctx, int rows, const float* state, const float* scaled_action, float* rew_out,
                         void* stream) {
   if (!ctx || !state || !rew_out || rows <= 0) return fail(ctx, MPG_ERR_ARG, "bad argument to mpg_compute_rewards%s");
-  if (ctx->cfg.env == MPG_ENV_PATH_TRACKING && !scaled_action) return fail(ctx, MPG_ERR_ARG, "PathTracking rewards need actions%s");
+  if ((ctx->cfg.env == MPG_ENV_PATH_TRACKING || ctx->cfg.env == MPG_ENV_PATH_TRACKING_REAL) && !scaled_action)
+    return fail(ctx, MPG_ERR_ARG, "PathTracking rewards need actions%s");
   cudaStream_t st = (cudaStream_t)stream;
   ENV_SWITCH(ctx, (rewards_kernel<EV><<<(rows + 127) / 128, 128, 0, st>>>(rows, state, scaled_action, rew_out)));
   ctx->launches++;

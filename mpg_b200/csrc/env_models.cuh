@@ -318,11 +318,102 @@ struct Env<MPG_ENV_INVERTED_DOUBLE_PENDULUM> {
   }
 };
 
+// =============================================================================================
+// PathTracking REAL environment (the ground truth the model approximates):
+// PathTrackingEnv.reset(init_obs)/step/_get_obs/judge_done (path_tracking_env.py:356-487), VehicleDynamics.simulation
+// (:144-179: 20 sub-steps of the non-model f_xu at 200 Hz with v_x clip, semi-implicit pose integration, projection on
+// the reference path, period / angle wraps) and ReferencePath (:202-242).  Forward only (it is used for targets and
+// acting, never differentiated).  state = (v_x, v_y, r, delta_y, delta_phi, x, y, phi).
+// =============================================================================================
+constexpr int MPG_ENV_PT_REAL = MPG_ENV_PATH_TRACKING_REAL;
+template <>
+struct Env<MPG_ENV_PT_REAL> {
+  using Mdl = Env<MPG_ENV_PATH_TRACKING>;
+  static constexpr int S = 8, A = 2;
+  static constexpr bool HAS_NOISE = false;
+  static constexpr float PI_F = 3.14159265358979323846f;
+  static constexpr float PERIOD = 1200.f, FREQ = 200.f;
+  static constexpr int SUBSTEPS = 20;
+
+  __device__ static float path_y(float x) {   // ReferencePath.compute_path_y (:207-212), fp32 in the reference's op order
+    return 7.5f * sinf(x * 2.f * PI_F / 200.f) + 2.5f * sinf(x * 2.f * PI_F / 300.f) + (-5.f) * sinf(x * 2.f * PI_F / 400.f);
+  }
+  __device__ static float path_phi(float x) {  // compute_path_phi (:214-220)
+    const float d = (float)(7.5 * 2 * 3.14159265358979323846 / 200.) * cosf(x * 2.f * PI_F / 200.f)
+                    + (float)(2.5 * 2 * 3.14159265358979323846 / 300.) * cosf(x * 2.f * PI_F / 300.f)
+                    + (float)(-5. * 2 * 3.14159265358979323846 / 400.) * cosf(x * 2.f * PI_F / 400.f);
+    return atanf(d);
+  }
+  __device__ static void reset(const float* o, float* s) {   // reset(init_obs=...) (:410-420)
+    Mdl::reset(o, s);
+    s[6] = s[3] + path_y(s[5]);
+    s[7] = s[4] + path_phi(s[5]);
+  }
+  __device__ static void get_obs(const float* s, float* o, int nfd) {   // _get_obs (:384-402)
+    o[0] = s[0] - 20.f; o[1] = s[1]; o[2] = s[2]; o[3] = s[3]; o[4] = s[4]; o[5] = s[5];
+    float x_ = s[5];
+    for (int i = 0; i < nfd; ++i) {
+      x_ += s[0] * 1.f / FREQ * (float)SUBSTEPS * 2.f;
+      o[6 + i] = s[6] - path_y(x_);
+    }
+  }
+  // step (:456-472); returns the RAW reward (pre-step state, clipped scaled action); *done gets judge_done (:474-487)
+  __device__ static float step_done(float* s, const float* act, int* done) {
+    float steer = act[0] * 1.2f * PI_F / 9.f, ax = act[1] * 3.f;
+    const float smax = 1.2f * PI_F / 9.f;
+    steer = fminf(fmaxf(steer, -smax), smax);
+    ax = fminf(fmaxf(ax, -3.f), 3.f);
+    const float rew = Mdl::reward_pre(s, steer, ax);
+    constexpr float tau = 1.f / 200.f;
+    constexpr float Cf = Mdl::Cf, Cr = Mdl::Cr, a = Mdl::a, b = Mdl::b, m = Mdl::m, Iz = Mdl::Iz;
+    float vx = s[0], vy = s[1], r = s[2], x = s[5], y = s[6], phi = s[7], dy = s[3], dphi = s[4];
+    float alpha_f = 0.f, alpha_r = 0.f, vx_in = vx;
+    for (int it = 0; it < SUBSTEPS; ++it) {
+      vx_in = vx;
+      alpha_f = atanf((vy + a * r) / vx) - steer;   // stability_related of THIS prediction call (:105-106)
+      alpha_r = atanf((vy - b * r) / vx);
+      const float vx1 = fminf(fmaxf(vx + tau * (ax + vy * r), 1.f), 35.f);
+      const float vy1 = (m * vy * vx + tau * Mdl::K * r - tau * Cf * steer * vx - tau * m * vx * vx * r) / (m * vx - tau * Mdl::CfCr);
+      const float r1 = (-Iz * r * vx - tau * Mdl::K * vy + tau * a * Cf * steer * vx) / (tau * Mdl::A2 - Iz * vx);
+      // pose: phi first (numpy views make the following lines see the UPDATED phi), old v_x, v_y, r (:160-165)
+      phi += r / FREQ;
+      float sn, cs;
+      sincosf(phi, &sn, &cs);
+      y += (vx * sn + vy * cs) / FREQ;
+      x += (vx * cs - vy * sn) / FREQ;
+      vx = vx1; vy = vy1; r = r1;
+      dphi = phi - path_phi(x);
+      dy = y - path_y(x);
+      if (phi > PI_F) phi -= 2.f * PI_F;
+      if (phi <= -PI_F) phi += 2.f * PI_F;
+      if (x > PERIOD) x -= PERIOD;
+      if (x <= 0.f) x += PERIOD;
+      if (dphi > PI_F) dphi -= 2.f * PI_F;
+      if (dphi <= -PI_F) dphi += 2.f * PI_F;
+    }
+    s[0] = vx; s[1] = vy; s[2] = r; s[3] = dy; s[4] = dphi; s[5] = x; s[6] = y; s[7] = phi;
+    if (done) {
+      // bounds from the last prediction call (:97-104,135-137); g = 9.81, miu = 1
+      const float g = 9.81f, F_zf = b * m * g / (a + b), F_zr = a * m * g / (a + b);
+      const float F_xf = ax < 0.f ? m * ax / 2.f : 0.f, F_xr = ax < 0.f ? m * ax / 2.f : m * ax;
+      const float miu_f = sqrtf(F_zf * F_zf - F_xf * F_xf) / F_zf, miu_r = sqrtf(F_zr * F_zr - F_xr * F_xr) / F_zr;
+      const float af_b = 3.f * miu_f * F_zf / Cf, ar_b = 3.f * miu_r * F_zr / Cr;   // negative: C_f, C_r < 0
+      const float r_b = miu_r * g / fabsf(vx_in);   // |v_x| entering the last sub-step, like the last prediction() call
+      *done = (fabsf(dy) > 3.f) | (fabsf(dphi) > PI_F / 4.f) | (vx < 2.f) | (alpha_f < -af_b) | (alpha_f > af_b)
+              | (alpha_r < -ar_b) | (alpha_r > ar_b) | (r < -r_b) | (r > r_b);
+    }
+    return rew;
+  }
+  __device__ static float step(float* s, const float* act, float, bool) { return step_done(s, act, nullptr); }
+  __device__ static void obs_grad_to_state(const float*, const float*, int, float*) {}
+};
+
 // uniform wrapper so the rollout kernel does not care whether the reward is pre- or post-step
 template <int ENV>
 __device__ __forceinline__ void env_step_bwd(const float* s, const float* act, const float* lam, float rc, float* gs,
                                              float* ga, const float* s1) {
   if constexpr (ENV == MPG_ENV_PATH_TRACKING) Env<ENV>::step_bwd(s, act, lam, rc, gs, ga);
+  else if constexpr (ENV == MPG_ENV_PT_REAL) { }   // the real environment is never differentiated
   else Env<ENV>::step_bwd(s, act, lam, rc, gs, ga, s1);
 }
 

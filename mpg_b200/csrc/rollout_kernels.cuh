@@ -287,6 +287,8 @@ __global__ void __launch_bounds__(NT, 1) q_grad_kernel(const __grid_constant__ Q
 //   mode 2: out = rho(r+shift) + gamma min(Q_net1, Q_net2)(sigma o', pi_net0(sigma o'))  (mpg_learner.py:126-134);
 //           single-Q when n_q == 1 (mpg_learner.py:147-152)
 //   mode 3: out = rho(r+shift) + gamma Q_net1(sigma o', pi_net0(sigma o')) - Q_net2(sigma o, a)  (mpg_learner.py:136-144)
+//   mode 4: out = rew[row] + gamma * Q_net1(sigma o, pi_net0(sigma o))   (n-step bootstrap, mpg_learner.py:153-169;
+//           `rew` carries the partial return, `gamma` the coefficient gamma^T)
 // ---------------------------------------------------------------------------------------------
 struct EvalArgs {
   int mode, obs_dim, act_dim, rows, n_q, policy_out_tanh;
@@ -346,6 +348,11 @@ __global__ void __launch_bounds__(NT, 1) eval_kernel(const __grid_constant__ Eva
       float q = q_eval(a.net1);
       if (a.n_q == 2) q = fminf(q, q_eval(a.net2));
       if (valid) a.out[row] = (a.rew[row] + a.rew_shift) * a.rew_scale + a.gamma * q;
+    } else if (a.mode == 4) {
+      load_obs(a.obs);
+      policy_to_xin(a.net0);
+      float q = q_eval(a.net1);
+      if (valid) a.out[row] = a.rew[row] + a.gamma * q;
     } else {
       load_obs(a.obs2);
       policy_to_xin(a.net0);
@@ -395,6 +402,27 @@ __global__ void model_step_kernel(int rows, int obs_dim, int nfd, const float* _
   if (rew_out) rew_out[r] = rew;
 }
 
+// real PathTracking environment step with the done flag
+__global__ void env_step_kernel(int rows, int obs_dim, int nfd, const float* __restrict__ state_in,
+                                const float* __restrict__ action, float* __restrict__ state_out,
+                                float* __restrict__ obs_out, float* __restrict__ rew_out, int* __restrict__ done_out) {
+  using E = Env<MPG_ENV_PT_REAL>;
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  float s[E::S], act[E::A], o[MPG_MAX_OBS];
+#pragma unroll
+  for (int j = 0; j < E::S; ++j) s[j] = state_in[(size_t)r * E::S + j];
+  act[0] = action[(size_t)r * 2]; act[1] = action[(size_t)r * 2 + 1];
+  int done = 0;
+  const float rew = E::step_done(s, act, &done);
+#pragma unroll
+  for (int j = 0; j < E::S; ++j) state_out[(size_t)r * E::S + j] = s[j];
+  E::get_obs(s, o, nfd);
+  if (obs_out) for (int i = 0; i < obs_dim; ++i) obs_out[(size_t)r * obs_dim + i] = o[i];
+  if (rew_out) rew_out[r] = rew;
+  if (done_out) done_out[r] = done;
+}
+
 // g_state_in = J_s^T (E^T g_obs_out + g_state_out) + g_rew dr/ds ; g_action likewise
 template <int ENV>
 __global__ void model_step_bwd_kernel(int rows, int obs_dim, int nfd, const float* __restrict__ state_in,
@@ -435,8 +463,8 @@ __global__ void rewards_kernel(int rows, const float* __restrict__ state, const 
   float s[E::S];
 #pragma unroll
   for (int j = 0; j < E::S; ++j) s[j] = state[(size_t)r * E::S + j];
-  if constexpr (ENV == MPG_ENV_PATH_TRACKING)
-    rew[r] = E::reward_pre(s, scaled_action[(size_t)r * 2], scaled_action[(size_t)r * 2 + 1]);
+  if constexpr (ENV == MPG_ENV_PATH_TRACKING || ENV == MPG_ENV_PT_REAL)
+    rew[r] = Env<MPG_ENV_PATH_TRACKING>::reward_pre(s, scaled_action[(size_t)r * 2], scaled_action[(size_t)r * 2 + 1]);
   else
     rew[r] = E::reward_post(s);
 }

@@ -48,6 +48,7 @@ inline bool tc_init(TcState& t, const mpg_config& cfg, int /*sms*/, size_t& ws_b
        && tc_set_smem(tc::tc_rollout_kernel<MPG_ENV_INVERTED_PENDULUM, false>, sm)
        && tc_set_smem(tc::tc_rollout_kernel<MPG_ENV_INVERTED_DOUBLE_PENDULUM, true>, sm)
        && tc_set_smem(tc::tc_rollout_kernel<MPG_ENV_INVERTED_DOUBLE_PENDULUM, false>, sm)
+       && tc_set_smem(tc::tc_rollout_kernel<MPG_ENV_PATH_TRACKING_REAL, false>, sm)
        && tc_set_smem(tc::tc_dw_kernel, 2 * tc::DW_STAGE + 128 + 1024);
   t.ready = ok;
   return ok;
@@ -92,6 +93,11 @@ inline bool tc_ensure_store(TcState& t, size_t bytes) {
 template <bool BWD>
 inline cudaError_t tc_launch_rollout(int env, const tc::TcArgs& a, int grid, cudaStream_t st) {
   const size_t smem = tc::SM_TOTAL + 1024;
+  if (env == MPG_ENV_PATH_TRACKING_REAL) {
+    if (BWD) return cudaErrorNotSupported;
+    tc::tc_rollout_kernel<MPG_ENV_PATH_TRACKING_REAL, false><<<grid, tc::CTA_THREADS, smem, st>>>(a);
+    return cudaGetLastError();
+  }
   switch (env) {
     case MPG_ENV_PATH_TRACKING: tc::tc_rollout_kernel<MPG_ENV_PATH_TRACKING, BWD><<<grid, tc::CTA_THREADS, smem, st>>>(a); break;
     case MPG_ENV_INVERTED_PENDULUM: tc::tc_rollout_kernel<MPG_ENV_INVERTED_PENDULUM, BWD><<<grid, tc::CTA_THREADS, smem, st>>>(a); break;

@@ -36,7 +36,7 @@ class Engine:
         self.env_id, self.obs_dim, self.act_dim = env_id, int(obs_dim), int(act_dim)
         cfg = MpgConfig()
         cfg.env = ENV_IDS[env_id]
-        cfg.num_future_data = int(num_future_data) if env_id == 'PathTracking-v0' else 0
+        cfg.num_future_data = int(num_future_data) if env_id.startswith('PathTracking-v0') else 0
         cfg.obs_dim, cfg.act_dim, cfg.hidden = int(obs_dim), int(act_dim), int(hidden)
         cfg.policy_out_tanh = 1 if policy_out_activation == 'tanh' else 0
         cfg.action_range = float(action_range) if action_range is not None else 0.0
@@ -159,7 +159,7 @@ class Engine:
 
     # ------------------------------------------------------------------ rollouts
     def _params(self, rows, M, horizon, rollout_list, list_w, full_bptt, q_net, policy_net, global_rows, row_offset,
-                noise_seed, use_philox):
+                noise_seed, use_philox, real_env=False):
         p = RolloutParams()
         p.rows, p.M, p.horizon, p.n_list = int(rows), int(M), int(horizon), len(rollout_list)
         for i, k in enumerate(rollout_list):
@@ -167,7 +167,7 @@ class Engine:
             p.list_w[i] = float(list_w[i])
         p.full_bptt, p.q_net, p.policy_net = int(full_bptt), int(q_net), int(policy_net)
         p.global_rows, p.row_offset = int(global_rows or rows), int(row_offset)
-        p.noise_seed, p.use_philox = int(noise_seed), int(use_philox)
+        p.noise_seed, p.use_philox, p.real_env = int(noise_seed), int(use_philox), int(bool(real_env))
         return p
 
     def policy_grad(self, obs, rollout_list, list_w, M=1, full_bptt=True, q_net=_lib.NET_Q1, policy_net=_lib.NET_POLICY,
@@ -214,12 +214,12 @@ class Engine:
 
     def rollout_forward(self, obs, rollout_list, M=1, q_net=_lib.NET_Q1, policy_net=_lib.NET_POLICY, start_actions=None,
                         noise=None, use_philox=False, noise_seed=0, global_rows=None, row_offset=0, want_traj=False,
-                        horizon=None):
+                        horizon=None, real_env=False):
         rows = obs.shape[0]
         horizon = max(rollout_list) if horizon is None else horizon
         self.ensure_capacity(rows * M, horizon)
         p = self._params(rows, M, horizon, rollout_list, [1.0] * len(rollout_list), 0, q_net, policy_net, global_rows,
-                         row_offset, noise_seed, use_philox)
+                         row_offset, noise_seed, use_philox, real_env)
         ret = self.empty(max(len(rollout_list), 1), M * rows)
         traj = (None, None, None)
         if want_traj:
@@ -270,6 +270,21 @@ class Engine:
         self._check(self.lib.mpg_q_target(self.h, int(bool(double_q)), obs_tp1.shape[0], _ptr(rew), _ptr(obs_tp1),
                                           _ptr(out), self.stream))
         return out
+
+    def q_bootstrap(self, base, coef, obs):
+        """base + coef * Q1_target(sigma obs, pi_target(sigma obs)) (mpg_learner.py:153-169)."""
+        out = self.empty(obs.shape[0])
+        self._check(self.lib.mpg_q_bootstrap(self.h, obs.shape[0], _ptr(base), float(coef), _ptr(obs), _ptr(out), self.stream))
+        return out
+
+    def env_step(self, state, action):
+        """One step of the real PathTracking env (handle created with env_id 'PathTracking-v0-real')."""
+        rows = state.shape[0]
+        s1, o1, r = self.empty(rows, self.state_dim), self.empty(rows, self.obs_dim), self.empty(rows)
+        done = torch.empty(rows, dtype=torch.int32, device=self.device)
+        self._check(self.lib.mpg_env_step(self.h, rows, _ptr(state), _ptr(action), _ptr(s1), _ptr(o1), _ptr(r),
+                                          ctypes.c_void_p(done.data_ptr()), self.stream))
+        return s1, o1, r, done
 
     def td_error(self, obs, act, rew, obs_tp1):
         out = self.empty(obs.shape[0])

@@ -122,6 +122,35 @@ class InvertedDoublePendulumModel(_ModelBase):
         self.tau = 0.01
 
 
+class PathTrackingEnv(object):
+    """The REAL PathTracking environment (path_tracking_env.py:356-487) batched on the GPU: reset(init_obs=obs) and
+    step(action) -> (obs, reward, done, info) with the reference's 200 Hz x 20 sub-step simulation, reference-path
+    projection and judge_done.  Used by the MPG-v1 n-step targets (through the fused rollout) and available to
+    workers / evaluators.  Random resets (`reset()` without init_obs) draw from the reset law in mpg_b200.synthetic."""
+
+    def __init__(self, num_future_data=0, num_agent=1, **kwargs):
+        self.num_future_data, self.num_agent = num_future_data, num_agent
+        self.engine = Engine(env_id='PathTracking-v0-real', obs_dim=6 + num_future_data, act_dim=2, obs_scale=None,
+                             rew_scale=1.0, rew_shift=0.0, gamma=1.0, num_future_data=num_future_data, max_rows=64,
+                             max_horizon=0, device=kwargs.get('device'))
+        self.obs = self.state = self.done = self.action = None
+        self._rng = __import__('numpy').random.default_rng(int(kwargs.get('seed', 0)))
+
+    def reset(self, **kwargs):
+        if 'init_obs' in kwargs:
+            self.obs = self.engine.dev(kwargs['init_obs'])
+        else:
+            from .synthetic import make_obs
+            self.obs = self.engine.dev(make_obs(self._rng, 'PathTracking-v0', self.num_agent, self.num_future_data))
+        self.state = self.engine.model_reset(self.obs)
+        return self.obs
+
+    def step(self, action):
+        self.action = self.engine.dev(action)
+        self.state, self.obs, reward, self.done = self.engine.env_step(self.state, self.action)
+        return self.obs, reward, self.done, {}
+
+
 NAME2MODELCLS = dict([('PathTracking-v0', PathTrackingModel),
                       ('InvertedDoublePendulum-v2', InvertedDoublePendulumModel),
                       ('InvertedPendulumConti-v0', InvertedPendulumModel)])

@@ -38,11 +38,18 @@ class MPGLearner(LearnerBase):
         return self.engine.q_target(True, self._dev['batch_rewards'], self._dev['batch_obs_tp1'])
 
     def compute_n_step_target(self):  # mpg_learner.py:146-169
-        if self.sample_num_in_learner is not None:
-            raise NotImplementedError('MPG-v1 n-step targets step the REAL environment for sample_num_in_learner steps '
-                                      '(mpg_learner.py:87-124,153-169); the batched real-env sampler is SURVEY.md 8(f) '
-                                      'next #3. Use sample_num_in_learner=None (1-step target) or MPG-v2.')
-        return self.engine.q_target(False, self._dev['batch_rewards'], self._dev['batch_obs_tp1'])
+        d = self._dev
+        if self.sample_num_in_learner is None:
+            return self.engine.q_target(False, d['batch_rewards'], d['batch_obs_tp1'])
+        # MPG-v1: sample_num_in_learner steps of the REAL environment from the replay (obs, action) with the online
+        # policy (sample(), mpg_learner.py:87-124), then the Q1_target / policy_target bootstrap on the last obs
+        if self.args.env_id != 'PathTracking-v0':
+            raise NotImplementedError('the real-env n-step sampler is built for PathTracking-v0; the pendulum ground truth '
+                                      'is a mujoco simulation (inverted_pendulum_conti.py) that is not part of this build')
+        T = int(self.sample_num_in_learner)
+        ret, t_obs, _, _ = self.engine.rollout_forward(d['batch_obs'], [T], q_net=-1, start_actions=d['batch_actions'],
+                                                      want_traj=True, real_env=True)
+        return self.engine.q_bootstrap(ret[0].contiguous(), float(self.args.gamma) ** T, t_obs[T - 1].contiguous())
 
     def compute_td_error(self):  # mpg_learner.py:136-144
         d = self._dev

@@ -475,3 +475,113 @@ def apply_gradients(weights, states, iteration, grads, double_q, delay_update, t
         for i in range(nm):
             w[nm + i] = [tau * s_ + (1.0 - tau) * t_ for s_, t_ in zip(w[i], w[nm + i])]
     return w
+
+
+# ----------------------------------------------------------------------------------------------
+# real PathTracking environment: path_tracking_env.py:144-179,202-242,356-487
+# ----------------------------------------------------------------------------------------------
+class PathTrackingEnvOracle:
+    """numpy restatement of PathTrackingEnv.reset(init_obs) / step / _get_obs / judge_done with
+    VehicleDynamics.simulation and ReferencePath, in `dtype` (the reference runs it in float32)."""
+    curves = [(7.5, 200., 0.), (2.5, 300., 0.), (-5., 400., 0.)]
+    period = 1200.
+
+    def __init__(self, num_future_data=0, dtype=np.float64):
+        self.nfd, self.dt = num_future_data, dtype
+
+    def path_y(self, x):
+        y = np.zeros_like(x)
+        for mag, T, sh in self.curves:
+            y = y + self.dt(mag) * np.sin((x - self.dt(sh)) * self.dt(2) * self.dt(np.pi) / self.dt(T))
+        return y
+
+    def path_phi(self, x):
+        d = np.zeros_like(x)
+        for mag, T, sh in self.curves:
+            d = d + self.dt(mag * 2 * np.pi / T) * np.cos((x - self.dt(sh)) * self.dt(2) * self.dt(np.pi) / self.dt(T))
+        return np.arctan(d)
+
+    def reset(self, obs):
+        o = np.asarray(obs, self.dt)
+        self.veh = np.stack([o[:, 0] + 20, o[:, 1], o[:, 2], o[:, 3], o[:, 4], o[:, 5]], 1).astype(self.dt)
+        x = self.veh[:, 5]
+        self.full = self.veh.copy()
+        self.full[:, 4] = self.veh[:, 4] + self.path_phi(x)
+        self.full[:, 3] = self.veh[:, 3] + self.path_y(x)
+
+    def get_obs(self):
+        v, f = self.veh, self.full
+        cols = [v[:, 0] - 20, v[:, 1], v[:, 2], v[:, 3], v[:, 4], f[:, 5]]
+        x_ = f[:, 5].copy()
+        for _ in range(self.nfd):
+            x_ = x_ + f[:, 0] * self.dt(1. / 200) * self.dt(20 * 2)
+            cols.append(f[:, 3] - self.path_y(x_))
+        return np.stack(cols, 1)
+
+    def step(self, action):
+        dt, pi = self.dt, self.dt(np.pi)
+        a = np.asarray(action, dt)
+        u = np.stack([a[:, 0] * dt(1.2) * pi / dt(9), a[:, 1] * dt(3)], 1)
+        lim = np.array([1.2 * np.pi / 9, 3], np.float32).astype(dt)
+        u = np.clip(u, -lim, lim)
+        m = PathTrackingModel()
+        st = torch.as_tensor(self.veh)
+        reward = m.compute_rewards(st, torch.as_tensor(u)).numpy()
+        C_f, C_r, aa, bb, mass, I_z, g = m.C_f, m.C_r, m.a, m.b, m.mass, m.I_z, 9.81
+        veh, full = self.veh.copy(), self.full.copy()
+        for _ in range(20):
+            vx_in = veh[:, 0].copy()
+            alpha_f = np.arctan((veh[:, 1] + aa * veh[:, 2]) / veh[:, 0]) - u[:, 0]
+            alpha_r = np.arctan((veh[:, 1] - bb * veh[:, 2]) / veh[:, 0])
+            nxt = m.f_xu(torch.as_tensor(veh), torch.as_tensor(u), 1 / 200).numpy()
+            nxt[:, 0] = np.clip(nxt[:, 0], 1, 35)
+            vxs, vys, rs = full[:, 0].copy(), full[:, 1].copy(), full[:, 2].copy()
+            full[:, 4] = full[:, 4] + rs / dt(200)
+            phis = full[:, 4]                      # numpy view semantics of the reference: UPDATED phi below
+            full[:, 3] = full[:, 3] + (vxs * np.sin(phis) + vys * np.cos(phis)) / dt(200)
+            full[:, 5] = full[:, 5] + (vxs * np.cos(phis) - vys * np.sin(phis)) / dt(200)
+            full[:, 0:3] = nxt[:, 0:3]
+            py, pphi = self.path_y(full[:, 5]), self.path_phi(full[:, 5])
+            nxt[:, 4] = full[:, 4] - pphi
+            nxt[:, 3] = full[:, 3] - py
+            full[:, 4] = np.where(full[:, 4] > pi, full[:, 4] - 2 * pi, full[:, 4])
+            full[:, 4] = np.where(full[:, 4] <= -pi, full[:, 4] + 2 * pi, full[:, 4])
+            full[:, 5] = np.where(full[:, 5] > self.period, full[:, 5] - dt(self.period), full[:, 5])
+            full[:, 5] = np.where(full[:, 5] <= 0, full[:, 5] + dt(self.period), full[:, 5])
+            nxt[:, 5] = full[:, 5]
+            nxt[:, 4] = np.where(nxt[:, 4] > pi, nxt[:, 4] - 2 * pi, nxt[:, 4])
+            nxt[:, 4] = np.where(nxt[:, 4] <= -pi, nxt[:, 4] + 2 * pi, nxt[:, 4])
+            veh = nxt.astype(dt)
+        self.veh, self.full = veh, full
+        F_zf, F_zr = bb * mass * g / (aa + bb), aa * mass * g / (aa + bb)
+        ax = u[:, 1]
+        F_xf = np.where(ax < 0, mass * ax / 2, 0.0)
+        F_xr = np.where(ax < 0, mass * ax / 2, mass * ax)
+        miu_f, miu_r = np.sqrt(F_zf ** 2 - F_xf ** 2) / F_zf, np.sqrt(F_zr ** 2 - F_xr ** 2) / F_zr
+        af_b, ar_b, r_b = 3 * miu_f * F_zf / C_f, 3 * miu_r * F_zr / C_r, miu_r * g / np.abs(vx_in)
+        r = veh[:, 2]
+        done = (np.abs(veh[:, 3]) > 3) | (np.abs(veh[:, 4]) > np.pi / 4) | (veh[:, 0] < 2) | (alpha_f < -af_b) | \
+               (alpha_f > af_b) | (alpha_r < -ar_b) | (alpha_r > ar_b) | (r < -r_b) | (r > r_b)
+        return self.get_obs(), reward, done
+
+
+def mpg_v1_n_step_target(args, weights, batch, T, dtype=torch.float64):
+    """MPGLearner.compute_n_step_target with sample_num_in_learner = T (mpg_learner.py:87-124,146-169)."""
+    nets = Nets(weights, False, dtype)
+    npdt = np.float64 if dtype == torch.float64 else np.float32
+    sigma = to_t(args.obs_scale, dtype)
+    env = PathTrackingEnvOracle(args.num_future_data, npdt)
+    obs = np.asarray(batch[0], npdt)
+    env.reset(obs)
+    target = torch.zeros(obs.shape[0], dtype=dtype)
+    with torch.no_grad():
+        for t in range(T):
+            a = policy_action(nets.policy, to_t(obs, dtype) * sigma, args.policy_out_activation, args.action_range).numpy()
+            if t == 0:
+                a = np.asarray(batch[1], npdt)
+            obs, rew, _ = env.step(a)
+            target = target + (args.gamma ** t) * (to_t(rew, dtype) + args.rew_shift) * args.rew_scale
+        p = to_t(obs, dtype) * sigma
+        a_t = policy_action(nets.policy_t, p, args.policy_out_activation, args.action_range)
+        target = target + (args.gamma ** T) * q_value(nets.Q1_t, p, a_t)
+    return target.numpy(), obs

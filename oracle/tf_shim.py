@@ -317,6 +317,8 @@ def _squeeze(x, axis=None):
 
 
 def _where(c, a, b):
+    if not isinstance(c, torch.Tensor):
+        c = torch.as_tensor(np.asarray(c))
     return torch.where(c, _t(a), _t(b))
 
 
@@ -329,6 +331,10 @@ def install():
     if getattr(sys.modules.get('tensorflow'), '_is_mpg_shim', False):
         return
     torch.Tensor.numpy = _numpy_detached
+    if not hasattr(np, 'int'):
+        np.int = int    # removed numpy aliases the reference still uses (path_tracking_env.py:371, dummy_vec_env.py:22)
+    if not hasattr(np, 'bool'):
+        np.bool = bool
     _patch_numpy_operands()
     noop = lambda *a, **k: None
     tf = _mod(
@@ -390,9 +396,21 @@ def install():
         def reset(self, **k):
             return np.zeros(4, np.float32)
 
-    gym = _mod('gym', make=_DummyEnv,
+    class _Box:
+        def __init__(self, low=None, high=None, dtype=np.float32, **k):
+            self.low, self.high = np.asarray(low, dtype), np.asarray(high, dtype)
+
+    def _make(env_id=None, *a, **k):
+        # the reference relies on a gym registration of 'PathTracking-v0' that is not in its repository; the class
+        # it must point to is envs_and_models.path_tracking_env.PathTrackingEnv
+        if env_id == 'PathTracking-v0':
+            import importlib
+            return importlib.import_module('envs_and_models.path_tracking_env').PathTrackingEnv(**k)
+        return _DummyEnv(*a, **k)
+
+    gym = _mod('gym', make=_make,
                Env=_Env, core=_mod('gym.core', Wrapper=_Wrapper),
-               spaces=_mod('gym.spaces', Box=lambda *a, **k: None))
+               spaces=_mod('gym.spaces', Box=_Box))
     gym.utils = _mod('gym.utils', seeding=_mod('gym.utils.seeding', np_random=lambda s=None: (np.random.RandomState(s), s)))
     plt = _mod('matplotlib.pyplot', ion=noop, cla=noop)
     mpl = _mod('matplotlib', pyplot=plt)

@@ -215,6 +215,34 @@ def run_apply_gradients(case):
     return {'weights': np.concatenate([np.asarray(a, np.float64).ravel() for net in pol.get_weights() for a in net])}
 
 
+def run_real_env(case):
+    """The reference's real PathTrackingEnv (reset(init_obs) / step incl. done) and MPGLearner (MPG-v1)
+    compute_n_step_target with sample_num_in_learner = T: T real-env steps from the replay (obs, action) with the
+    online policy, Q1_target / policy_target bootstrap (mpg_learner.py:87-124,146-169)."""
+    from envs_and_models.path_tracking_env import PathTrackingEnv
+    from learners.mpg_learner import MPGLearner
+    from policy import PolicyWithQs
+    B, H, T, nfd = case['B'], case['H'], case['T'], case['nfd']
+    rng = np.random.default_rng(case['bseed'])
+    obs0 = synthetic.make_obs(rng, PT, B, nfd)
+    acts = rng.uniform(-1.2, 1.2, (case['n_env'], B, 2)).astype(np.float32)   # some beyond the clip range
+    env = PathTrackingEnv(num_future_data=nfd, num_agent=B)
+    env.reset(init_obs=obs0.copy())
+    o_l, r_l, d_l = [], [], []
+    for t in range(case['n_env']):
+        o, r, d, _ = env.step(acts[t])
+        o_l.append(np.asarray(o)); r_l.append(np.asarray(r)); d_l.append(np.asarray(d))
+    out = {'env_obs': np.stack(o_l), 'env_rew': np.stack(r_l), 'env_done': np.stack(d_l).astype(np.int32)}
+    args = default_args('MPG-v1', PT, replay_batch_size=B, num_future_data=nfd, value_num_hidden_units=H,
+                        policy_num_hidden_units=H, sample_num_in_learner=T)
+    learner = MPGLearner(PolicyWithQs, args)
+    learner.set_weights(synthetic.make_policy_with_qs_weights(case['wseed'], args.obs_dim, args.act_dim, H, double_q=False))
+    batch = make_batch(case['bseed'] + 1, PT, B, nfd)
+    learner.get_batch_data(batch, None, None)
+    out['batch_targets'] = np.asarray(learner.batch_data['batch_targets'])
+    return out
+
+
 def run_replay(case):
     """The reference's own PrioritizedReplayBuffer / segment trees (pure Python, imported unmodified) driven through
     add(weight=None), find_prefixsum_idx on explicit masses, sample_with_weights_and_idxes and update_priorities.
@@ -294,12 +322,14 @@ CASES = {
     'model_idp': dict(fn='model', env_id=IDP, B=32, H=64, n=25, nfd=0, wseed=131, bseed=132, nseed=133),
     'apply_grads_v2_h64': dict(fn='apply', version='MPG-v2', H=64, iters=5, wseed=141, gseed=142),
     'apply_grads_nadp_h64': dict(fn='apply', version='NADP', H=64, iters=4, wseed=151, gseed=152),
+    'real_env_h64': dict(fn='real_env', B=24, H=64, T=25, nfd=2, n_env=12, wseed=171, bseed=172),
+    'real_env_h256': dict(fn='real_env', B=16, H=256, T=25, nfd=0, n_env=4, wseed=181, bseed=182),
     'replay': dict(fn='replay', capacity=64, n_add0=40, n_add1=40, n_sample=128, n_update=50, seed=161),
     'rule_weights': dict(fn='rule', rollout_list=[0, 25], iterations=[0, 2000, 4000, 4500, 5000, 9000, 27000]),
     'rule_weights3': dict(fn='rule', rollout_list=[0, 3, 25], iterations=[0, 3000, 4500, 6000, 12000]),
 }
 FNS = dict(nadp=run_nadp, mpg=run_mpg, model=run_model, rule=run_weights_rule, apply=run_apply_gradients,
-           replay=run_replay)
+           replay=run_replay, real_env=run_real_env)
 
 
 def extract_mpc_fixture():
