@@ -179,6 +179,10 @@ int mpg_state_dim(const mpg_ctx* ctx);
  *   by the caller);  step: t = optimizer.iterations + 1.  Kernel-layout copies of the weights are re-packed. */
 int mpg_adam_step(mpg_ctx* ctx, int net, const float* grad, float lr, int64_t step, float beta1, float beta2, float eps,
                   void* stream);
+/* Adam moments of `net` (flat, Keras order, device pointers) -- what tf.train.Checkpoint stores for the optimizers in
+ * PolicyWithQs.save_weights / load_weights (policy.py:98-110).  Moments of a never-stepped net read as zeros. */
+int mpg_get_adam_state(mpg_ctx* ctx, int net, float* m, float* v, void* stream);
+int mpg_set_adam_state(mpg_ctx* ctx, int net, const float* m, const float* v, void* stream);
 /* Polyak target update (policy.py:158-171): dst = tau * src + (1 - tau) * dst, then re-pack dst */
 int mpg_polyak_update(mpg_ctx* ctx, int src_net, int dst_net, float tau, void* stream);
 

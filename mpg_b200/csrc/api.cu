@@ -419,6 +419,15 @@ static int repack(mpg_ctx* ctx, int net, cudaStream_t st) {
                                                                            : fail(ctx, MPG_ERR_CUDA, "tc weight pack failed%s");
 }
 
+static int adam_alloc(mpg_ctx* ctx, NetStore& ns, int n, cudaStream_t st) {
+  if (ns.adam_m) return MPG_OK;
+  CUDA_OK(ctx, cudaMalloc(&ns.adam_m, n * sizeof(float)));
+  CUDA_OK(ctx, cudaMalloc(&ns.adam_v, n * sizeof(float)));
+  CUDA_OK(ctx, cudaMemsetAsync(ns.adam_m, 0, n * sizeof(float), st));
+  CUDA_OK(ctx, cudaMemsetAsync(ns.adam_v, 0, n * sizeof(float), st));
+  return MPG_OK;
+}
+
 int mpg_adam_step(mpg_ctx* ctx, int net, const float* grad, float lr, int64_t step, float beta1, float beta2, float eps,
                   void* stream) {
   if (!ctx || !grad || step < 1) return fail(ctx, MPG_ERR_ARG, "bad argument to mpg_adam_step%s");
@@ -427,18 +436,39 @@ int mpg_adam_step(mpg_ctx* ctx, int net, const float* grad, float lr, int64_t st
   cudaStream_t st = (cudaStream_t)stream;
   NetStore& ns = ctx->nets[net];
   const int n = GradLayout(ns.in_dim, ns.out_dim).total;
-  if (!ns.adam_m) {
-    CUDA_OK(ctx, cudaMalloc(&ns.adam_m, n * sizeof(float)));
-    CUDA_OK(ctx, cudaMalloc(&ns.adam_v, n * sizeof(float)));
-    CUDA_OK(ctx, cudaMemsetAsync(ns.adam_m, 0, n * sizeof(float), st));
-    CUDA_OK(ctx, cudaMemsetAsync(ns.adam_v, 0, n * sizeof(float), st));
-  }
+  if ((rc = adam_alloc(ctx, ns, n, st))) return rc;
   const double t = (double)step;
   const float lr_t = (float)((double)lr * sqrt(1.0 - pow((double)beta2, t)) / (1.0 - pow((double)beta1, t)));
   adam_kernel<<<(n + 255) / 256, 256, 0, st>>>(ns.flat, ns.adam_m, ns.adam_v, grad, n, lr_t, beta1, beta2, eps);
   ctx->launches++;
   CUDA_OK(ctx, cudaGetLastError());
   return repack(ctx, net, st);
+}
+
+int mpg_get_adam_state(mpg_ctx* ctx, int net, float* m, float* v, void* stream) {
+  if (!ctx || !m || !v) return fail(ctx, MPG_ERR_ARG, "bad argument to mpg_get_adam_state%s");
+  int rc = check_net(ctx, net);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  NetStore& ns = ctx->nets[net];
+  const int n = GradLayout(ns.in_dim, ns.out_dim).total;
+  if ((rc = adam_alloc(ctx, ns, n, st))) return rc;
+  CUDA_OK(ctx, cudaMemcpyAsync(m, ns.adam_m, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  CUDA_OK(ctx, cudaMemcpyAsync(v, ns.adam_v, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return MPG_OK;
+}
+
+int mpg_set_adam_state(mpg_ctx* ctx, int net, const float* m, const float* v, void* stream) {
+  if (!ctx || !m || !v) return fail(ctx, MPG_ERR_ARG, "bad argument to mpg_set_adam_state%s");
+  int rc = check_net(ctx, net);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  NetStore& ns = ctx->nets[net];
+  const int n = GradLayout(ns.in_dim, ns.out_dim).total;
+  if ((rc = adam_alloc(ctx, ns, n, st))) return rc;
+  CUDA_OK(ctx, cudaMemcpyAsync(ns.adam_m, m, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  CUDA_OK(ctx, cudaMemcpyAsync(ns.adam_v, v, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return MPG_OK;
 }
 
 int mpg_polyak_update(mpg_ctx* ctx, int src_net, int dst_net, float tau, void* stream) {

@@ -154,6 +154,19 @@ class Engine:
     def adam_step(self, net, grad, lr, step, beta1=0.9, beta2=0.999, eps=1e-7):
         self._check(self.lib.mpg_adam_step(self.h, net, _ptr(grad), float(lr), int(step), beta1, beta2, eps, self.stream))
 
+    def get_adam_state(self, net):
+        n = self.param_count(net)
+        m, v = torch.empty(n, device=self.device), torch.empty(n, device=self.device)
+        self._check(self.lib.mpg_get_adam_state(self.h, net, _ptr(m), _ptr(v), self.stream))
+        return m.cpu().numpy(), v.cpu().numpy()
+
+    def set_adam_state(self, net, m, v):
+        m, v = self.dev(m).contiguous(), self.dev(v).contiguous()
+        if m.numel() != self.param_count(net) or v.numel() != m.numel():
+            raise ValueError('adam state size does not match the net')
+        self._check(self.lib.mpg_set_adam_state(self.h, net, _ptr(m), _ptr(v), self.stream))
+        torch.cuda.current_stream(self.device).synchronize()
+
     def polyak_update(self, src_net, dst_net, tau):
         self._check(self.lib.mpg_polyak_update(self.h, src_net, dst_net, float(tau), self.stream))
 

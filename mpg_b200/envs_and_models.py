@@ -150,6 +150,20 @@ class PathTrackingEnv(object):
         self.state, self.obs, reward, self.done = self.engine.env_step(self.state, self.action)
         return self.obs, reward, self.done, {}
 
+    def reset_done(self):
+        """reset() of the reference without init_obs (path_tracking_env.py:422-454): agents whose `done` flag is set
+        are re-drawn from the reset law, the others keep their state."""
+        import torch
+        from .synthetic import make_obs
+        if self.done is None:
+            return self.reset()
+        fresh = self.engine.dev(make_obs(self._rng, 'PathTracking-v0', self.num_agent, self.num_future_data))
+        fresh_state = self.engine.model_reset(fresh)
+        m = (self.done != 0).unsqueeze(1)
+        self.state = torch.where(m, fresh_state, self.state)
+        self.obs = torch.where(m, fresh, self.obs)
+        return self.obs
+
 
 NAME2MODELCLS = dict([('PathTracking-v0', PathTrackingModel),
                       ('InvertedDoublePendulum-v2', InvertedDoublePendulumModel),

@@ -6,7 +6,8 @@ Kept: constructor keywords, get_weights / set_weights nested-list format
 compute_action / compute_mode / compute_target_action / compute_Q1 / compute_Q2 / compute_Q1_target /
 compute_Q2_target on RAW-scaled ("processed") observations exactly like the reference.
 apply_gradients (policy.py:123-171) runs on the device-resident weights: Keras-Adam with PolynomialDecay
-learning rates, delayed policy update and Polyak targets. Checkpoints are not built.
+learning rates, delayed policy update and Polyak targets.  save_weights / load_weights
+(policy.py:98-110) write one .npz per iteration: weights, target weights, Adam moments and step counters.
 """
 import numpy as np
 import torch
@@ -76,6 +77,29 @@ class PolicyWithQs(object):
         slots = self.model_slots + self.target_slots
         for i, w in enumerate(weights):
             self.engine.set_net_weights(slots[i], w)
+
+    def save_weights(self, save_dir, iteration):
+        """policy.py:98-103: models + target models + optimizers of one iteration -> save_dir/ckpt_ite<iteration>.npz"""
+        import os
+        os.makedirs(save_dir, exist_ok=True)
+        blob = {}
+        for s in self.model_slots + self.target_slots:
+            for i, w in enumerate(self.engine.get_net_weights(s)):
+                blob['net%d_w%d' % (s, i)] = w
+        for s in self.model_slots:
+            blob['net%d_adam_m' % s], blob['net%d_adam_v' % s] = self.engine.get_adam_state(s)
+            blob['net%d_opt_iterations' % s] = np.int64(self.opt_iterations.get(s, 0))
+        np.savez(os.path.join(save_dir, 'ckpt_ite%d.npz' % iteration), **blob)
+
+    def load_weights(self, load_dir, iteration):
+        """policy.py:105-110"""
+        import os
+        with np.load(os.path.join(load_dir, 'ckpt_ite%d.npz' % iteration)) as blob:
+            for s in self.model_slots + self.target_slots:
+                self.engine.set_net_weights(s, [blob['net%d_w%d' % (s, i)] for i in range(6)])
+            for s in self.model_slots:
+                self.engine.set_adam_state(s, blob['net%d_adam_m' % s], blob['net%d_adam_v' % s])
+                self.opt_iterations[s] = int(blob['net%d_opt_iterations' % s])
 
     @staticmethod
     def polynomial_decay(schedule, step):

@@ -35,3 +35,9 @@ class Preprocessor(object):
 
     def get_params(self):
         return {}
+
+    def save_params(self, save_dir):  # preprocessor.py:176-182
+        np.save(save_dir + '/ppc_params.npy', self.get_params())
+
+    def load_params(self, load_dir):
+        self.set_params(np.load(load_dir + '/ppc_params.npy', allow_pickle=True).item())
