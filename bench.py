@@ -29,8 +29,15 @@ import torch
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-# stdout carries exactly ONE JSON line: NCCL prints its version banner / debug lines on stdout, send them to stderr
-os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
+# stdout carries exactly ONE JSON line: everything else that writes to fd 1 (NCCL's version banner, library chatter)
+# is sent to stderr; the JSON line goes to a private duplicate of the original stdout.
+_JSON_FD = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line):
+    os.write(_JSON_FD, (json.dumps(line) + '\n').encode())
+
 
 from mpg_b200 import synthetic  # noqa: E402
 from mpg_b200.config import default_args  # noqa: E402
@@ -126,6 +133,11 @@ class ClockSampler:
         return out
 
 
+def workload_name(rows):
+    return ('PathTrackingModel NADP (pure n-step ADP gradient, full BPTT), n=25, H=256, '
+            f'B={rows} rows per GPU (BASELINE.json configs[1])')
+
+
 def run_reference(opts, rank):
     """Reference arm: the restated TF2 learner on the host cores, bounded sample of the workload."""
     if rank != 0:
@@ -148,15 +160,16 @@ def run_reference(opts, rank):
     value = sample_rows * N_STEPS / dt
     sample = (f'{sample_rows} of {ROWS_PER_GPU} rows per step, full NADP compute_gradient (Q-target rollout + Q grad + '
               f'policy rollout fwd+bwd + clip), PyTorch-CPU fp32 restatement of the TF2 learner, {threads} threads')
-    print(json.dumps({
+    emit({
         'impl': 'reference', 'metric': 'model state-steps/s (fwd+bwd, n=25)', 'value': value,
         'unit': 'state-steps/s', 'n_gpus': opts.gpus, 'steps': opts.steps, 'warmup': opts.warmup,
         'ms_per_step': dt * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
         'data': 'synthetic', 'updates_per_s': 1.0 / dt,
-        'config': {'workload': 'PathTrackingModel NADP n=25 H=256, B=65536 per GPU (bounded CPU sample: 4096 rows)'},
+        'config': {'workload': workload_name(ROWS_PER_GPU), 'global_batch': ROWS_PER_GPU * opts.gpus, 'horizon': N_STEPS,
+                   'sample': f'{sample_rows} of {ROWS_PER_GPU} rows per step on the host cores'},
         'cpu_baseline': {'value': value, 'unit': 'state-steps/s', 'cores': threads, 'kind': 'port', 'sample': sample},
         'e2e': {'value': value, 'unit': 'state-steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
-    }), flush=True)
+    })
 
 
 def main():
@@ -333,8 +346,7 @@ def main():
         'metric': 'model state-steps/s (fwd+bwd, n=25)', 'value': value, 'unit': 'state-steps/s', 'n_gpus': world,
         'steps': opts.steps, 'warmup': opts.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': 'PathTrackingModel NADP (pure n-step ADP gradient, full BPTT), n=25, H=256, '
-                               f'B={rows} rows per GPU (BASELINE.json configs[1])',
+        'config': {'workload': workload_name(rows),
                    'global_batch': rows * world, 'horizon': N_STEPS, 'backend': backend,
                    'noise': 'in-kernel Philox4x32-10 keyed (seed, global row, step)',
                    'cache': 'L2 flushed between timed iterations (256 MiB memset)',
@@ -350,7 +362,7 @@ def main():
         'cpu_baseline': cpu_baseline,
         'target_state_steps_per_s_per_gpu': 1e8,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
