@@ -43,6 +43,9 @@ struct mpg_ctx {
   int timing = 0, timed = 0;
   long long* prof = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaStream_t aux = nullptr;             // side stream: weight-gradient GEMMs of finished waves run under the tail wave
+  cudaEvent_t ev_wave = nullptr, ev_aux = nullptr;
+  int tail_overlap = 1;
   char err[512];
   TcState tc;
 };
@@ -352,7 +355,7 @@ int mpg_create(const mpg_config* cfg, mpg_ctx** out) {
   }
   c->partial_stride = (maxP + 3) & ~size_t(3);
   ok = ok && alloc(&c->ckpt, (size_t)(cfg->max_horizon + 1) * cfg->max_rows * c->S)
-       && alloc(&c->partial, (size_t)c->sms * c->partial_stride) && alloc(&c->loss_partial, c->sms)
+       && alloc(&c->partial, (size_t)2 * c->sms * c->partial_stride) && alloc(&c->loss_partial, c->sms)
        && alloc(&c->stats_part, (size_t)MPG_MAX_LIST * 64 * 2);
   if (ok) ok = tc_init(c->tc, c->cfg, c->sms, c->ws_bytes);
   if (!ok) {
@@ -375,6 +378,15 @@ int mpg_create(const mpg_config* cfg, mpg_ctx** out) {
     mpg_destroy(c);
     return MPG_ERR_CUDA;
   }
+  if (cudaStreamCreateWithFlags(&c->aux, cudaStreamNonBlocking) != cudaSuccess
+      || cudaEventCreateWithFlags(&c->ev_wave, cudaEventDisableTiming) != cudaSuccess
+      || cudaEventCreateWithFlags(&c->ev_aux, cudaEventDisableTiming) != cudaSuccess) {
+    snprintf(g_create_err, 512, "side stream / event creation failed: %s", cudaGetErrorString(cudaGetLastError()));
+    mpg_destroy(c);
+    return MPG_ERR_CUDA;
+  }
+  const char* ov = getenv("MPG_TAIL_OVERLAP");
+  c->tail_overlap = !(ov && ov[0] == '0');
   *out = c;
   return MPG_OK;
 }
@@ -387,6 +399,9 @@ void mpg_destroy(mpg_ctx* c) {
   }
   cudaFree(c->ckpt); cudaFree(c->partial); cudaFree(c->loss_partial); cudaFree(c->stats_part);
   if (c->ev0) { cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); }
+  if (c->aux) { cudaStreamSynchronize(c->aux); cudaStreamDestroy(c->aux); }
+  if (c->ev_wave) cudaEventDestroy(c->ev_wave);
+  if (c->ev_aux) cudaEventDestroy(c->ev_aux);
   tc_destroy(c->tc);
   delete c;
 }
@@ -525,19 +540,51 @@ int mpg_policy_grad(mpg_ctx* ctx, const mpg_rollout_params* p, const float* obs,
     if (!tc_ensure_store(ctx->tc, need)) return fail(ctx, MPG_ERR_CUDA, "cudaMalloc of the dW operand store failed%s");
     ta.store = ctx->tc.store;
     ta.prof = ctx->prof;
-    CUDA_OK(ctx, cudaMemsetAsync(ctx->partial, 0, (size_t)ctx->sms * ctx->partial_stride * sizeof(float), st));
+    const size_t dw_smem = tc::DW_SMEM;
+    auto dw_args = [&](int tile0, int tiles, int part_row) {
+      tc::DwArgs da;
+      da.store = ctx->tc.store + (size_t)tile0 * ta.store_steps * tc::SLOT_BYTES;
+      da.nrecords = tiles * ta.store_steps; da.has_h2 = 1;
+      da.in_dim = a.pol.in_dim; da.out_dim = a.pol.out_dim; da.act_dim = ctx->cfg.act_dim;
+      da.partial = ctx->partial + (size_t)part_row * ctx->partial_stride; da.partial_stride = (long long)ctx->partial_stride;
+      return da;
+    };
+    // Wave-tail overlap: with ntiles = w * sms + tail the last wave leaves sms - tail SMs idle.  The full waves and
+    // the tail wave are two launches; the weight-gradient GEMMs of the full waves (HBM-bound) run on the side
+    // stream on exactly the SMs the tail wave does not use.  Partial rows [0, sms): full waves, [sms, 2 sms): tail.
+    const int tail = ntiles % ctx->sms, full = ntiles - tail;
+    const bool split = ctx->tail_overlap && ctx->aux && full > 0 && tail > 0 && ctx->sms - tail >= 16 && !ctx->prof;
+    CUDA_OK(ctx, cudaMemsetAsync(ctx->partial, 0, (size_t)(split ? 2 : 1) * ctx->sms * ctx->partial_stride * sizeof(float), st));
     if (ctx->timing) cudaEventRecord(ctx->ev0, st);
-    CUDA_OK(ctx, tc_launch_rollout<true>(ctx->cfg.env, ta, grid, st));
-    if (ctx->timing) { cudaEventRecord(ctx->ev1, st); ctx->timed = 1; }
-    tc::DwArgs da;
-    da.store = ctx->tc.store; da.nrecords = ntiles * ta.store_steps; da.has_h2 = 1;
-    da.in_dim = a.pol.in_dim; da.out_dim = a.pol.out_dim; da.act_dim = ctx->cfg.act_dim;
-    da.partial = ctx->partial; da.partial_stride = (long long)ctx->partial_stride;
-    int dgrid = 2 * da.nrecords < ctx->sms ? 2 * da.nrecords : (ctx->sms & ~1);
-    tc::tc_dw_kernel<<<dgrid, 192, 2 * tc::DW_STAGE + 128 + 1024, st>>>(da);
-    reduce_partials_kernel<<<(L.total + 255) / 256, 256, 0, st>>>(ctx->partial, ctx->partial_stride, ctx->sms, L.total,
-                                                                  grad_out, nullptr, nullptr);
-    ctx->launches += 3;
+    if (!split) {
+      CUDA_OK(ctx, tc_launch_rollout<true>(ctx->cfg.env, ta, grid, st));
+      if (ctx->timing) { cudaEventRecord(ctx->ev1, st); ctx->timed = 1; }
+      tc::DwArgs da = dw_args(0, ntiles, 0);
+      int dgrid = 2 * da.nrecords < ctx->sms ? 2 * da.nrecords : (ctx->sms & ~1);
+      tc::tc_dw_kernel<<<dgrid, 192, dw_smem, st>>>(da);
+      reduce_partials_kernel<<<(L.total + 255) / 256, 256, 0, st>>>(ctx->partial, ctx->partial_stride, ctx->sms, L.total,
+                                                                    grad_out, nullptr, nullptr);
+      ctx->launches += 3;
+    } else {
+      ta.tile0 = 0; ta.tile1 = full;
+      CUDA_OK(ctx, tc_launch_rollout<true>(ctx->cfg.env, ta, ctx->sms, st));
+      CUDA_OK(ctx, cudaEventRecord(ctx->ev_wave, st));
+      tc::TcArgs tb = ta;
+      tb.tile0 = full; tb.tile1 = ntiles;
+      tb.r.partial = ctx->partial + (size_t)ctx->sms * ctx->partial_stride;
+      CUDA_OK(ctx, tc_launch_rollout<true>(ctx->cfg.env, tb, tail, st));
+      if (ctx->timing) { cudaEventRecord(ctx->ev1, st); ctx->timed = 1; }
+      CUDA_OK(ctx, cudaStreamWaitEvent(ctx->aux, ctx->ev_wave, 0));
+      tc::tc_dw_kernel<<<(ctx->sms - tail) & ~1, 192, dw_smem, ctx->aux>>>(dw_args(0, full, 0));
+      CUDA_OK(ctx, cudaEventRecord(ctx->ev_aux, ctx->aux));
+      tc::DwArgs db = dw_args(full, tail, ctx->sms);
+      int dgrid = 2 * db.nrecords < ctx->sms ? 2 * db.nrecords : (ctx->sms & ~1);
+      tc::tc_dw_kernel<<<dgrid, 192, dw_smem, st>>>(db);
+      CUDA_OK(ctx, cudaStreamWaitEvent(st, ctx->ev_aux, 0));
+      reduce_partials_kernel<<<(L.total + 255) / 256, 256, 0, st>>>(ctx->partial, ctx->partial_stride, 2 * ctx->sms, L.total,
+                                                                    grad_out, nullptr, nullptr);
+      ctx->launches += 5;
+    }
     CUDA_OK(ctx, cudaGetLastError());
     return MPG_OK;
   }
@@ -648,7 +695,7 @@ int mpg_q_grad(mpg_ctx* ctx, int net, int rows, int64_t global_rows, const float
     da.in_dim = qin; da.out_dim = 1; da.act_dim = 1;
     da.partial = ctx->partial; da.partial_stride = (long long)ctx->partial_stride;
     const int dgrid = 2 * da.nrecords < ctx->sms ? 2 * da.nrecords : (ctx->sms & ~1);
-    tc::tc_dw_kernel<<<dgrid, 192, 2 * tc::DW_STAGE + 128 + 1024, st>>>(da);
+    tc::tc_dw_kernel<<<dgrid, 192, tc::DW_SMEM, st>>>(da);
     const GradLayout L(qin, 1);
     reduce_partials_kernel<<<(L.total + 255) / 256, 256, 0, st>>>(ctx->partial, ctx->partial_stride, ctx->sms, L.total,
                                                                   grad_out, nullptr, nullptr);

@@ -43,6 +43,7 @@ struct TcArgs {
   float* act_ckpt;          // [n_list][M*rows][A] actions at the list steps (for the Q input gradient)
   uint8_t* store;           // dW operand store: [tile][step][SLOT_BYTES]
   int store_steps;          // steps recorded per tile: horizon+1 (full BPTT) or 1 (first action only)
+  int tile0, tile1;         // tile range of this launch (tile1 == 0: all tiles); CTA c owns tile0 + c, tile0 + c + grid, ...
   int q_regress;            // 1: Q regression gradient (q_forward_and_backward): horizon 0, given actions,
                             //    upstream (Q - target) / B_global, dW operands of the Q net recorded, no policy part
   const float* q_target;    // (rows) regression targets
@@ -229,7 +230,8 @@ __device__ __forceinline__ void run_rollout(const TcArgs& A, uint8_t* smem, Bars
       A.prof[(ROLE == ROLE_MMA ? 32 : 0) + id] = clock64();
   };
 
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+  const int tile_end = A.tile1 > 0 && A.tile1 < ntiles ? A.tile1 : ntiles;
+  for (int tile = A.tile0 + blockIdx.x; tile < tile_end; tile += gridDim.x) {
     const int grow = tile * ACT_ROWS + row;
     const bool valid = rowthread && grow < MB;
     const int m_idx = valid ? grow / a.rows : 0, i_idx = valid ? grow % a.rows : 0;
@@ -388,7 +390,7 @@ __device__ __forceinline__ void run_rollout(const TcArgs& A, uint8_t* smem, Bars
         for (int i = 0; i < t; ++i) gp *= a.gamma;
         const bool want_dw = a.full_bptt || t == 0;
         const bool rec = store_dw && want_dw;
-        prof_t = (tile == (int)blockIdx.x && t == a.horizon - 1) ? t : -1;
+        prof_t = (tile == A.tile0 + (int)blockIdx.x && t == a.horizon - 1) ? t : -1;
         stamp(0);
         uint8_t* slot = rec ? A.store + ((size_t)tile * A.store_steps + (a.full_bptt ? t : 0)) * SLOT_BYTES : nullptr;
         float g_a[NA], g_s[S], act[NA], zpre[NA];
@@ -601,19 +603,36 @@ struct DwArgs {
   long long partial_stride;
 };
 
-constexpr int DW_ROWS = 32;                                     // rows (K) per stage
-constexpr int DW_OFF_H1 = 0, DW_OFF_D2 = 16384, DW_OFF_D1 = 49152, DW_OFF_H2 = 65536, DW_OFF_P = 81920, DW_OFF_D3 = 83968;
-constexpr int DW_STAGE = 86016;                                 // bytes per stage (84 KB)
+#ifndef MPG_DW_ROWS
+#define MPG_DW_ROWS 32
+#endif
+#ifndef MPG_DW_NSTAGE
+#define MPG_DW_NSTAGE 2
+#endif
+constexpr int DW_ROWS = MPG_DW_ROWS;                            // rows (K) per stage (multiple of the UMMA k-step)
+constexpr int DW_NSTAGE = MPG_DW_NSTAGE;                                    // ring depth: bytes in flight per SM set the HBM rate
+constexpr int DW_BLK = DW_ROWS * 128;                           // one 64-feature block of one stage
+constexpr int DW_R16 = DW_ROWS * 32;                            // one [rows x 16] bf16 image of one stage
+constexpr int DW_OFF_H1 = 0, DW_OFF_D2 = 4 * DW_BLK, DW_OFF_D1 = 12 * DW_BLK, DW_OFF_H2 = 16 * DW_BLK,
+              DW_OFF_P = 20 * DW_BLK, DW_OFF_D3 = DW_OFF_P + 2 * DW_R16;
+constexpr int DW_STAGE = DW_OFF_D3 + 2 * DW_R16;                // bytes per stage (42 KB)
+constexpr int DW_SMEM = DW_NSTAGE * DW_STAGE + 256 + 1024;      // dynamic shared memory of tc_dw_kernel
 constexpr int DW_TM_D2 = 0, DW_TM_DB2 = 256, DW_TM_D1 = 272, DW_TM_D3 = 288;
+static_assert(DW_STAGE % 1024 == 0 && DW_ROWS % 16 == 0, "stages hold whole SW128 atoms and UMMA k-steps");
+
+struct DwBars {
+  uint64_t full[DW_NSTAGE], empty[DW_NSTAGE], d_full;
+  uint32_t tmem_base;
+};
 
 __global__ void __launch_bounds__(192, 1) tc_dw_kernel(const __grid_constant__ DwArgs A) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* stage_buf = smem;                                    // 2 x DW_STAGE
-  Bars* b = reinterpret_cast<Bars*>(smem + 2 * DW_STAGE);
+  uint8_t* stage_buf = smem;                                    // DW_NSTAGE x DW_STAGE
+  DwBars* b = reinterpret_cast<DwBars*>(smem + DW_NSTAGE * DW_STAGE);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    for (int i = 0; i < NSLOT; ++i) { mbar_init(&b->full[i], 1); mbar_init(&b->empty[i], 1); }
+    for (int i = 0; i < DW_NSTAGE; ++i) { mbar_init(&b->full[i], 1); mbar_init(&b->empty[i], 1); }
     mbar_init(&b->d_full, 1);
     fence_barrier_init();
   }
@@ -627,30 +646,37 @@ __global__ void __launch_bounds__(192, 1) tc_dw_kernel(const __grid_constant__ D
   const int nstages = nmine * (ACT_ROWS / DW_ROWS);
 
   if (warp == 4) {
-    // ------------------------------- producer -------------------------------
-    if (lane == 0) {
-      uint32_t st = 0;
+    // ------------------------------- producer: 24 lanes issue the 24 bulk copies of a stage in parallel ----------
+    {
+      // lane -> (source offset inside the record, destination offset inside the stage, bytes); q-independent parts
+      const int sp = lane / 12, k = lane % 12;
+      size_t src = 0; uint32_t dsto = 0, bytes = DW_BLK, qstep = DW_BLK;
+      if (k < 6) {            // left operands h1 / delta1 / h2: the two 64-feature blocks of half mh
+        const int which = k >> 1, jb = k & 1;
+        const size_t slot_off = which == 0 ? SLOT_H1 : (which == 1 ? SLOT_D1 : SLOT_H2);
+        const uint32_t dst_off = which == 0 ? DW_OFF_H1 : (which == 1 ? DW_OFF_D1 : DW_OFF_H2);
+        src = slot_off + (size_t)sp * ACT_SPLIT + (size_t)(2 * mh + jb) * ACT_BLOCK;
+        dsto = dst_off + (sp * 2 + jb) * DW_BLK;
+      } else if (k < 10) {    // right operand delta2: all four blocks
+        const int jb = k - 6;
+        src = SLOT_D2 + (size_t)sp * ACT_SPLIT + (size_t)jb * ACT_BLOCK;
+        dsto = DW_OFF_D2 + (sp * 4 + jb) * DW_BLK;
+      } else {                // [p|1] and [delta3|0] images
+        src = (k == 10 ? SLOT_P : SLOT_D3) + (size_t)sp * 4096;
+        dsto = (k == 10 ? DW_OFF_P : DW_OFF_D3) + sp * DW_R16;
+        bytes = DW_R16; qstep = DW_R16;
+      }
+      uint32_t slot = 0, par = 0;
       for (int r = first; r < A.nrecords; r += stride) {
         const uint8_t* rec = A.store + (size_t)r * SLOT_BYTES;
-        for (int q = 0; q < ACT_ROWS / DW_ROWS; ++q, ++st) {
-          const uint32_t slot = st & 1, par = (st >> 1) & 1;
-          uint8_t* dst = stage_buf + slot * DW_STAGE;
-          mbar_wait(&b->empty[slot], par ^ 1);
-          mbar_expect_tx(&b->full[slot], DW_STAGE);
-          const size_t rowoff = (size_t)q * DW_ROWS * 128;       // 32 rows x 128 B inside a 64-feature block
-          for (int sp = 0; sp < 2; ++sp) {
-            for (int j = 0; j < 2; ++j) {   // left operands: the two 64-feature blocks of half mh
-              const size_t src = (size_t)sp * ACT_SPLIT + (size_t)(2 * mh + j) * ACT_BLOCK + rowoff;
-              bulk_g2s(dst + DW_OFF_H1 + (sp * 2 + j) * 4096, rec + SLOT_H1 + src, 4096, &b->full[slot]);
-              bulk_g2s(dst + DW_OFF_D1 + (sp * 2 + j) * 4096, rec + SLOT_D1 + src, 4096, &b->full[slot]);
-              bulk_g2s(dst + DW_OFF_H2 + (sp * 2 + j) * 4096, rec + SLOT_H2 + src, 4096, &b->full[slot]);
-            }
-            for (int j = 0; j < 4; ++j)     // right operand delta2: all four blocks
-              bulk_g2s(dst + DW_OFF_D2 + (sp * 4 + j) * 4096, rec + SLOT_D2 + (size_t)sp * ACT_SPLIT + (size_t)j * ACT_BLOCK + rowoff,
-                       4096, &b->full[slot]);
-            bulk_g2s(dst + DW_OFF_P + sp * 1024, rec + SLOT_P + (size_t)sp * 4096 + (size_t)q * 1024, 1024, &b->full[slot]);
-            bulk_g2s(dst + DW_OFF_D3 + sp * 1024, rec + SLOT_D3 + (size_t)sp * 4096 + (size_t)q * 1024, 1024, &b->full[slot]);
+        for (int q = 0; q < ACT_ROWS / DW_ROWS; ++q) {
+          if (lane == 0) {
+            mbar_wait(&b->empty[slot], par ^ 1);
+            mbar_expect_tx(&b->full[slot], DW_STAGE);
           }
+          __syncwarp();
+          if (lane < 24) bulk_g2s(stage_buf + slot * DW_STAGE + dsto, rec + src + (size_t)q * qstep, bytes, &b->full[slot]);
+          if (++slot == DW_NSTAGE) { slot = 0; par ^= 1; }
         }
       }
     }
@@ -659,25 +685,25 @@ __global__ void __launch_bounds__(192, 1) tc_dw_kernel(const __grid_constant__ D
     if (lane == 0) {
       constexpr uint32_t id256 = make_idesc(128, 256, 1, 1), id16 = make_idesc(128, 16, 1, 1);
       const uint32_t sbase = smem_u32(stage_buf);
+      uint32_t slot = 0, par = 0;
       for (int st = 0; st < nstages; ++st) {
-        const uint32_t slot = st & 1, par = (st >> 1) & 1;
         mbar_wait(&b->full[slot], par);
         tc_fence_after();
         const uint32_t base = sbase + slot * DW_STAGE;
 #pragma unroll
         for (int ks = 0; ks < DW_ROWS / 16; ++ks) {
           const uint32_t acc = (st | ks) ? 1u : 0u;
-          // left operands (MN-major SW128, M = 128 features = 2 blocks 4096 B apart, 8-row groups 1024 B apart)
-          auto L = [&](int off, int sp) { return make_desc(base + off + sp * 8192 + ks * 2048, 4096, 1024, LAYOUT_SW128); };
+          // left operands (MN-major SW128, M = 128 features = 2 blocks DW_BLK apart, 8-row groups 1024 B apart)
+          auto L = [&](int off, int sp) { return make_desc(base + off + sp * 2 * DW_BLK + ks * 2048, DW_BLK, 1024, LAYOUT_SW128); };
           // right operand delta2 (N = 256 = 4 blocks)
-          auto R2 = [&](int sp) { return make_desc(base + DW_OFF_D2 + sp * 16384 + ks * 2048, 4096, 1024, LAYOUT_SW128); };
+          auto R2 = [&](int sp) { return make_desc(base + DW_OFF_D2 + sp * 4 * DW_BLK + ks * 2048, DW_BLK, 1024, LAYOUT_SW128); };
           // right operands [p|1], [delta3|0] (MN-major INTERLEAVE, N = 16: halves 128 B apart (SBO), 8-row groups 256 B apart (LBO))
-          auto R16 = [&](int off, int sp) { return make_desc(base + off + sp * 1024 + ks * 512, 256, 128, LAYOUT_NONE); };
+          auto R16 = [&](int off, int sp) { return make_desc(base + off + sp * DW_R16 + ks * 512, 256, 128, LAYOUT_NONE); };
           umma_bf16(tmem + DW_TM_D2, L(DW_OFF_H1, 0), R2(0), id256, acc);
           umma_bf16(tmem + DW_TM_D2, L(DW_OFF_H1, 1), R2(0), id256, 1u);
           umma_bf16(tmem + DW_TM_D2, L(DW_OFF_H1, 0), R2(1), id256, 1u);
           // delta2 as LEFT operand for db2: its blocks 2mh, 2mh+1 inside the right-operand buffer
-          auto LD2 = [&](int sp) { return make_desc(base + DW_OFF_D2 + sp * 16384 + mh * 8192 + ks * 2048, 4096, 1024, LAYOUT_SW128); };
+          auto LD2 = [&](int sp) { return make_desc(base + DW_OFF_D2 + sp * 4 * DW_BLK + mh * 2 * DW_BLK + ks * 2048, DW_BLK, 1024, LAYOUT_SW128); };
           umma_bf16(tmem + DW_TM_DB2, LD2(0), R16(DW_OFF_P, 0), id16, acc);
           umma_bf16(tmem + DW_TM_DB2, LD2(1), R16(DW_OFF_P, 0), id16, 1u);
           umma_bf16(tmem + DW_TM_D1, L(DW_OFF_D1, 0), R16(DW_OFF_P, 0), id16, acc);
@@ -688,6 +714,7 @@ __global__ void __launch_bounds__(192, 1) tc_dw_kernel(const __grid_constant__ D
           umma_bf16(tmem + DW_TM_D3, L(DW_OFF_H2, 0), R16(DW_OFF_D3, 1), id16, 1u);
         }
         umma_commit(&b->empty[slot]);
+        if (++slot == DW_NSTAGE) { slot = 0; par ^= 1; }
       }
       umma_commit(&b->d_full);
     }

@@ -49,7 +49,7 @@ inline bool tc_init(TcState& t, const mpg_config& cfg, int /*sms*/, size_t& ws_b
        && tc_set_smem(tc::tc_rollout_kernel<MPG_ENV_INVERTED_DOUBLE_PENDULUM, true>, sm)
        && tc_set_smem(tc::tc_rollout_kernel<MPG_ENV_INVERTED_DOUBLE_PENDULUM, false>, sm)
        && tc_set_smem(tc::tc_rollout_kernel<MPG_ENV_PATH_TRACKING_REAL, false>, sm)
-       && tc_set_smem(tc::tc_dw_kernel, 2 * tc::DW_STAGE + 128 + 1024);
+       && tc_set_smem(tc::tc_dw_kernel, tc::DW_SMEM);
   t.ready = ok;
   return ok;
 }
