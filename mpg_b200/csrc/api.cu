@@ -544,8 +544,8 @@ int mpg_policy_grad(mpg_ctx* ctx, const mpg_rollout_params* p, const float* obs,
     auto dw_args = [&](int tile0, int tiles, int part_row) {
       tc::DwArgs da;
       da.store = ctx->tc.store + (size_t)tile0 * ta.store_steps * tc::SLOT_BYTES;
-      da.nrecords = tiles * ta.store_steps; da.has_h2 = 1;
-      da.in_dim = a.pol.in_dim; da.out_dim = a.pol.out_dim; da.act_dim = ctx->cfg.act_dim;
+      da.nrecords = tiles * ta.store_steps;
+      da.in_dim = a.pol.in_dim; da.out_dim = a.pol.out_dim;
       da.partial = ctx->partial + (size_t)part_row * ctx->partial_stride; da.partial_stride = (long long)ctx->partial_stride;
       return da;
     };
@@ -691,8 +691,8 @@ int mpg_q_grad(mpg_ctx* ctx, int net, int rows, int64_t global_rows, const float
     CUDA_OK(ctx, cudaMemsetAsync(ctx->partial, 0, (size_t)ctx->sms * ctx->partial_stride * sizeof(float), st));
     CUDA_OK(ctx, tc_launch_rollout<true>(c.env, ta, grid, st));
     tc::DwArgs da;
-    da.store = ctx->tc.store; da.nrecords = ntiles; da.has_h2 = 1;
-    da.in_dim = qin; da.out_dim = 1; da.act_dim = 1;
+    da.store = ctx->tc.store; da.nrecords = ntiles;
+    da.in_dim = qin; da.out_dim = 1;
     da.partial = ctx->partial; da.partial_stride = (long long)ctx->partial_stride;
     const int dgrid = 2 * da.nrecords < ctx->sms ? 2 * da.nrecords : (ctx->sms & ~1);
     tc::tc_dw_kernel<<<dgrid, 192, tc::DW_SMEM, st>>>(da);

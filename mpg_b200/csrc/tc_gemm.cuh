@@ -26,7 +26,10 @@ constexpr int STAGE_BYTES = 16384;            // ring slot: one split (hi or lo)
 constexpr int NSLOT = 4;                      // 3 loads in flight while one slot is consumed
 constexpr int BIG_IMAGE_BYTES = 16 * STAGE_BYTES;
 constexpr int TMEM_COLS = 512;
-constexpr int TM_Z1 = 0, TM_WORK = 256;       // TMEM column regions
+// TMEM column regions: two 64-column first-layer chunk buffers (z1 is streamed, never resident), the 256-column
+// working accumulator (z2 / g_h1), the 16-column input gradient, and the persistent weight-gradient accumulators
+// D1 = delta1^T [p|1] and D3 = h2^T [delta3|0] (two 128-feature halves x 16 columns each)
+constexpr int TM_Z1C = 0, TM_WORK = 128, TM_GP = 384, TM_D1 = 400, TM_D3 = 432;
 
 // shared memory map (bytes, 1024-aligned base)
 struct SmemMap {
@@ -36,7 +39,7 @@ struct SmemMap {
   static constexpr int MISC = PIMG + 8192;                    // fp32 scratch, see MiscF
   static constexpr int MISC_BYTES = 12288;
   static constexpr int BARS = MISC + MISC_BYTES;              // mbarriers + tmem pointer
-  static constexpr int TOTAL = BARS + 128;
+  static constexpr int TOTAL = BARS + 256;
 };
 
 struct Bars {
@@ -45,8 +48,12 @@ struct Bars {
   uint64_t a_full;       // [p|a|1] image written (first-layer GEMMs)
   uint64_t a_blk[4];     // 64-feature block kb of the activation image written (K-block pipelining)
   uint64_t d_full;
+  uint64_t z_full[2];    // first-layer chunk buffer j holds a fresh 64-column chunk (mma -> epilogue)
+  uint64_t z_empty[2];   // chunk buffer j has been read out (epilogue -> mma)
+  uint64_t acc_done;     // the D1 accumulation UMMAs have read the delta1 / [p|1] images
   uint32_t tmem_base;
 };
+static_assert(sizeof(Bars) <= 256, "BARS region too small");
 
 // per-role running counters (phase tracking)
 struct Sync {
@@ -54,6 +61,7 @@ struct Sync {
   uint32_t a_cnt = 0;    // a_full phases seen
   uint32_t g_cnt = 0;    // a_blk[] phases seen (GEMMs whose A operand is the activation image)
   uint32_t d_cnt = 0;    // d_full phases seen
+  uint32_t acc_cnt = 0;  // acc_done phases seen (epilogue side)
 };
 
 enum Role { ROLE_EPI = 0, ROLE_PRODUCER = 1, ROLE_MMA = 2 };
@@ -90,7 +98,10 @@ __device__ __forceinline__ void consume_pad(Bars* b, Sync& s) {
 // N = 256 UMMA reads both (half the instruction count and 25 % less shared-memory operand traffic than two
 // N = 128 UMMAs).  K-block kb is issued as soon as the epilogue has published that 64-feature block of the
 // activation image, so the UMMAs overlap the epilogue that produces A.
-__device__ __forceinline__ void mma_big(Bars* b, uint32_t act_addr, uint32_t ring_addr, Sync& s, uint32_t d_tmem) {
+struct NoHook { __device__ __forceinline__ void operator()() const {} };
+template <typename Hook = NoHook>
+__device__ __forceinline__ void mma_big(Bars* b, uint32_t act_addr, uint32_t ring_addr, Sync& s, uint32_t d_tmem,
+                                        Hook hook = Hook()) {
   constexpr uint32_t idesc = make_idesc(128, 256, 0, 0);
   for (int kb = 0; kb < 4; ++kb) {
     mbar_wait(&b->a_blk[kb], s.g_cnt & 1);
@@ -117,9 +128,53 @@ __device__ __forceinline__ void mma_big(Bars* b, uint32_t act_addr, uint32_t rin
       umma_commit(&b->empty[slot]);
       umma_commit(&b->empty[slot + 1]);
       s.stage += 2;
+      if (kb == 0 && sp == 0) hook();
     }
   }
   ++s.g_cnt;
+}
+// 64-column chunk c of the first-layer GEMM into chunk buffer c & 1.  Every streamed first-layer GEMM issues
+// exactly chunks 0..3, so buffer j is used twice per GEMM and the mbarrier parities depend on c only.
+__device__ __forceinline__ void mma_l1_chunk(Bars* b, uint32_t p_addr, uint32_t bbase, int c, uint32_t tm_z1c) {
+  constexpr uint32_t idesc = make_idesc(128, 64, 0, 0);
+  mbar_wait(&b->z_empty[c & 1], ((c >> 1) & 1) ^ 1);
+  tc_fence_after();
+  const uint64_t dah = make_desc(p_addr, 128, 256, LAYOUT_NONE), dal = make_desc(p_addr + 4096, 128, 256, LAYOUT_NONE);
+  const uint64_t dbh = make_desc(bbase + c * 2048, 128, 256, LAYOUT_NONE), dbl = make_desc(bbase + 8192 + c * 2048, 128, 256, LAYOUT_NONE);
+  const uint32_t d = tm_z1c + (c & 1) * 64;
+  umma_bf16(d, dah, dbh, idesc, 0u);
+  umma_bf16(d, dal, dbh, idesc, 1u);
+  umma_bf16(d, dah, dbl, idesc, 1u);
+  umma_commit(&b->z_full[c & 1]);
+}
+// epilogue side of the chunk stream
+__device__ __forceinline__ void epi_wait_chunk(Bars* b, int c) {
+  mbar_wait(&b->z_full[c & 1], (c >> 1) & 1);
+  tc_fence_after();
+}
+__device__ __forceinline__ void epi_release_chunk(Bars* b, int c) {
+  tc_fence_before();
+  mbar_arrive(&b->z_empty[c & 1]);
+}
+// Weight-gradient accumulation with the operands where they already are: D[half][128 features x 16] +=
+// IMG[:, half]^T . R16, IMG = activation image read MN-major (K = rows), R16 = [p|1] or [delta3|0] image read
+// MN-major.  48 UMMAs (2 halves x 8 row steps x 3 split products).
+__device__ __forceinline__ void mma_acc16(uint32_t act_addr, uint32_t r16_addr, uint32_t d_tmem, bool& started) {
+  constexpr uint32_t idesc = make_idesc(128, 16, 1, 1);
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+#pragma unroll
+    for (int ks = 0; ks < ACT_ROWS / 16; ++ks) {
+      const uint32_t a = act_addr + half * 2 * ACT_BLOCK + ks * 2048;
+      const uint64_t dah = make_desc(a, ACT_BLOCK, 1024, LAYOUT_SW128), dal = make_desc(a + ACT_SPLIT, ACT_BLOCK, 1024, LAYOUT_SW128);
+      const uint64_t dbh = make_desc(r16_addr + ks * 512, 256, 128, LAYOUT_NONE), dbl = make_desc(r16_addr + 4096 + ks * 512, 256, 128, LAYOUT_NONE);
+      const uint32_t d = d_tmem + half * 16;
+      umma_bf16(d, dah, dbh, idesc, (started || ks) ? 1u : 0u);
+      umma_bf16(d, dal, dbh, idesc, 1u);
+      umma_bf16(d, dah, dbl, idesc, 1u);
+    }
+  }
+  started = true;
 }
 // first-layer GEMM: D[128 x 256] = P[128 x 16] . W1aug^T ; P is the INTERLEAVE image in shared memory,
 // W1aug image streamed as ONE stage = [hi: 256 rows x 32 B][lo: 256 rows x 32 B] = 16 KB
@@ -206,6 +261,89 @@ __device__ __forceinline__ void gemm_issue(int kind, Bars* b, uint8_t* smem, Syn
     if (kind == 1) epi_publish_a(b);
   }
 }
+// Streamed first layer + layer 2 (or the Q net's): the first-layer result never sits in TMEM as a whole; its four
+// 64-column chunks go through two buffers, chunk c+2 is issued when the epilogue has read chunk c, and the K-blocks
+// of the big GEMM follow the h1 blocks the epilogue publishes.  Result: z2 in tm_work (d_full).
+template <int ROLE>
+__device__ __forceinline__ void fwd_pair_issue(Bars* b, uint8_t* smem, Sync& s, const uint8_t* l1_img, const uint8_t* big_img,
+                                               uint32_t tm_z1c, uint32_t tm_work) {
+  if (ROLE == ROLE_PRODUCER) {
+    produce(b, smem + SmemMap::RING, s, l1_img, 1, 16384);
+    produce_pad(b, s);
+    produce(b, smem + SmemMap::RING, s, big_img, 16, STAGE_BYTES);
+  } else if (ROLE == ROLE_MMA) {
+    const uint32_t base = smem_u32(smem), p_addr = base + SmemMap::PIMG, ring = base + SmemMap::RING;
+    mbar_wait(&b->a_full, s.a_cnt & 1);
+    ++s.a_cnt;
+    const uint32_t slot = s.stage & (NSLOT - 1), par = (s.stage / NSLOT) & 1;
+    mbar_wait(&b->full[slot], par);
+    tc_fence_after();
+    const uint32_t bbase = ring + slot * STAGE_BYTES;
+    mma_l1_chunk(b, p_addr, bbase, 0, tm_z1c);
+    mma_l1_chunk(b, p_addr, bbase, 1, tm_z1c);
+    mma_l1_chunk(b, p_addr, bbase, 2, tm_z1c);
+    ++s.stage;
+    consume_pad(b, s);
+    // the last chunk waits for the epilogue to finish chunk 1; the first UMMAs of the big GEMM keep the tensor
+    // pipe busy meanwhile.  The first-layer ring slot is released after its last reader.
+    mma_big(b, base + SmemMap::ACT, ring, s, tm_work, [&]() {
+      mma_l1_chunk(b, p_addr, bbase, 3, tm_z1c);
+      umma_commit(&b->empty[slot]);
+    });
+    mma_publish_d(b);
+  } else {
+    epi_publish_a(b);
+  }
+}
+// Tail of a backward step: the first-layer pre-activations are recomputed chunk by chunk for elu'(z1) (the [p|a|1]
+// image of this step is still in place), then the input-gradient GEMM (do_gp) follows the delta1 blocks, then the
+// delta1 / [p|1] images are contracted over the rows into the persistent D1 accumulator (do_d1).
+template <int ROLE>
+__device__ __forceinline__ void bwd_tail_issue(Bars* b, uint8_t* smem, Sync& s, const uint8_t* l1_img, const uint8_t* in_img,
+                                               bool do_gp, bool do_d1, bool& d1_started, uint32_t tm_z1c, uint32_t tm_gp,
+                                               uint32_t tm_d1) {
+  if (ROLE == ROLE_PRODUCER) {
+    produce(b, smem + SmemMap::RING, s, l1_img, 1, 16384);
+    produce_pad(b, s);
+    if (do_gp) { produce(b, smem + SmemMap::RING, s, in_img, 1, 16384); produce_pad(b, s); }
+  } else if (ROLE == ROLE_MMA) {
+    const uint32_t base = smem_u32(smem), p_addr = base + SmemMap::PIMG, ring = base + SmemMap::RING;
+    const uint32_t slot = s.stage & (NSLOT - 1), par = (s.stage / NSLOT) & 1;
+    mbar_wait(&b->full[slot], par);
+    tc_fence_after();
+    const uint32_t bbase = ring + slot * STAGE_BYTES;
+    for (int c = 0; c < 4; ++c) mma_l1_chunk(b, p_addr, bbase, c, tm_z1c);
+    umma_commit(&b->empty[slot]);
+    ++s.stage;
+    consume_pad(b, s);
+    if (do_gp) {
+      mma_in(b, base + SmemMap::ACT, ring, s, tm_gp);
+      mma_publish_d(b);
+    } else {
+      for (int kb = 0; kb < 4; ++kb) mbar_wait(&b->a_blk[kb], s.g_cnt & 1);
+      ++s.g_cnt;
+      tc_fence_after();
+    }
+    if (do_d1) {
+      mma_acc16(base + SmemMap::ACT, p_addr, tm_d1, d1_started);
+      umma_commit(&b->acc_done);
+    }
+  }
+}
+// D3 += h2^T [delta3|0]: the epilogue publishes (h2 image + delta3 image written), the UMMAs complete on d_full
+template <int ROLE>
+__device__ __forceinline__ void d3_issue(Bars* b, uint8_t* smem, Sync& s, uint32_t d3_off, bool& d3_started, uint32_t tm_d3) {
+  if (ROLE == ROLE_MMA) {
+    const uint32_t base = smem_u32(smem);
+    mbar_wait(&b->a_full, s.a_cnt & 1);
+    ++s.a_cnt;
+    tc_fence_after();
+    mma_acc16(base + SmemMap::ACT, base + d3_off, tm_d3, d3_started);
+    mma_publish_d(b);
+  } else if (ROLE == ROLE_EPI) {
+    epi_publish_a(b);
+  }
+}
 // compatibility wrapper: issue + wait, A image published as a whole (self test)
 template <int ROLE>
 __device__ __forceinline__ void gemm(int kind, Bars* b, uint8_t* smem, Sync& s, const uint8_t* gimg, uint32_t d_tmem) {
@@ -224,6 +362,8 @@ __device__ __forceinline__ Bars* cta_setup(uint8_t* smem) {
     mbar_init(&b->a_full, EPI_THREADS);
     for (int i = 0; i < 4; ++i) mbar_init(&b->a_blk[i], EPI_THREADS);
     mbar_init(&b->d_full, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&b->z_full[i], 1); mbar_init(&b->z_empty[i], EPI_THREADS); }
+    mbar_init(&b->acc_done, 1);
     fence_barrier_init();
   }
   if (warp == EPI_WARPS + 1) tmem_alloc(&b->tmem_base, TMEM_COLS);

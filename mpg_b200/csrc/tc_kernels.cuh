@@ -34,8 +34,10 @@ struct TcNet {
 };
 
 constexpr int BIAS_K = 15;                    // column of the [p|a|1] image that carries the constant 1
-constexpr size_t SLOT_H1 = 0, SLOT_H2 = 131072, SLOT_D1 = 262144, SLOT_D2 = 393216, SLOT_P = 524288, SLOT_D3 = 532480;
-constexpr size_t SLOT_BYTES = 540672;         // one (tile, step) record of the dW operand store
+// one (tile, step) record of the dW operand store: the h1 and delta2 images (dW2 = h1^T delta2) and the [p|1] image
+// (db2 = delta2^T 1).  dW1, db1 and dW3 are accumulated inside the rollout kernel (TM_D1 / TM_D3).
+constexpr size_t SLOT_H1 = 0, SLOT_D2 = 131072, SLOT_P = 262144;
+constexpr size_t SLOT_BYTES = 270336;
 
 struct TcArgs {
   RolloutArgs r;            // config, lists, pointers (r.pol / r.q unused here)
@@ -86,16 +88,18 @@ __device__ __forceinline__ void act_load8(const uint8_t* act_hi, const uint8_t* 
 // Block-ordered epilogues: every warp handles 16 columns of each 64-feature block kb, so that block kb of
 // the activation image is complete (and published to the MMA warp) after 1/4 of the epilogue.
 
-// z1 (TMEM, bias folded in) -> h1 image
-__device__ MPG_EPI_INLINE void epi_hidden1_blocks(Bars* b, uint32_t tm_lane, uint8_t* act, int row, int hc, uint8_t* gimg) {
+// z1 (streamed through the two TMEM chunk buffers, bias folded in) -> h1 image
+__device__ MPG_EPI_INLINE void epi_hidden1_blocks(Bars* b, uint32_t tm_zc_lane, uint8_t* act, int row, int hc) {
   for (int kb = 0; kb < 4; ++kb) {
     const int c0 = kb * 64 + hc * 16;
     float v[16];
-    tmem_ld16(tm_lane + c0, v);
+    epi_wait_chunk(b, kb);
+    tmem_ld16(tm_zc_lane + (kb & 1) * 64 + hc * 16, v);
+    epi_release_chunk(b, kb);
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = elu_fast(v[i]);
-    act_store8(act, act + ACT_SPLIT, row, c0 >> 3, v, gimg);
-    act_store8(act, act + ACT_SPLIT, row, (c0 >> 3) + 1, v + 8, gimg);
+    act_store8(act, act + ACT_SPLIT, row, c0 >> 3, v);
+    act_store8(act, act + ACT_SPLIT, row, (c0 >> 3) + 1, v + 8);
     epi_block_done(b, kb);
   }
 }
@@ -116,7 +120,7 @@ __device__ MPG_EPI_INLINE void epi_hidden2(uint32_t tm_lane, const float* b2, co
 }
 // same, and keep h2 as an image (backward pass: delta2 and the dW3 operand are derived from it)
 __device__ MPG_EPI_INLINE void epi_hidden2_img(uint32_t tm_lane, const float* b2, const float* W3, uint8_t* act, int row,
-                                               int hc, float& p0, float& p1, uint8_t* gimg) {
+                                               int hc, float& p0, float& p1) {
   p0 = 0.f; p1 = 0.f;
   for (int kb = 0; kb < 4; ++kb) {
     const int c0 = kb * 64 + hc * 16;
@@ -129,13 +133,12 @@ __device__ MPG_EPI_INLINE void epi_hidden2_img(uint32_t tm_lane, const float* b2
       p0 = fmaf(v[i], w.x, p0);
       p1 = fmaf(v[i], w.y, p1);
     }
-    act_store8(act, act + ACT_SPLIT, row, c0 >> 3, v, gimg);
-    act_store8(act, act + ACT_SPLIT, row, (c0 >> 3) + 1, v + 8, gimg);
+    act_store8(act, act + ACT_SPLIT, row, c0 >> 3, v);
+    act_store8(act, act + ACT_SPLIT, row, (c0 >> 3) + 1, v + 8);
   }
 }
 // delta2 = (delta3 W3^T) * elu'(h2), h2 read back from its image and overwritten in place by delta2
-__device__ MPG_EPI_INLINE void epi_delta2_blocks(Bars* b, const float* W3, float d30, float d31, uint8_t* act, int row, int hc,
-                                                 uint8_t* gimg) {
+__device__ MPG_EPI_INLINE void epi_delta2_blocks(Bars* b, const float* W3, float d30, float d31, uint8_t* act, int row, int hc) {
   for (int kb = 0; kb < 4; ++kb) {
     const int c0 = kb * 64 + hc * 16;
     float v[16];
@@ -147,24 +150,26 @@ __device__ MPG_EPI_INLINE void epi_delta2_blocks(Bars* b, const float* W3, float
       const float g = fmaf(d30, w.x, d31 * w.y);
       v[i] = g * (v[i] > 0.f ? 1.f : v[i] + 1.f);     // elu'(z) expressed through the output h2
     }
-    act_store8(act, act + ACT_SPLIT, row, c0 >> 3, v, gimg);
-    act_store8(act, act + ACT_SPLIT, row, (c0 >> 3) + 1, v + 8, gimg);
+    act_store8(act, act + ACT_SPLIT, row, c0 >> 3, v);
+    act_store8(act, act + ACT_SPLIT, row, (c0 >> 3) + 1, v + 8);
     epi_block_done(b, kb);
   }
 }
-// delta1 = g_h1 (TMEM work) * elu'(z1) (TMEM z1) -> delta1 image
-__device__ MPG_EPI_INLINE void epi_delta1_blocks(Bars* b, bool publish, uint32_t tm_work, uint32_t tm_z1, uint8_t* act,
-                                                 int row, int hc, uint8_t* gimg) {
+// delta1 = g_h1 (TMEM work) * elu'(z1) (recomputed, streamed through the chunk buffers) -> delta1 image
+__device__ MPG_EPI_INLINE void epi_delta1_blocks(Bars* b, uint32_t tm_work_lane, uint32_t tm_zc_lane, uint8_t* act, int row,
+                                                 int hc) {
   for (int kb = 0; kb < 4; ++kb) {
     const int c0 = kb * 64 + hc * 16;
     float g[16], z[16];
-    tmem_ld16(tm_work + c0, g);
-    tmem_ld16(tm_z1 + c0, z);
+    tmem_ld16(tm_work_lane + c0, g);
+    epi_wait_chunk(b, kb);
+    tmem_ld16(tm_zc_lane + (kb & 1) * 64 + hc * 16, z);
+    epi_release_chunk(b, kb);
 #pragma unroll
     for (int i = 0; i < 16; ++i) g[i] *= (z[i] > 0.f ? 1.f : exp_fast(z[i]));
-    act_store8(act, act + ACT_SPLIT, row, c0 >> 3, g, gimg);
-    act_store8(act, act + ACT_SPLIT, row, (c0 >> 3) + 1, g + 8, gimg);
-    if (publish) epi_block_done(b, kb);
+    act_store8(act, act + ACT_SPLIT, row, c0 >> 3, g);
+    act_store8(act, act + ACT_SPLIT, row, (c0 >> 3) + 1, g + 8);
+    epi_block_done(b, kb);
   }
 }
 // [x0..x15] -> INTERLEAVE image row (hi | lo 4 KB apart)
@@ -218,11 +223,21 @@ __device__ __forceinline__ void run_rollout(const TcArgs& A, uint8_t* smem, Bars
   uint8_t* p_img = smem + SmemMap::PIMG;
   uint8_t* d3_img = smem + SM_D3IMG;
   const uint32_t tmem = b->tmem_base;
-  const uint32_t tm_z1 = tmem + TM_Z1, tm_work = tmem + TM_WORK;
+  const uint32_t tm_z1c = tmem + TM_Z1C, tm_work = tmem + TM_WORK, tm_gp = tmem + TM_GP, tm_d1 = tmem + TM_D1, tm_d3 = tmem + TM_D3;
   const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
   const float cscale = -1.f / ((float)a.M * (float)a.global_rows);
   const bool store_dw = BWD && A.store != nullptr;
   Sync sy;
+  bool d1_started = false, d3_started = false;   // mma role: the persistent accumulators hold a value
+  bool d1_pending = false, any_dw = false;       // epilogue role: D1 UMMAs in flight / accumulators were used
+  // the D1 UMMAs of the previous step read the delta1 and [p|1] images: wait before either is rewritten
+  auto acc_wait = [&]() {
+    if (ROLE == ROLE_EPI && d1_pending) {
+      mbar_wait(&b->acc_done, sy.acc_cnt & 1);
+      ++sy.acc_cnt;
+      d1_pending = false;
+    }
+  };
   float db3acc[2] = {0.f, 0.f};
   int prof_t = -1;   // step being traced
   auto stamp = [&](int id) {
@@ -263,15 +278,11 @@ __device__ __forceinline__ void run_rollout(const TcArgs& A, uint8_t* smem, Bars
     // The layer-2 UMMAs are issued K-block by K-block while the epilogue is still producing h1.
     auto policy_forward = [&](float* zpre, bool bwd_pass, bool rec_, uint8_t* slot) {
       if (ROLE == ROLE_MMA && bwd_pass) stamp(0);
-      gemm_issue<ROLE>(1, b, smem, sy, A.pol.l1, tm_z1);
-      if (ROLE == ROLE_MMA && bwd_pass) stamp(1);
-      gemm_issue<ROLE>(0, b, smem, sy, A.pol.big_fwd, tm_work);
+      fwd_pair_issue<ROLE>(b, smem, sy, A.pol.l1, A.pol.big_fwd, tm_z1c, tm_work);
       if (ROLE == ROLE_MMA && bwd_pass) stamp(2);
       if (ROLE == ROLE_EPI) {
-        epi_wait_d(b, sy);                                   // z1
         if (bwd_pass) stamp(2);
-        if (rec_) store_wait(elected);                       // previous step's delta1 image has been read out
-        epi_hidden1_blocks(b, tm_z1 + lane_off, act_img, row, hc, nullptr);
+        epi_hidden1_blocks(b, tm_z1c + lane_off, act_img, row, hc);   // follows the z1 chunk stream
         if (bwd_pass) stamp(3);
         if (rec_) store_image(elected, slot + SLOT_H1, act_img, 2 * ACT_SPLIT);
         epi_wait_d(b, sy);                                   // z2 (all layer-2 UMMAs done: h1 image free)
@@ -279,8 +290,7 @@ __device__ __forceinline__ void run_rollout(const TcArgs& A, uint8_t* smem, Bars
         float p0, p1;
         if (bwd_pass) {
           if (rec_) store_wait(elected);                     // h1 image has been read out
-          epi_hidden2_img(tm_work + lane_off, mf->b2p, mf->W3p, act_img, row, hc, p0, p1, nullptr);
-          if (rec_) store_image(elected, slot + SLOT_H2, act_img, 2 * ACT_SPLIT);
+          epi_hidden2_img(tm_work + lane_off, mf->b2p, mf->W3p, act_img, row, hc, p0, p1);
         } else {
           epi_hidden2(tm_work + lane_off, mf->b2p, mf->W3p, hc, p0, p1);
         }
@@ -299,18 +309,15 @@ __device__ __forceinline__ void run_rollout(const TcArgs& A, uint8_t* smem, Bars
     // Q forward on the current [p|a|1] image: returns Q for the row thread
     auto q_forward = [&](bool with_img, uint8_t* qslot) -> float {
       float qv = 0.f;
-      gemm_issue<ROLE>(1, b, smem, sy, A.q.l1, tm_z1);
-      gemm_issue<ROLE>(0, b, smem, sy, A.q.big_fwd, tm_work);
+      fwd_pair_issue<ROLE>(b, smem, sy, A.q.l1, A.q.big_fwd, tm_z1c, tm_work);
       if (ROLE == ROLE_EPI) {
-        epi_wait_d(b, sy);
-        epi_hidden1_blocks(b, tm_z1 + lane_off, act_img, row, hc, nullptr);
+        epi_hidden1_blocks(b, tm_z1c + lane_off, act_img, row, hc);
         if (qslot) store_image(elected, qslot + SLOT_H1, act_img, 2 * ACT_SPLIT);
         epi_wait_d(b, sy);
         float p0, p1;
         if (with_img) {
           if (qslot) store_wait(elected);
-          epi_hidden2_img(tm_work + lane_off, mf->b2q, mf->W3q, act_img, row, hc, p0, p1, nullptr);
-          if (qslot) store_image(elected, qslot + SLOT_H2, act_img, 2 * ACT_SPLIT);
+          epi_hidden2_img(tm_work + lane_off, mf->b2q, mf->W3q, act_img, row, hc, p0, p1);
         } else {
           epi_hidden2(tm_work + lane_off, mf->b2q, mf->W3q, hc, p0, p1);
         }
@@ -323,6 +330,7 @@ __device__ __forceinline__ void run_rollout(const TcArgs& A, uint8_t* smem, Bars
     };
 
     // =========================================== forward ===========================================
+    acc_wait();   // previous tile's last D1 UMMAs still read the [p|1] image
     for (int t = 0; t <= a.horizon; ++t) {
       float act[NA];
 #pragma unroll
@@ -411,54 +419,57 @@ __device__ __forceinline__ void run_rollout(const TcArgs& A, uint8_t* smem, Bars
         }
         int kidx = -1;
         for (int k = 0; k < a.n_list; ++k) if (a.list[k] == t) kidx = k;
+        acc_wait();
+        if (want_dw) any_dw = true;
         // ---- Q input gradient at the list steps: upstream c w_k gamma^t on Q1(p_t, a_t) ----
         if (kidx >= 0 && a.has_q && (a.list_w[kidx] != 0.f || A.q_regress)) {
-          uint8_t* qslot = (A.q_regress && store_dw) ? A.store + (size_t)tile * SLOT_BYTES : nullptr;
-          if (ROLE == ROLE_EPI && store_dw) store_wait(elected);   // the previous step's delta1 store still reads ACT
+          const bool reg = A.q_regress != 0;      // regression: weight gradients of the Q net, no input gradient
+          uint8_t* qslot = (reg && store_dw) ? A.store + (size_t)tile * SLOT_BYTES : nullptr;
           if (rowthread) {
             float ak[NA];
 #pragma unroll
             for (int j = 0; j < NA; ++j) ak[j] = valid ? A.act_ckpt[((size_t)kidx * MB + grow) * NA + j] : 0.f;
             write_pimg(s, ak, qslot ? qslot + SLOT_P : nullptr);
           }
-          const float qv = q_forward(true, qslot);         // z1q in tm_z1, h2q image in ACT
-          if (ROLE == ROLE_EPI) {
-            if (rowthread) {
-              // upstream on Q: policy loss c w_k gamma^t, or the regression residual (Q - target) / B_global
-              const float up = !valid ? 0.f : (A.q_regress ? (qv - A.q_target[i_idx]) * A.q_inv_rows : cscale * a.list_w[kidx] * gp);
-              mf->d3s[row] = up;
-              if (A.q_regress) {
-                float x[16];
+          const float qv = q_forward(true, qslot);         // h2q image in ACT
+          if (ROLE == ROLE_EPI && rowthread) {
+            // upstream on Q: policy loss c w_k gamma^t, or the regression residual (Q - target) / B_global
+            const float up = !valid ? 0.f : (reg ? (qv - A.q_target[i_idx]) * A.q_inv_rows : cscale * a.list_w[kidx] * gp);
+            mf->d3s[row] = up;
+            if (reg) {
+              float x[16];
 #pragma unroll
-                for (int i = 0; i < 16; ++i) x[i] = 0.f;
-                x[0] = up;
-                if (qslot) write_row16(nullptr, row, x, qslot + SLOT_D3);
-                float s0 = up;
+              for (int i = 0; i < 16; ++i) x[i] = 0.f;
+              x[0] = up;
+              write_row16(d3_img, row, x);
+              float s0 = up;
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) s0 += __shfl_xor_sync(0xffffffffu, s0, o);
-                if (lane == 0) mf->wsum[warp * 2] = s0;
-              }
+              for (int o = 16; o > 0; o >>= 1) s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+              if (lane == 0) mf->wsum[warp * 2] = s0;
             }
-            if (qslot) store_wait(elected);                // h2q image read out before delta2 overwrites it (has epi_bar)
-            else epi_bar();
-            if (A.q_regress && tid == 0) db3acc[0] += (mf->wsum[0] + mf->wsum[2]) + (mf->wsum[4] + mf->wsum[6]);
+          }
+          if (reg) d3_issue<ROLE>(b, smem, sy, SM_D3IMG, d3_started, tm_d3);   // dW3q += h2q^T delta3
+          if (ROLE == ROLE_EPI) {
+            if (reg) epi_wait_d(b, sy);                    // h2q image read by the D3 UMMAs before delta2 overwrites it
+            epi_bar();
+            if (reg && tid == 0) db3acc[0] += (mf->wsum[0] + mf->wsum[2]) + (mf->wsum[4] + mf->wsum[6]);
           }
           gemm_issue<ROLE>(0, b, smem, sy, A.q.big_dx, tm_work);  // g_h1q, K-blocks issued as delta2 blocks appear
           if (ROLE == ROLE_EPI) {
-            epi_delta2_blocks(b, mf->W3q, mf->d3s[row], 0.f, act_img, row, hc, nullptr);
+            epi_delta2_blocks(b, mf->W3q, mf->d3s[row], 0.f, act_img, row, hc);
             if (qslot) store_image(elected, qslot + SLOT_D2, act_img, 2 * ACT_SPLIT);
             epi_wait_d(b, sy);
           }
-          if (!A.q_regress) gemm_issue<ROLE>(2, b, smem, sy, A.q.in, tm_z1);   // g_in -> 16 columns of the z1 region
+          bwd_tail_issue<ROLE>(b, smem, sy, A.q.l1, A.q.in, !reg, reg, d1_started, tm_z1c, tm_gp, tm_d1);
           if (ROLE == ROLE_EPI) {
-            if (qslot) store_wait(elected);
-            epi_delta1_blocks(b, !A.q_regress, tm_work + lane_off, tm_z1 + lane_off, act_img, row, hc, nullptr);
-            if (qslot) store_image(elected, qslot + SLOT_D1, act_img, 2 * ACT_SPLIT);
-            if (!A.q_regress) epi_wait_d(b, sy);
+            if (qslot) store_wait(elected);                // delta2 image read out before it is overwritten
+            epi_delta1_blocks(b, tm_work + lane_off, tm_z1c + lane_off, act_img, row, hc);
+            if (!reg) epi_wait_d(b, sy);
+            else d1_pending = true;
           }
-          if (rowthread && !A.q_regress) {
+          if (rowthread && !reg) {
             float gin[16];
-            tmem_ld16(tm_z1 + lane_off, gin);
+            tmem_ld16(tm_gp + lane_off, gin);
             if (valid) {
               float go[MPG_MAX_OBS];
               for (int i = 0; i < a.obs_dim; ++i) go[i] = gin[i] * a.obs_scale[i];
@@ -482,29 +493,30 @@ __device__ __forceinline__ void run_rollout(const TcArgs& A, uint8_t* smem, Bars
           }
         }
         // ---- delta3, its image, db3 ----
-        if (ROLE == ROLE_EPI) {
+        if (ROLE == ROLE_EPI && rowthread) {
           float d3[2] = {0.f, 0.f};
-          if (rowthread) {
 #pragma unroll
-            for (int j = 0; j < NA; ++j) {
-              d3[j] = valid ? g_a[j] * head_grad(zpre[j], a.policy_out_tanh, a.action_range) : 0.f;
-              mf->d3s[j * ACT_ROWS + row] = d3[j];
-            }
-            if (NA == 1) mf->d3s[ACT_ROWS + row] = 0.f;
-            if (want_dw) {
-              float x[16];
-#pragma unroll
-              for (int i = 0; i < 16; ++i) x[i] = 0.f;
-              x[0] = d3[0]; x[1] = d3[1];
-              if (rec) write_row16(nullptr, row, x, slot + SLOT_D3);
-              float s0 = d3[0], s1 = d3[1];
-#pragma unroll
-              for (int o = 16; o > 0; o >>= 1) { s0 += __shfl_xor_sync(0xffffffffu, s0, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o); }
-              if (lane == 0) { mf->wsum[warp * 2] = s0; mf->wsum[warp * 2 + 1] = s1; }
-            }
+          for (int j = 0; j < NA; ++j) {
+            d3[j] = valid ? g_a[j] * head_grad(zpre[j], a.policy_out_tanh, a.action_range) : 0.f;
+            mf->d3s[j * ACT_ROWS + row] = d3[j];
           }
-          if (rec) store_wait(elected);                     // h2 image read out before delta2 overwrites it (has epi_bar)
-          else epi_bar();
+          if (NA == 1) mf->d3s[ACT_ROWS + row] = 0.f;
+          if (want_dw) {
+            float x[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) x[i] = 0.f;
+            x[0] = d3[0]; x[1] = d3[1];
+            write_row16(d3_img, row, x);
+            float s0 = d3[0], s1 = d3[1];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) { s0 += __shfl_xor_sync(0xffffffffu, s0, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o); }
+            if (lane == 0) { mf->wsum[warp * 2] = s0; mf->wsum[warp * 2 + 1] = s1; }
+          }
+        }
+        if (want_dw) d3_issue<ROLE>(b, smem, sy, SM_D3IMG, d3_started, tm_d3);   // dW3 += h2^T delta3
+        if (ROLE == ROLE_EPI) {
+          if (want_dw) epi_wait_d(b, sy);                   // h2 image read by the D3 UMMAs before delta2 overwrites it
+          epi_bar();
           if (tid == 0 && want_dw) {
             db3acc[0] += (mf->wsum[0] + mf->wsum[2]) + (mf->wsum[4] + mf->wsum[6]);
             db3acc[1] += (mf->wsum[1] + mf->wsum[3]) + (mf->wsum[5] + mf->wsum[7]);
@@ -516,24 +528,25 @@ __device__ __forceinline__ void run_rollout(const TcArgs& A, uint8_t* smem, Bars
         if (ROLE == ROLE_MMA) stamp(4);
         if (ROLE == ROLE_EPI) {
           stamp(6);
-          epi_delta2_blocks(b, mf->W3p, mf->d3s[row], mf->d3s[ACT_ROWS + row], act_img, row, hc, nullptr);
+          epi_delta2_blocks(b, mf->W3p, mf->d3s[row], mf->d3s[ACT_ROWS + row], act_img, row, hc);
           stamp(7);
           if (rec) store_image(elected, slot + SLOT_D2, act_img, 2 * ACT_SPLIT);
           epi_wait_d(b, sy);                                       // g_h1 complete, delta2 image consumed
           stamp(8);
         }
-        if (t > 0) gemm_issue<ROLE>(2, b, smem, sy, A.pol.in, tm_z1);   // g_p
+        // z1 recompute stream, g_p following the delta1 blocks, D1 += delta1^T [p|1]
+        bwd_tail_issue<ROLE>(b, smem, sy, A.pol.l1, A.pol.in, t > 0, want_dw, d1_started, tm_z1c, tm_gp, tm_d1);
         if (ROLE == ROLE_EPI) {
           if (rec) store_wait(elected);                            // delta2 image read out before it is overwritten
-          epi_delta1_blocks(b, t > 0, tm_work + lane_off, tm_z1 + lane_off, act_img, row, hc, nullptr);
+          epi_delta1_blocks(b, tm_work + lane_off, tm_z1c + lane_off, act_img, row, hc);
           stamp(9);
-          if (rec) store_image(elected, slot + SLOT_D1, act_img, 2 * ACT_SPLIT);
           if (t > 0) epi_wait_d(b, sy);
+          if (want_dw) d1_pending = true;
           stamp(10);
         }
         if (t > 0 && rowthread) {
           float gin[16];
-          tmem_ld16(tm_z1 + lane_off, gin);
+          tmem_ld16(tm_gp + lane_off, gin);
           if (valid) {
 #pragma unroll
             for (int j = 0; j < S; ++j) { lam[j] = g_s[j]; snext[j] = s[j]; }
@@ -546,14 +559,32 @@ __device__ __forceinline__ void run_rollout(const TcArgs& A, uint8_t* smem, Bars
       }
     }
   }
+  acc_wait();
   if (ROLE == ROLE_EPI) {
     tc_fence_before();
     if (elected) bulk_wait_all();
-    if (BWD && tid == 0) {
+    if (BWD) {
       const GradLayout L(A.pol.in_dim, A.pol.out_dim);
       float* partial = a.partial + (size_t)blockIdx.x * a.partial_stride;
-      partial[L.ob3 + 0] = db3acc[0];
-      if (NA > 1) partial[L.ob3 + 1] = db3acc[1];
+      if (tid == 0) {
+        partial[L.ob3 + 0] = db3acc[0];
+        if (NA > 1) partial[L.ob3 + 1] = db3acc[1];
+      }
+      if (any_dw && hc == 0) {
+        // D1 / D3: TMEM lane = feature inside the 128-feature half, columns = input index (BIAS_K: bias) / action
+        tc_fence_after();
+        const int ncol3 = A.q_regress ? 1 : NA;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const int f = half * 128 + row;
+          float v[16];
+          tmem_ld16(tm_d1 + half * 16 + lane_off, v);
+          for (int i = 0; i < A.pol.in_dim; ++i) partial[L.oW1 + (size_t)i * H + f] = v[i];
+          partial[L.ob1 + f] = v[BIAS_K];
+          tmem_ld16(tm_d3 + half * 16 + lane_off, v);
+          for (int j = 0; j < ncol3; ++j) partial[L.oW3 + (size_t)f * A.pol.out_dim + j] = v[j];
+        }
+      }
     }
   }
 }
@@ -587,18 +618,16 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) tc_rollout_kernel(const __grid
 }
 
 // =================================================================================================
-// Weight gradients from the operand store: split-K tcgen05 GEMMs with MN-major operands (K = rows).
-// CTA c owns feature half mh = c & 1 of every left operand and the records r = c>>1, c>>1 + G/2, ...
+// dW2 / db2 from the operand store: split-K tcgen05 GEMMs with MN-major operands (K = rows).
+// CTA c owns feature half mh = c & 1 of the left operand and the records r = c>>1, c>>1 + G/2, ...
 //   D2  [128 x 256] += h1[:, mh]^T . delta2            -> dW2[k][n]
 //   Db2 [128 x 16]  += delta2[:, mh]^T . [p|1]         -> column BIAS_K = db2[n]
-//   D1  [128 x 16]  += delta1[:, mh]^T . [p|1]         -> dW1[i][n] (columns i < in_dim), db1[n] (column BIAS_K)
-//   D3  [128 x 16]  += h2[:, mh]^T . [delta3|0]        -> dW3[k][j]
+// (dW1, db1, dW3 are accumulated inside the rollout kernel, db3 is a shuffle reduction there.)
 // =================================================================================================
 struct DwArgs {
   const uint8_t* store;
   int nrecords;            // tiles * store_steps
-  int has_h2;              // records carry h2 / delta3 images for every step (full BPTT) or only ... always with dW
-  int in_dim, out_dim, act_dim;
+  int in_dim, out_dim;     // gradient layout of the net
   float* partial;
   long long partial_stride;
 };
@@ -607,18 +636,19 @@ struct DwArgs {
 #define MPG_DW_ROWS 32
 #endif
 #ifndef MPG_DW_NSTAGE
-#define MPG_DW_NSTAGE 2
+#define MPG_DW_NSTAGE 4
 #endif
 constexpr int DW_ROWS = MPG_DW_ROWS;                            // rows (K) per stage (multiple of the UMMA k-step)
-constexpr int DW_NSTAGE = MPG_DW_NSTAGE;                                    // ring depth: bytes in flight per SM set the HBM rate
+constexpr int DW_NSTAGE = MPG_DW_NSTAGE;                        // ring depth: bytes in flight per SM set the HBM rate
 constexpr int DW_BLK = DW_ROWS * 128;                           // one 64-feature block of one stage
 constexpr int DW_R16 = DW_ROWS * 32;                            // one [rows x 16] bf16 image of one stage
-constexpr int DW_OFF_H1 = 0, DW_OFF_D2 = 4 * DW_BLK, DW_OFF_D1 = 12 * DW_BLK, DW_OFF_H2 = 16 * DW_BLK,
-              DW_OFF_P = 20 * DW_BLK, DW_OFF_D3 = DW_OFF_P + 2 * DW_R16;
-constexpr int DW_STAGE = DW_OFF_D3 + 2 * DW_R16;                // bytes per stage (42 KB)
+constexpr int DW_OFF_H1 = 0, DW_OFF_D2 = 4 * DW_BLK, DW_OFF_P = 12 * DW_BLK;
+constexpr int DW_STAGE = DW_OFF_P + 2 * DW_R16;                 // bytes per stage (50 KB)
+constexpr int DW_COPIES = 14;                                   // bulk copies per stage, one lane each
 constexpr int DW_SMEM = DW_NSTAGE * DW_STAGE + 256 + 1024;      // dynamic shared memory of tc_dw_kernel
-constexpr int DW_TM_D2 = 0, DW_TM_DB2 = 256, DW_TM_D1 = 272, DW_TM_D3 = 288;
+constexpr int DW_TM_D2 = 0, DW_TM_DB2 = 256;
 static_assert(DW_STAGE % 1024 == 0 && DW_ROWS % 16 == 0, "stages hold whole SW128 atoms and UMMA k-steps");
+static_assert(DW_SMEM <= 232448, "tc_dw_kernel shared memory");
 
 struct DwBars {
   uint64_t full[DW_NSTAGE], empty[DW_NSTAGE], d_full;
@@ -646,38 +676,31 @@ __global__ void __launch_bounds__(192, 1) tc_dw_kernel(const __grid_constant__ D
   const int nstages = nmine * (ACT_ROWS / DW_ROWS);
 
   if (warp == 4) {
-    // ------------------------------- producer: 24 lanes issue the 24 bulk copies of a stage in parallel ----------
-    {
-      // lane -> (source offset inside the record, destination offset inside the stage, bytes); q-independent parts
-      const int sp = lane / 12, k = lane % 12;
-      size_t src = 0; uint32_t dsto = 0, bytes = DW_BLK, qstep = DW_BLK;
-      if (k < 6) {            // left operands h1 / delta1 / h2: the two 64-feature blocks of half mh
-        const int which = k >> 1, jb = k & 1;
-        const size_t slot_off = which == 0 ? SLOT_H1 : (which == 1 ? SLOT_D1 : SLOT_H2);
-        const uint32_t dst_off = which == 0 ? DW_OFF_H1 : (which == 1 ? DW_OFF_D1 : DW_OFF_H2);
-        src = slot_off + (size_t)sp * ACT_SPLIT + (size_t)(2 * mh + jb) * ACT_BLOCK;
-        dsto = dst_off + (sp * 2 + jb) * DW_BLK;
-      } else if (k < 10) {    // right operand delta2: all four blocks
-        const int jb = k - 6;
-        src = SLOT_D2 + (size_t)sp * ACT_SPLIT + (size_t)jb * ACT_BLOCK;
-        dsto = DW_OFF_D2 + (sp * 4 + jb) * DW_BLK;
-      } else {                // [p|1] and [delta3|0] images
-        src = (k == 10 ? SLOT_P : SLOT_D3) + (size_t)sp * 4096;
-        dsto = (k == 10 ? DW_OFF_P : DW_OFF_D3) + sp * DW_R16;
-        bytes = DW_R16; qstep = DW_R16;
-      }
-      uint32_t slot = 0, par = 0;
-      for (int r = first; r < A.nrecords; r += stride) {
-        const uint8_t* rec = A.store + (size_t)r * SLOT_BYTES;
-        for (int q = 0; q < ACT_ROWS / DW_ROWS; ++q) {
-          if (lane == 0) {
-            mbar_wait(&b->empty[slot], par ^ 1);
-            mbar_expect_tx(&b->full[slot], DW_STAGE);
-          }
-          __syncwarp();
-          if (lane < 24) bulk_g2s(stage_buf + slot * DW_STAGE + dsto, rec + src + (size_t)q * qstep, bytes, &b->full[slot]);
-          if (++slot == DW_NSTAGE) { slot = 0; par ^= 1; }
+    // ------------------------------- producer: one lane per bulk copy of a stage -------------------------------
+    const int sp = lane / 7, k = lane % 7;
+    size_t src = 0; uint32_t dsto = 0, bytes = DW_BLK, qstep = DW_BLK;
+    if (k < 2) {            // left operand h1: the two 64-feature blocks of half mh
+      src = SLOT_H1 + (size_t)sp * ACT_SPLIT + (size_t)(2 * mh + k) * ACT_BLOCK;
+      dsto = DW_OFF_H1 + (sp * 2 + k) * DW_BLK;
+    } else if (k < 6) {     // right operand delta2: all four blocks
+      src = SLOT_D2 + (size_t)sp * ACT_SPLIT + (size_t)(k - 2) * ACT_BLOCK;
+      dsto = DW_OFF_D2 + (sp * 4 + (k - 2)) * DW_BLK;
+    } else {                // [p|1] image
+      src = SLOT_P + (size_t)sp * 4096;
+      dsto = DW_OFF_P + sp * DW_R16;
+      bytes = DW_R16; qstep = DW_R16;
+    }
+    uint32_t slot = 0, par = 0;
+    for (int r = first; r < A.nrecords; r += stride) {
+      const uint8_t* rec = A.store + (size_t)r * SLOT_BYTES;
+      for (int q = 0; q < ACT_ROWS / DW_ROWS; ++q) {
+        if (lane == 0) {
+          mbar_wait(&b->empty[slot], par ^ 1);
+          mbar_expect_tx(&b->full[slot], DW_STAGE);
         }
+        __syncwarp();
+        if (lane < DW_COPIES) bulk_g2s(stage_buf + slot * DW_STAGE + dsto, rec + src + (size_t)q * qstep, bytes, &b->full[slot]);
+        if (++slot == DW_NSTAGE) { slot = 0; par ^= 1; }
       }
     }
   } else if (warp == 5) {
@@ -693,25 +716,20 @@ __global__ void __launch_bounds__(192, 1) tc_dw_kernel(const __grid_constant__ D
 #pragma unroll
         for (int ks = 0; ks < DW_ROWS / 16; ++ks) {
           const uint32_t acc = (st | ks) ? 1u : 0u;
-          // left operands (MN-major SW128, M = 128 features = 2 blocks DW_BLK apart, 8-row groups 1024 B apart)
-          auto L = [&](int off, int sp) { return make_desc(base + off + sp * 2 * DW_BLK + ks * 2048, DW_BLK, 1024, LAYOUT_SW128); };
+          // left operand (MN-major SW128, M = 128 features = 2 blocks DW_BLK apart, 8-row groups 1024 B apart)
+          auto L = [&](int sp) { return make_desc(base + DW_OFF_H1 + sp * 2 * DW_BLK + ks * 2048, DW_BLK, 1024, LAYOUT_SW128); };
           // right operand delta2 (N = 256 = 4 blocks)
           auto R2 = [&](int sp) { return make_desc(base + DW_OFF_D2 + sp * 4 * DW_BLK + ks * 2048, DW_BLK, 1024, LAYOUT_SW128); };
-          // right operands [p|1], [delta3|0] (MN-major INTERLEAVE, N = 16: halves 128 B apart (SBO), 8-row groups 256 B apart (LBO))
-          auto R16 = [&](int off, int sp) { return make_desc(base + off + sp * DW_R16 + ks * 512, 256, 128, LAYOUT_NONE); };
-          umma_bf16(tmem + DW_TM_D2, L(DW_OFF_H1, 0), R2(0), id256, acc);
-          umma_bf16(tmem + DW_TM_D2, L(DW_OFF_H1, 1), R2(0), id256, 1u);
-          umma_bf16(tmem + DW_TM_D2, L(DW_OFF_H1, 0), R2(1), id256, 1u);
           // delta2 as LEFT operand for db2: its blocks 2mh, 2mh+1 inside the right-operand buffer
           auto LD2 = [&](int sp) { return make_desc(base + DW_OFF_D2 + sp * 4 * DW_BLK + mh * 2 * DW_BLK + ks * 2048, DW_BLK, 1024, LAYOUT_SW128); };
-          umma_bf16(tmem + DW_TM_DB2, LD2(0), R16(DW_OFF_P, 0), id16, acc);
-          umma_bf16(tmem + DW_TM_DB2, LD2(1), R16(DW_OFF_P, 0), id16, 1u);
-          umma_bf16(tmem + DW_TM_D1, L(DW_OFF_D1, 0), R16(DW_OFF_P, 0), id16, acc);
-          umma_bf16(tmem + DW_TM_D1, L(DW_OFF_D1, 1), R16(DW_OFF_P, 0), id16, 1u);
-          umma_bf16(tmem + DW_TM_D1, L(DW_OFF_D1, 0), R16(DW_OFF_P, 1), id16, 1u);
-          umma_bf16(tmem + DW_TM_D3, L(DW_OFF_H2, 0), R16(DW_OFF_D3, 0), id16, acc);
-          umma_bf16(tmem + DW_TM_D3, L(DW_OFF_H2, 1), R16(DW_OFF_D3, 0), id16, 1u);
-          umma_bf16(tmem + DW_TM_D3, L(DW_OFF_H2, 0), R16(DW_OFF_D3, 1), id16, 1u);
+          // right operand [p|1] (MN-major INTERLEAVE, N = 16: halves 128 B apart (SBO), 8-row groups 256 B apart (LBO));
+          // only its hi split is needed: the constant-1 column is exact in bf16
+          const uint64_t rp = make_desc(base + DW_OFF_P + ks * 512, 256, 128, LAYOUT_NONE);
+          umma_bf16(tmem + DW_TM_D2, L(0), R2(0), id256, acc);
+          umma_bf16(tmem + DW_TM_D2, L(1), R2(0), id256, 1u);
+          umma_bf16(tmem + DW_TM_D2, L(0), R2(1), id256, 1u);
+          umma_bf16(tmem + DW_TM_DB2, LD2(0), rp, id16, acc);
+          umma_bf16(tmem + DW_TM_DB2, LD2(1), rp, id16, 1u);
         }
         umma_commit(&b->empty[slot]);
         if (++slot == DW_NSTAGE) { slot = 0; par ^= 1; }
@@ -737,11 +755,6 @@ __global__ void __launch_bounds__(192, 1) tc_dw_kernel(const __grid_constant__ D
       float v[16];
       tmem_ld16(tmem + DW_TM_DB2 + lane_off, v);
       partial[L.ob2 + f] = v[BIAS_K];
-      tmem_ld16(tmem + DW_TM_D1 + lane_off, v);
-      for (int i = 0; i < A.in_dim; ++i) partial[L.oW1 + (size_t)i * H + f] = v[i];
-      partial[L.ob1 + f] = v[BIAS_K];
-      tmem_ld16(tmem + DW_TM_D3 + lane_off, v);
-      for (int j = 0; j < A.act_dim; ++j) partial[L.oW3 + (size_t)f * A.out_dim + j] = v[j];
     }
     tc_fence_before();
   }
