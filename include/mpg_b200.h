@@ -208,7 +208,9 @@ int mpg_set_timing(mpg_ctx* ctx, int enabled);
 float mpg_kernel_ms(mpg_ctx* ctx);
 
 /* Self test of the tcgen05 GEMM building blocks (tests only). kind 0: Z[128x256] = X[128x256].W[256x256]^T;
- * kind 1: Z[128x256] = X[128x16].W[16x256]; kind 2: Z[128x16] = X[128x256].W[16x256]^T. fp32 device pointers. */
+ * kind 1: Z[128x256] = X[128x16].W[16x256]; kind 2: Z[128x16] = X[128x256].W[16x256]^T. fp32 device pointers.
+ * kinds 3 / 4 are timing probes (tools/gemm_probe.py): the big GEMM `repeats` times back to back with streamed /
+ * resident weights on MPG_SELFTEST_GRID CTAs; Z is not written. */
 int mpg_tc_selftest(mpg_ctx* ctx, int kind, const float* X, const float* W, float* Z, int repeats, void* stream);
 
 /* Debug timeline of the tensor-core rollout kernel: when `buf` (64 int64, device) is non-NULL the next

@@ -101,10 +101,10 @@ __device__ __forceinline__ void consume_pad(Bars* b, Sync& s) {
 struct NoHook { __device__ __forceinline__ void operator()() const {} };
 template <typename Hook = NoHook>
 __device__ __forceinline__ void mma_big(Bars* b, uint32_t act_addr, uint32_t ring_addr, Sync& s, uint32_t d_tmem,
-                                        Hook hook = Hook()) {
+                                        Hook hook = Hook(), bool wait_a = true) {
   constexpr uint32_t idesc = make_idesc(128, 256, 0, 0);
   for (int kb = 0; kb < 4; ++kb) {
-    mbar_wait(&b->a_blk[kb], s.g_cnt & 1);
+    if (wait_a) mbar_wait(&b->a_blk[kb], s.g_cnt & 1);
     tc_fence_after();
     const uint64_t dah = make_desc(act_addr + kb * ACT_BLOCK, 16, 1024, LAYOUT_SW128);
     const uint64_t dal = make_desc(act_addr + ACT_SPLIT + kb * ACT_BLOCK, 16, 1024, LAYOUT_SW128);
@@ -161,18 +161,21 @@ __device__ __forceinline__ void epi_release_chunk(Bars* b, int c) {
 // MN-major.  48 UMMAs (2 halves x 8 row steps x 3 split products).
 __device__ __forceinline__ void mma_acc16(uint32_t act_addr, uint32_t r16_addr, uint32_t d_tmem, bool& started) {
   constexpr uint32_t idesc = make_idesc(128, 16, 1, 1);
+  // the two halves are independent accumulation chains: alternate them so that back-to-back UMMAs never wait for
+  // each other's accumulator
 #pragma unroll
-  for (int half = 0; half < 2; ++half) {
-#pragma unroll
-    for (int ks = 0; ks < ACT_ROWS / 16; ++ks) {
-      const uint32_t a = act_addr + half * 2 * ACT_BLOCK + ks * 2048;
-      const uint64_t dah = make_desc(a, ACT_BLOCK, 1024, LAYOUT_SW128), dal = make_desc(a + ACT_SPLIT, ACT_BLOCK, 1024, LAYOUT_SW128);
-      const uint64_t dbh = make_desc(r16_addr + ks * 512, 256, 128, LAYOUT_NONE), dbl = make_desc(r16_addr + 4096 + ks * 512, 256, 128, LAYOUT_NONE);
-      const uint32_t d = d_tmem + half * 16;
-      umma_bf16(d, dah, dbh, idesc, (started || ks) ? 1u : 0u);
-      umma_bf16(d, dal, dbh, idesc, 1u);
-      umma_bf16(d, dah, dbl, idesc, 1u);
-    }
+  for (int ks = 0; ks < ACT_ROWS / 16; ++ks) {
+    const uint64_t dbh = make_desc(r16_addr + ks * 512, 256, 128, LAYOUT_NONE), dbl = make_desc(r16_addr + 4096 + ks * 512, 256, 128, LAYOUT_NONE);
+    const uint32_t a0 = act_addr + ks * 2048, a1 = a0 + 2 * ACT_BLOCK;
+    const uint64_t d0h = make_desc(a0, ACT_BLOCK, 1024, LAYOUT_SW128), d0l = make_desc(a0 + ACT_SPLIT, ACT_BLOCK, 1024, LAYOUT_SW128);
+    const uint64_t d1h = make_desc(a1, ACT_BLOCK, 1024, LAYOUT_SW128), d1l = make_desc(a1 + ACT_SPLIT, ACT_BLOCK, 1024, LAYOUT_SW128);
+    const uint32_t acc = (started || ks) ? 1u : 0u;
+    umma_bf16(d_tmem, d0h, dbh, idesc, acc);
+    umma_bf16(d_tmem + 16, d1h, dbh, idesc, acc);
+    umma_bf16(d_tmem, d0l, dbh, idesc, 1u);
+    umma_bf16(d_tmem + 16, d1l, dbh, idesc, 1u);
+    umma_bf16(d_tmem, d0h, dbl, idesc, 1u);
+    umma_bf16(d_tmem + 16, d1h, dbl, idesc, 1u);
   }
   started = true;
 }
@@ -448,6 +451,10 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) selftest_kernel(int kind, cons
     const int row = (warp & 3) * 32 + lane, hc = warp >> 2;
     constexpr int CW = COLS_PER_WARP;
     for (int rep = 0; rep < repeats; ++rep) {
+      if (kind >= 3) {          // timing probes: back-to-back big GEMMs on whatever the images hold, one wait at the end
+        if (rep == repeats - 1) epi_wait_d(b, s);
+        continue;
+      }
       if (kind == 1) {
         if (hc == 0) {
           for (int kh = 0; kh < 2; ++kh) {
@@ -485,10 +492,32 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) selftest_kernel(int kind, cons
     tc_fence_before();
   } else if (warp == EPI_WARPS) {
     if (lane == 0)
-      for (int rep = 0; rep < repeats; ++rep) gemm<ROLE_PRODUCER>(kind, b, smem, s, img, 0);
+      for (int rep = 0; rep < repeats; ++rep)
+        if (kind != 4) gemm<ROLE_PRODUCER>(kind == 3 ? 0 : kind, b, smem, s, img, 0);
   } else {
     if (lane == 0)
-      for (int rep = 0; rep < repeats; ++rep) gemm<ROLE_MMA>(kind, b, smem, s, img, tmem + TM_WORK);
+      for (int rep = 0; rep < repeats; ++rep) {
+        if (kind == 3) {          // weights streamed through the ring, no epilogue in the loop
+          mma_big(b, smem_u32(smem) + SmemMap::ACT, smem_u32(smem) + SmemMap::RING, s, tmem + TM_WORK, NoHook(), false);
+          if (rep == repeats - 1) mma_publish_d(b);
+        } else if (kind == 4) {   // operands resident, no streaming: the tensor pipe's own rate for this shape
+          constexpr uint32_t idesc = make_idesc(128, 256, 0, 0);
+          const uint32_t act = smem_u32(smem) + SmemMap::ACT, ring = smem_u32(smem) + SmemMap::RING;
+          for (int k = 0; k < 16; ++k) {
+            const uint64_t ko = (uint64_t)((k & 3) * 2);
+            const uint64_t dah = make_desc(act + (k >> 2) * ACT_BLOCK, 16, 1024, LAYOUT_SW128) + ko;
+            const uint64_t dal = make_desc(act + ACT_SPLIT + (k >> 2) * ACT_BLOCK, 16, 1024, LAYOUT_SW128) + ko;
+            const uint64_t dbh = make_desc(ring, 16, 1024, LAYOUT_SW128) + ko;
+            const uint64_t dbl = make_desc(ring + 2 * STAGE_BYTES, 16, 1024, LAYOUT_SW128) + ko;
+            umma_bf16(tmem + TM_WORK, dah, dbh, idesc, 1u);
+            umma_bf16(tmem + TM_WORK, dal, dbh, idesc, 1u);
+            umma_bf16(tmem + TM_WORK, dah, dbl, idesc, 1u);
+          }
+          if (rep == repeats - 1) mma_publish_d(b);
+        } else {
+          gemm<ROLE_MMA>(kind, b, smem, s, img, tmem + TM_WORK);
+        }
+      }
   }
   cta_teardown(b);
 }

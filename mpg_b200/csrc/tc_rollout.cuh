@@ -109,6 +109,11 @@ inline cudaError_t tc_launch_rollout(int env, const tc::TcArgs& a, int grid, cud
 // self test of one GEMM kind (see tc_gemm.cuh): W is fp32 [256 x 256] (kind 0), [16 x 256] (kinds 1, 2)
 inline cudaError_t tc_selftest(TcState& t, int kind, const float* X, const float* W, float* Z, int repeats, cudaStream_t st) {
   if (!t.scratch_img) return cudaErrorNotSupported;
+  if (kind >= 3) {   // timing probes (tools/gemm_probe.py): MPG_SELFTEST_GRID CTAs run the big GEMM `repeats` times
+    const char* g = getenv("MPG_SELFTEST_GRID");
+    tc::selftest_kernel<<<g ? atoi(g) : 1, tc::CTA_THREADS, tc::SmemMap::TOTAL + 1024, st>>>(kind, X, t.scratch_img, Z, repeats);
+    return cudaGetLastError();
+  }
   if (kind == 0) tc::pack_big_image<<<32, 256, 0, st>>>(W, H, 1, t.scratch_img);
   else if (kind == 1) tc::pack_l1_image<<<2, 256, 0, st>>>(W, W, 16, -1, t.scratch_img);
   else tc::pack_in_image<<<2, 256, 0, st>>>(W, 16, t.scratch_img);
