@@ -304,7 +304,8 @@ def main():
     sm_mhz = (clocks or {}).get('sm_mhz') or 1965.0
     ffma_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
     traffic = None   # dram__bytes_read.sum + dram__bytes_write.sum of the same kernel, one ncu --set full capture
-    prof = os.path.join(ROOT, 'profiles', 'r1_tc_rollout_kernel_ncu_full.csv' if backend == 'tc' else
+    # tc: the rollout runs as two launches of the same kernel (full waves + tail wave); their bytes are summed
+    prof = os.path.join(ROOT, 'profiles', 'r1b_tc_rollout_kernel_ncu_full.csv' if backend == 'tc' else
                         'r1_ffma_rollout_kernel_ncu_full.csv')
     try:
         mult = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
@@ -320,7 +321,8 @@ def main():
         'bound': 'tensor', 'achieved': achieved_tf, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': achieved_tf / peak_tf,
         'traffic': traffic,
         'traffic_note': 'bytes per launch from profiles/ (ncu --set full of the same kernel at B=65536); algorithmic '
-                        'bytes are 56 B/state-step = 92 MB; the tc path adds the dW operand store (4 KB/state-step)',
+                        'bytes are 56 B/state-step = 92 MB; the tc path adds the dW operand store (2.1 KB/state-step: h1 and '
+                        'delta2 images for dW2); tc kernel_ms spans both launches of the rollout (full waves + tail wave)',
         'kernel': 'rollout_kernel<PathTracking,BWD> (fused forward rollout + BPTT, %s backend)' % backend,
         'kernel_ms': k_ms, 'algorithmic_flop_per_state_step': FLOP_PER_STATE_STEP,
         'peak_source': ('MEASURED_PEAKS.json bf16_tflops_sustained (of measured)' if peaks else 'fallback 1.4 PFLOP/s (of fallback)'),

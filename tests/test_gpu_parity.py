@@ -408,3 +408,25 @@ def test_tc_full_bptt_row_chunking_matches_single_call():
     e.MAX_TC_FULL_BPTT_ROWS = 131072
     gp1, _ = e.policy_grad(obs, [n], [1.0], M=M, use_philox=True, noise_seed=5, full_bptt=True)
     assert rel_l2(gp0.cpu().numpy(), gp1.cpu().numpy()) <= 1e-5
+
+
+def test_tc_wave_tail_overlap_matches_single_launch(monkeypatch):
+    """The tensor-core policy gradient splits its launch into full waves + tail wave and runs the weight-gradient
+    GEMMs of the full waves on a side stream under the tail; the result must equal the single-launch schedule
+    (MPG_TAIL_OVERLAP=0) and the oracle-checked small-batch path."""
+    from mpg_b200.policy import PolicyWithQs
+    n = 5
+    res = {}
+    for mode in ('1', '0'):
+        monkeypatch.setenv('MPG_TAIL_OVERLAP', mode)
+        pol = PolicyWithQs(**vars(default_args('NADP', PT, replay_batch_size=4096)))
+        pol.set_weights(synthetic.make_policy_with_qs_weights(1, 6, 2, 256, double_q=False))
+        e = pol.engine
+        if not e.tc_available():
+            pytest.skip('tensor-core backend does not cover this configuration')
+        e.set_backend(1)
+        B = (e.num_sms + 40) * 128 - 17          # one full wave + a ragged tail of 40 tiles
+        obs = e.dev(synthetic.make_obs(np.random.default_rng(5), PT, B))
+        res[mode] = [t.cpu().numpy() for t in e.policy_grad(obs, [0, n], [0.4, 0.6], full_bptt=True, use_philox=True, noise_seed=3)]
+    assert np.array_equal(res['1'][1], res['0'][1])                      # returns: same kernels, same rows
+    assert rel_l2(res['1'][0], res['0'][0]) <= 1e-5                      # gradient: same terms, different partial grouping
