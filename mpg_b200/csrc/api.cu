@@ -100,6 +100,7 @@ __global__ void adam_kernel(float* __restrict__ w, float* __restrict__ m, float*
 __global__ void sq_err_kernel(const float* __restrict__ q, const float* __restrict__ target, int n, float* __restrict__ out) {
   __shared__ float red[1024];
   float s = 0.f;
+#pragma unroll 8
   for (int i = threadIdx.x; i < n; i += blockDim.x) { const float d = q[i] - target[i]; s = fmaf(0.5f * d, d, s); }
   red[threadIdx.x] = s;
   __syncthreads();
@@ -132,9 +133,19 @@ __global__ void reduce_partials_kernel(const float* __restrict__ partial, size_t
 }
 
 __global__ void clip_kernel(float* __restrict__ g, int n, float clip, float* __restrict__ norm_out) {
+  // one block (fixed summation order => bit-reproducible); 8 independent loads in flight per thread hide the
+  // global-memory latency that otherwise serialises the 67 iterations of a 68K-float net
   __shared__ float red[1024];
   float s = 0.f;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) s = fmaf(g[i], g[i], s);
+  int i = threadIdx.x;
+  for (; i + 7 * (int)blockDim.x < n; i += 8 * blockDim.x) {
+    float v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = g[i + u * blockDim.x];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) s = fmaf(v[u], v[u], s);
+  }
+  for (; i < n; i += blockDim.x) s = fmaf(g[i], g[i], s);
   red[threadIdx.x] = s;
   __syncthreads();
   for (int o = blockDim.x / 2; o > 0; o >>= 1) {
@@ -143,7 +154,10 @@ __global__ void clip_kernel(float* __restrict__ g, int n, float clip, float* __r
   }
   const float norm = sqrtf(red[0]);
   const float scale = clip * fminf(1.f / norm, 1.f / clip);   // tf.clip_by_global_norm
-  for (int i = threadIdx.x; i < n; i += blockDim.x) g[i] *= scale;
+  if (scale != 1.f) {
+#pragma unroll 8
+    for (int j = threadIdx.x; j < n; j += blockDim.x) g[j] *= scale;
+  }
   if (threadIdx.x == 0 && norm_out) norm_out[0] = norm;
 }
 
