@@ -51,6 +51,7 @@ struct Bars {
   uint64_t z_full[2];    // first-layer chunk buffer j holds a fresh 64-column chunk (mma -> epilogue)
   uint64_t z_empty[2];   // chunk buffer j has been read out (epilogue -> mma)
   uint64_t acc_done;     // the D1 accumulation UMMAs have read the delta1 / [p|1] images
+  uint64_t kb_done[4];   // big GEMM: the UMMAs of K-block kb are complete (block kb of the A image is no longer read)
   uint32_t tmem_base;
 };
 static_assert(sizeof(Bars) <= 256, "BARS region too small");
@@ -62,6 +63,7 @@ struct Sync {
   uint32_t g_cnt = 0;    // a_blk[] phases seen (GEMMs whose A operand is the activation image)
   uint32_t d_cnt = 0;    // d_full phases seen
   uint32_t acc_cnt = 0;  // acc_done phases seen (epilogue side)
+  uint32_t k_cnt = 0;    // big GEMMs issued so far (kb_done[] phases, epilogue side)
 };
 
 enum Role { ROLE_EPI = 0, ROLE_PRODUCER = 1, ROLE_MMA = 2 };
@@ -130,6 +132,7 @@ __device__ __forceinline__ void mma_big(Bars* b, uint32_t act_addr, uint32_t rin
       s.stage += 2;
       if (kb == 0 && sp == 0) hook();
     }
+    umma_commit(&b->kb_done[kb]);
   }
   ++s.g_cnt;
 }
@@ -262,6 +265,7 @@ __device__ __forceinline__ void gemm_issue(int kind, Bars* b, uint8_t* smem, Syn
     mma_publish_d(b);
   } else {
     if (kind == 1) epi_publish_a(b);
+    if (kind == 0) ++s.k_cnt;
   }
 }
 // Streamed first layer + layer 2 (or the Q net's): the first-layer result never sits in TMEM as a whole; its four
@@ -296,6 +300,7 @@ __device__ __forceinline__ void fwd_pair_issue(Bars* b, uint8_t* smem, Sync& s, 
     mma_publish_d(b);
   } else {
     epi_publish_a(b);
+    ++s.k_cnt;
   }
 }
 // Tail of a backward step: the first-layer pre-activations are recomputed chunk by chunk for elu'(z1) (the [p|a|1]
@@ -367,6 +372,7 @@ __device__ __forceinline__ Bars* cta_setup(uint8_t* smem) {
     mbar_init(&b->d_full, 1);
     for (int i = 0; i < 2; ++i) { mbar_init(&b->z_full[i], 1); mbar_init(&b->z_empty[i], EPI_THREADS); }
     mbar_init(&b->acc_done, 1);
+    for (int i = 0; i < 4; ++i) mbar_init(&b->kb_done[i], 1);
     fence_barrier_init();
   }
   if (warp == EPI_WARPS + 1) tmem_alloc(&b->tmem_base, TMEM_COLS);

@@ -85,6 +85,43 @@ __device__ __forceinline__ void act_load8(const uint8_t* act_hi, const uint8_t* 
   }
 }
 
+// whole-image bulk store to the dW operand store (one elected epilogue thread); the matching wait must come
+// before the shared-memory source is overwritten
+__device__ __forceinline__ void store_image(bool elected, uint8_t* gdst, const uint8_t* ssrc, uint32_t bytes) {
+  fence_proxy_async();
+  epi_bar();
+  if (elected) {
+    bulk_s2g(gdst, ssrc, bytes);
+    bulk_commit();
+  }
+}
+// Block-ordered variant for the big GEMMs' A images (h1, delta2): each K-block of the GEMM reads one 64-feature
+// block of the image exactly once, so block kb can leave as soon as the UMMAs of K-block kb are complete
+// (kb_done[kb]).  The elected thread -- idle anyway until the accumulator is ready -- issues the four bulk groups
+// (hi and lo 16 KB pieces of block kb) behind the GEMM; the next epilogue overwrites the image block by block and
+// waits for group kb only (store_wait_block), so the 128 KB store (~4.8 K cycles at the per-SM store rate) drains
+// under the GEMM tail and that epilogue instead of in front of it.
+__device__ __forceinline__ void store_image_follow(bool elected, Bars* b, const Sync& s, uint8_t* gdst, const uint8_t* ssrc) {
+  if (elected) {
+    const uint32_t par = (s.k_cnt - 1) & 1;                  // the big GEMM issued last
+#pragma unroll
+    for (int kb = 0; kb < 4; ++kb) {
+      mbar_wait(&b->kb_done[kb], par);
+      bulk_s2g(gdst + kb * ACT_BLOCK, ssrc + kb * ACT_BLOCK, ACT_BLOCK);
+      bulk_s2g(gdst + ACT_SPLIT + kb * ACT_BLOCK, ssrc + ACT_SPLIT + kb * ACT_BLOCK, ACT_BLOCK);
+      bulk_commit();
+    }
+  }
+}
+__device__ __forceinline__ void store_wait_block(bool elected, int kb) {
+  if (elected) bulk_wait_read_pending(3 - kb);
+  epi_bar();
+}
+__device__ __forceinline__ void store_wait(bool elected) {
+  if (elected) bulk_wait_read_all();
+  epi_bar();
+}
+
 // Block-ordered epilogues: every warp handles 16 columns of each 64-feature block kb, so that block kb of
 // the activation image is complete (and published to the MMA warp) after 1/4 of the epilogue.
 
@@ -120,12 +157,13 @@ __device__ MPG_EPI_INLINE void epi_hidden2(uint32_t tm_lane, const float* b2, co
 }
 // same, and keep h2 as an image (backward pass: delta2 and the dW3 operand are derived from it)
 __device__ MPG_EPI_INLINE void epi_hidden2_img(uint32_t tm_lane, const float* b2, const float* W3, uint8_t* act, int row,
-                                               int hc, float& p0, float& p1) {
+                                               int hc, float& p0, float& p1, bool draining = false, bool elected = false) {
   p0 = 0.f; p1 = 0.f;
   for (int kb = 0; kb < 4; ++kb) {
     const int c0 = kb * 64 + hc * 16;
     float v[16];
     tmem_ld16(tm_lane + c0, v);
+    if (draining) store_wait_block(elected, kb);             // block kb of the old image has been read out
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
       v[i] = elu_fast(v[i] + b2[c0 + i]);
@@ -157,7 +195,7 @@ __device__ MPG_EPI_INLINE void epi_delta2_blocks(Bars* b, const float* W3, float
 }
 // delta1 = g_h1 (TMEM work) * elu'(z1) (recomputed, streamed through the chunk buffers) -> delta1 image
 __device__ MPG_EPI_INLINE void epi_delta1_blocks(Bars* b, uint32_t tm_work_lane, uint32_t tm_zc_lane, uint8_t* act, int row,
-                                                 int hc) {
+                                                 int hc, bool draining = false, bool elected = false) {
   for (int kb = 0; kb < 4; ++kb) {
     const int c0 = kb * 64 + hc * 16;
     float g[16], z[16];
@@ -165,6 +203,7 @@ __device__ MPG_EPI_INLINE void epi_delta1_blocks(Bars* b, uint32_t tm_work_lane,
     epi_wait_chunk(b, kb);
     tmem_ld16(tm_zc_lane + (kb & 1) * 64 + hc * 16, z);
     epi_release_chunk(b, kb);
+    if (draining) store_wait_block(elected, kb);             // block kb of the old image has been read out
 #pragma unroll
     for (int i = 0; i < 16; ++i) g[i] *= (z[i] > 0.f ? 1.f : exp_fast(z[i]));
     act_store8(act, act + ACT_SPLIT, row, c0 >> 3, g);
@@ -192,20 +231,6 @@ __device__ __forceinline__ void write_row16(uint8_t* img, int row, const float* 
   }
 }
 
-// whole-image bulk store to the dW operand store (one elected epilogue thread); the matching wait must come
-// before the shared-memory source is overwritten
-__device__ __forceinline__ void store_image(bool elected, uint8_t* gdst, const uint8_t* ssrc, uint32_t bytes) {
-  fence_proxy_async();
-  epi_bar();
-  if (elected) {
-    bulk_s2g(gdst, ssrc, bytes);
-    bulk_commit();
-  }
-}
-__device__ __forceinline__ void store_wait(bool elected) {
-  if (elected) bulk_wait_read_all();
-  epi_bar();
-}
 
 template <int ENV, bool BWD, int ROLE>
 __device__ __forceinline__ void run_rollout(const TcArgs& A, uint8_t* smem, Bars* b) {
@@ -284,13 +309,12 @@ __device__ __forceinline__ void run_rollout(const TcArgs& A, uint8_t* smem, Bars
         if (bwd_pass) stamp(2);
         epi_hidden1_blocks(b, tm_z1c + lane_off, act_img, row, hc);   // follows the z1 chunk stream
         if (bwd_pass) stamp(3);
-        if (rec_) store_image(elected, slot + SLOT_H1, act_img, 2 * ACT_SPLIT);
+        if (rec_) store_image_follow(elected, b, sy, slot + SLOT_H1, act_img);   // h1 blocks leave behind their K-blocks
         epi_wait_d(b, sy);                                   // z2 (all layer-2 UMMAs done: h1 image free)
         if (bwd_pass) stamp(4);
         float p0, p1;
         if (bwd_pass) {
-          if (rec_) store_wait(elected);                     // h1 image has been read out
-          epi_hidden2_img(tm_work + lane_off, mf->b2p, mf->W3p, act_img, row, hc, p0, p1);
+          epi_hidden2_img(tm_work + lane_off, mf->b2p, mf->W3p, act_img, row, hc, p0, p1, rec_, elected);
         } else {
           epi_hidden2(tm_work + lane_off, mf->b2p, mf->W3p, hc, p0, p1);
         }
@@ -530,15 +554,14 @@ __device__ __forceinline__ void run_rollout(const TcArgs& A, uint8_t* smem, Bars
           stamp(6);
           epi_delta2_blocks(b, mf->W3p, mf->d3s[row], mf->d3s[ACT_ROWS + row], act_img, row, hc);
           stamp(7);
-          if (rec) store_image(elected, slot + SLOT_D2, act_img, 2 * ACT_SPLIT);
+          if (rec) store_image_follow(elected, b, sy, slot + SLOT_D2, act_img);   // delta2 blocks leave behind their K-blocks
           epi_wait_d(b, sy);                                       // g_h1 complete, delta2 image consumed
           stamp(8);
         }
         // z1 recompute stream, g_p following the delta1 blocks, D1 += delta1^T [p|1]
         bwd_tail_issue<ROLE>(b, smem, sy, A.pol.l1, A.pol.in, t > 0, want_dw, d1_started, tm_z1c, tm_gp, tm_d1);
         if (ROLE == ROLE_EPI) {
-          if (rec) store_wait(elected);                            // delta2 image read out before it is overwritten
-          epi_delta1_blocks(b, tm_work + lane_off, tm_z1c + lane_off, act_img, row, hc);
+          epi_delta1_blocks(b, tm_work + lane_off, tm_z1c + lane_off, act_img, row, hc, rec, elected);
           stamp(9);
           if (t > 0) epi_wait_d(b, sy);
           if (want_dw) d1_pending = true;
