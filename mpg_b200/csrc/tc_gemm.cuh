@@ -161,26 +161,20 @@ __device__ __forceinline__ void epi_release_chunk(Bars* b, int c) {
 }
 // Weight-gradient accumulation with the operands where they already are: D[half][128 features x 16] +=
 // IMG[:, half]^T . R16, IMG = activation image read MN-major (K = rows), R16 = [p|1] or [delta3|0] image read
-// MN-major.  48 UMMAs (2 halves x 8 row steps x 3 split products).
-__device__ __forceinline__ void mma_acc16(uint32_t act_addr, uint32_t r16_addr, uint32_t d_tmem, bool& started) {
+// MN-major.  24 UMMAs per half (8 row steps x 3 split products); a half needs only its two 64-feature blocks of the
+// image, so it can be issued as soon as those are written and lets the image be overwritten half by half.
+__device__ __forceinline__ void mma_acc16_half(uint32_t act_addr, uint32_t r16_addr, uint32_t d_tmem, int half, bool started) {
   constexpr uint32_t idesc = make_idesc(128, 16, 1, 1);
-  // the two halves are independent accumulation chains: alternate them so that back-to-back UMMAs never wait for
-  // each other's accumulator
+  const uint32_t d = d_tmem + half * 16;
 #pragma unroll
   for (int ks = 0; ks < ACT_ROWS / 16; ++ks) {
+    const uint32_t a = act_addr + half * 2 * ACT_BLOCK + ks * 2048;
+    const uint64_t dah = make_desc(a, ACT_BLOCK, 1024, LAYOUT_SW128), dal = make_desc(a + ACT_SPLIT, ACT_BLOCK, 1024, LAYOUT_SW128);
     const uint64_t dbh = make_desc(r16_addr + ks * 512, 256, 128, LAYOUT_NONE), dbl = make_desc(r16_addr + 4096 + ks * 512, 256, 128, LAYOUT_NONE);
-    const uint32_t a0 = act_addr + ks * 2048, a1 = a0 + 2 * ACT_BLOCK;
-    const uint64_t d0h = make_desc(a0, ACT_BLOCK, 1024, LAYOUT_SW128), d0l = make_desc(a0 + ACT_SPLIT, ACT_BLOCK, 1024, LAYOUT_SW128);
-    const uint64_t d1h = make_desc(a1, ACT_BLOCK, 1024, LAYOUT_SW128), d1l = make_desc(a1 + ACT_SPLIT, ACT_BLOCK, 1024, LAYOUT_SW128);
-    const uint32_t acc = (started || ks) ? 1u : 0u;
-    umma_bf16(d_tmem, d0h, dbh, idesc, acc);
-    umma_bf16(d_tmem + 16, d1h, dbh, idesc, acc);
-    umma_bf16(d_tmem, d0l, dbh, idesc, 1u);
-    umma_bf16(d_tmem + 16, d1l, dbh, idesc, 1u);
-    umma_bf16(d_tmem, d0h, dbl, idesc, 1u);
-    umma_bf16(d_tmem + 16, d1h, dbl, idesc, 1u);
+    umma_bf16(d, dah, dbh, idesc, (started || ks) ? 1u : 0u);
+    umma_bf16(d, dal, dbh, idesc, 1u);
+    umma_bf16(d, dah, dbl, idesc, 1u);
   }
-  started = true;
 }
 // first-layer GEMM: D[128 x 256] = P[128 x 16] . W1aug^T ; P is the INTERLEAVE image in shared memory,
 // W1aug image streamed as ONE stage = [hi: 256 rows x 32 B][lo: 256 rows x 32 B] = 16 KB
@@ -324,21 +318,48 @@ __device__ __forceinline__ void bwd_tail_issue(Bars* b, uint8_t* smem, Sync& s, 
     umma_commit(&b->empty[slot]);
     ++s.stage;
     consume_pad(b, s);
+    // g_p K-block kb follows delta1 block kb; the D1 UMMAs are issued after g_p has been committed, so they run
+    // under the epilogue's lambda update and the start of the next step (acc_done gates the next image writes)
+    constexpr uint32_t idesc_in = make_idesc(128, 16, 0, 0);
+    const uint32_t act_addr = base + SmemMap::ACT;
+    const uint32_t islot = s.stage & (NSLOT - 1), ipar = (s.stage / NSLOT) & 1;
+    const uint32_t ibase = ring + islot * STAGE_BYTES;
+    for (int kb = 0; kb < 4; ++kb) {
+      mbar_wait(&b->a_blk[kb], s.g_cnt & 1);
+      if (do_gp) {
+        if (kb == 0) mbar_wait(&b->full[islot], ipar);
+        tc_fence_after();
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          const uint32_t a_hi = act_addr + kb * ACT_BLOCK + ks * 32, a_lo = a_hi + ACT_SPLIT;
+          const uint32_t b_hi = ibase + kb * 2048 + ks * 32, b_lo = b_hi + 8192;
+          const uint64_t dah = make_desc(a_hi, 16, 1024, LAYOUT_SW128), dal = make_desc(a_lo, 16, 1024, LAYOUT_SW128);
+          const uint64_t dbh = make_desc(b_hi, 16, 1024, LAYOUT_SW128), dbl = make_desc(b_lo, 16, 1024, LAYOUT_SW128);
+          umma_bf16(tm_gp, dah, dbh, idesc_in, (kb | ks) ? 1u : 0u);
+          umma_bf16(tm_gp, dal, dbh, idesc_in, 1u);
+          umma_bf16(tm_gp, dah, dbl, idesc_in, 1u);
+        }
+      } else {
+        tc_fence_after();
+      }
+    }
+    ++s.g_cnt;
     if (do_gp) {
-      mma_in(b, base + SmemMap::ACT, ring, s, tm_gp);
+      umma_commit(&b->empty[islot]);
+      ++s.stage;
+      consume_pad(b, s);
       mma_publish_d(b);
-    } else {
-      for (int kb = 0; kb < 4; ++kb) mbar_wait(&b->a_blk[kb], s.g_cnt & 1);
-      ++s.g_cnt;
-      tc_fence_after();
     }
     if (do_d1) {
-      mma_acc16(base + SmemMap::ACT, p_addr, tm_d1, d1_started);
+      mma_acc16_half(act_addr, p_addr, tm_d1, 0, d1_started);
+      mma_acc16_half(act_addr, p_addr, tm_d1, 1, d1_started);
+      d1_started = true;
       umma_commit(&b->acc_done);
     }
   }
 }
-// D3 += h2^T [delta3|0]: the epilogue publishes (h2 image + delta3 image written), the UMMAs complete on d_full
+// D3 += h2^T [delta3|0]: the epilogue publishes (h2 image + delta3 image written); the UMMAs complete on d_full
+// twice, once per 128-feature half, so that the delta2 epilogue can start on the first half of the image
 template <int ROLE>
 __device__ __forceinline__ void d3_issue(Bars* b, uint8_t* smem, Sync& s, uint32_t d3_off, bool& d3_started, uint32_t tm_d3) {
   if (ROLE == ROLE_MMA) {
@@ -346,8 +367,11 @@ __device__ __forceinline__ void d3_issue(Bars* b, uint8_t* smem, Sync& s, uint32
     mbar_wait(&b->a_full, s.a_cnt & 1);
     ++s.a_cnt;
     tc_fence_after();
-    mma_acc16(base + SmemMap::ACT, base + d3_off, tm_d3, d3_started);
-    mma_publish_d(b);
+    mma_acc16_half(base + SmemMap::ACT, base + d3_off, tm_d3, 0, d3_started);
+    mma_publish_d(b);                      // blocks 0, 1 of the h2 image may be overwritten
+    mma_acc16_half(base + SmemMap::ACT, base + d3_off, tm_d3, 1, d3_started);
+    mma_publish_d(b);                      // blocks 2, 3
+    d3_started = true;
   } else if (ROLE == ROLE_EPI) {
     epi_publish_a(b);
   }

@@ -176,9 +176,11 @@ __device__ MPG_EPI_INLINE void epi_hidden2_img(uint32_t tm_lane, const float* b2
   }
 }
 // delta2 = (delta3 W3^T) * elu'(h2), h2 read back from its image and overwritten in place by delta2
-__device__ MPG_EPI_INLINE void epi_delta2_blocks(Bars* b, const float* W3, float d30, float d31, uint8_t* act, int row, int hc) {
+__device__ MPG_EPI_INLINE void epi_delta2_blocks(Bars* b, const float* W3, float d30, float d31, uint8_t* act, int row, int hc,
+                                                 Sync* wait_half1 = nullptr) {
   for (int kb = 0; kb < 4; ++kb) {
     const int c0 = kb * 64 + hc * 16;
+    if (kb == 2 && wait_half1) epi_wait_d(b, *wait_half1);   // the D3 UMMAs have read blocks 2, 3 of the h2 image
     float v[16];
     act_load8(act, act + ACT_SPLIT, row, c0 >> 3, v);
     act_load8(act, act + ACT_SPLIT, row, (c0 >> 3) + 1, v + 8);
@@ -474,13 +476,13 @@ __device__ __forceinline__ void run_rollout(const TcArgs& A, uint8_t* smem, Bars
           }
           if (reg) d3_issue<ROLE>(b, smem, sy, SM_D3IMG, d3_started, tm_d3);   // dW3q += h2q^T delta3
           if (ROLE == ROLE_EPI) {
-            if (reg) epi_wait_d(b, sy);                    // h2q image read by the D3 UMMAs before delta2 overwrites it
+            if (reg) epi_wait_d(b, sy);                    // blocks 0, 1 of the h2q image read by the D3 UMMAs
             epi_bar();
             if (reg && tid == 0) db3acc[0] += (mf->wsum[0] + mf->wsum[2]) + (mf->wsum[4] + mf->wsum[6]);
           }
           gemm_issue<ROLE>(0, b, smem, sy, A.q.big_dx, tm_work);  // g_h1q, K-blocks issued as delta2 blocks appear
           if (ROLE == ROLE_EPI) {
-            epi_delta2_blocks(b, mf->W3q, mf->d3s[row], 0.f, act_img, row, hc);
+            epi_delta2_blocks(b, mf->W3q, mf->d3s[row], 0.f, act_img, row, hc, reg ? &sy : nullptr);
             if (qslot) store_image(elected, qslot + SLOT_D2, act_img, 2 * ACT_SPLIT);
             epi_wait_d(b, sy);
           }
@@ -539,7 +541,7 @@ __device__ __forceinline__ void run_rollout(const TcArgs& A, uint8_t* smem, Bars
         }
         if (want_dw) d3_issue<ROLE>(b, smem, sy, SM_D3IMG, d3_started, tm_d3);   // dW3 += h2^T delta3
         if (ROLE == ROLE_EPI) {
-          if (want_dw) epi_wait_d(b, sy);                   // h2 image read by the D3 UMMAs before delta2 overwrites it
+          if (want_dw) epi_wait_d(b, sy);                   // blocks 0, 1 of the h2 image read by the D3 UMMAs
           epi_bar();
           if (tid == 0 && want_dw) {
             db3acc[0] += (mf->wsum[0] + mf->wsum[2]) + (mf->wsum[4] + mf->wsum[6]);
@@ -552,7 +554,7 @@ __device__ __forceinline__ void run_rollout(const TcArgs& A, uint8_t* smem, Bars
         if (ROLE == ROLE_MMA) stamp(4);
         if (ROLE == ROLE_EPI) {
           stamp(6);
-          epi_delta2_blocks(b, mf->W3p, mf->d3s[row], mf->d3s[ACT_ROWS + row], act_img, row, hc);
+          epi_delta2_blocks(b, mf->W3p, mf->d3s[row], mf->d3s[ACT_ROWS + row], act_img, row, hc, want_dw ? &sy : nullptr);
           stamp(7);
           if (rec) store_image_follow(elected, b, sy, slot + SLOT_D2, act_img);   // delta2 blocks leave behind their K-blocks
           epi_wait_d(b, sy);                                       // g_h1 complete, delta2 image consumed
