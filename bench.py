@@ -305,7 +305,7 @@ def main():
     ffma_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
     traffic = None   # dram__bytes_read.sum + dram__bytes_write.sum of the same kernel, one ncu --set full capture
     # tc: the rollout runs as two launches of the same kernel (full waves + tail wave); their bytes are summed
-    prof = os.path.join(ROOT, 'profiles', 'r1b_tc_rollout_kernel_ncu_full.csv' if backend == 'tc' else
+    prof = os.path.join(ROOT, 'profiles', 'r1c_tc_rollout_kernel_ncu_full.csv' if backend == 'tc' else
                         'r1_ffma_rollout_kernel_ncu_full.csv')
     try:
         mult = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}

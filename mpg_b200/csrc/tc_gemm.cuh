@@ -285,12 +285,11 @@ __device__ __forceinline__ void fwd_pair_issue(Bars* b, uint8_t* smem, Sync& s, 
     mma_l1_chunk(b, p_addr, bbase, 2, tm_z1c);
     ++s.stage;
     consume_pad(b, s);
-    // the last chunk waits for the epilogue to finish chunk 1; the first UMMAs of the big GEMM keep the tensor
-    // pipe busy meanwhile.  The first-layer ring slot is released after its last reader.
-    mma_big(b, base + SmemMap::ACT, ring, s, tm_work, [&]() {
-      mma_l1_chunk(b, p_addr, bbase, 3, tm_z1c);
-      umma_commit(&b->empty[slot]);
-    });
+    // the last chunk waits for the epilogue to have read chunk 1, which happens about when h1 block 0 is published:
+    // issuing it BEFORE the first big UMMAs keeps it from queueing behind them in the tensor pipe
+    mma_l1_chunk(b, p_addr, bbase, 3, tm_z1c);
+    umma_commit(&b->empty[slot]);
+    mma_big(b, base + SmemMap::ACT, ring, s, tm_work);
     mma_publish_d(b);
   } else {
     epi_publish_a(b);

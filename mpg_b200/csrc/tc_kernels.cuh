@@ -308,19 +308,19 @@ __device__ __forceinline__ void run_rollout(const TcArgs& A, uint8_t* smem, Bars
       fwd_pair_issue<ROLE>(b, smem, sy, A.pol.l1, A.pol.big_fwd, tm_z1c, tm_work);
       if (ROLE == ROLE_MMA && bwd_pass) stamp(2);
       if (ROLE == ROLE_EPI) {
-        if (bwd_pass) stamp(2);
+        stamp(bwd_pass ? 2 : 17);
         epi_hidden1_blocks(b, tm_z1c + lane_off, act_img, row, hc);   // follows the z1 chunk stream
-        if (bwd_pass) stamp(3);
+        stamp(bwd_pass ? 3 : 18);
         if (rec_) store_image_follow(elected, b, sy, slot + SLOT_H1, act_img);   // h1 blocks leave behind their K-blocks
         epi_wait_d(b, sy);                                   // z2 (all layer-2 UMMAs done: h1 image free)
-        if (bwd_pass) stamp(4);
+        stamp(bwd_pass ? 4 : 19);
         float p0, p1;
         if (bwd_pass) {
           epi_hidden2_img(tm_work + lane_off, mf->b2p, mf->W3p, act_img, row, hc, p0, p1, rec_, elected);
         } else {
           epi_hidden2(tm_work + lane_off, mf->b2p, mf->W3p, hc, p0, p1);
         }
-        if (bwd_pass) stamp(5);
+        stamp(bwd_pass ? 5 : 20);
         mf->part[(hc * 2 + 0) * ACT_ROWS + row] = p0;
         mf->part[(hc * 2 + 1) * ACT_ROWS + row] = p1;
         epi_bar();
@@ -362,6 +362,10 @@ __device__ __forceinline__ void run_rollout(const TcArgs& A, uint8_t* smem, Bars
 #pragma unroll
       for (int j = 0; j < NA; ++j) act[j] = 0.f;
       const bool given = (t == 0 && a.use_start_actions);
+      if (ROLE == ROLE_EPI) {
+        if (tile == A.tile0 + (int)blockIdx.x && t == 2) { prof_t = t; stamp(16); }
+        else if (prof_t >= 0) { stamp(22); prof_t = -1; }
+      }
       if (rowthread) {
         if (BWD && valid) {
           float* c = a.ckpt + ((size_t)t * MB + grow) * S;
@@ -373,6 +377,7 @@ __device__ __forceinline__ void run_rollout(const TcArgs& A, uint8_t* smem, Bars
       if (!given) {
         float zpre[NA];
         policy_forward(zpre, false, false, nullptr);
+        stamp(21);
         if (rowthread)
 #pragma unroll
           for (int j = 0; j < NA; ++j) act[j] = head_fwd(zpre[j], a.policy_out_tanh, a.action_range);

@@ -200,7 +200,7 @@ class Engine:
         return grad, ret
 
     # The tensor-core full-BPTT path records 110 KB of dW operands per row: bound it per call.
-    MAX_TC_FULL_BPTT_ROWS = 131072
+    MAX_TC_FULL_BPTT_ROWS = 262144    # 53 KB of dW2 operand records per row at n = 25: 14 GB
 
     def _policy_grad_chunked(self, obs, rollout_list, list_w, M, q_net, policy_net, noise, use_philox, noise_seed,
                              global_rows, row_offset, want_returns):

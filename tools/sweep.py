@@ -49,8 +49,8 @@ if __name__ == '__main__':
         cases += [(env, 'nadp', b) for b in (1024, 16384, 131072, 1048576)]
     for env, mode, B in cases:
         for backend in ('ffma', 'tc'):
-            if backend == 'tc' and mode == 'nadp' and B > 131072:
-                continue  # full-BPTT dW operand store is 110 KB per row: call in <= 128K-row chunks
+            if backend == 'tc' and mode == 'nadp' and B > 262144:
+                continue  # full-BPTT dW2 operand store is 53 KB per row: call in <= 256K-row chunks
             if backend == 'ffma' and B > 262144:
                 continue
             r = run(env, mode, B, backend)

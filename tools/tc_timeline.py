@@ -19,3 +19,5 @@ for full in (1,0):
     print('full_bptt',full)
     for i,n in enumerate(names): print(f'  epi {n:12s} {ep[i]:8d}')
     print('  mma: fwd-start',mm[0],'l1-issued',mm[1],'big-fwd-done-issue',mm[2],'dx-start',mm[3],'dx-issued',mm[4])
+    fw=t[16:23]-t[16]
+    print('  forward step t=2: start 0, p image published', fw[1], 'E1 done', fw[2], 'z2 ready', fw[3], 'E2 done', fw[4], 'zpre', fw[5], 'next step', fw[6])
