@@ -1,14 +1,16 @@
 // Warp-specialised GEMM machinery shared by the tensor-core rollout kernels.
 //
-// Roles inside one CTA (320 threads):
+// Roles inside one CTA (576 threads):
 //   warps 0-15 "epilogue": thread = (TMEM lane = row, 64-column quarter); they build the A-operand images in
 //              shared memory, read accumulators back with tcgen05.ld and run all per-row math;
-//   warp 16    "producer": one elected lane streams weight images from global/L2 into a 2-slot ring with
+//   warp 16    "producer": one elected lane streams weight images from global/L2 into a 4-slot ring with
 //              1-D bulk async copies (TMA engine) completing on mbarriers;
 //   warp 17    "mma": one elected lane issues tcgen05.mma and commits to mbarriers.
 // The three roles execute the SAME schedule (same function, same CTA-uniform control flow) and meet only
-// through mbarriers:  a_full (epilogue -> mma: A image written), d_full (mma -> epilogue: accumulator
-// complete, A image and ring slots free), ring full[]/empty[] (producer <-> mma).
+// through mbarriers:  a_full / a_blk[] (epilogue -> mma: operand image / 64-feature block written), d_full
+// (mma -> epilogue: accumulator complete), z_full[] / z_empty[] (first-layer chunk stream), kb_done[] (K-block of
+// a big GEMM complete: its image block may leave for the record store), acc_done (in-kernel dW1 UMMAs done),
+// ring full[]/empty[] (producer <-> mma).
 #pragma once
 #include "tc_common.cuh"
 
