@@ -196,7 +196,9 @@ int mpg_philox_noise(mpg_ctx* ctx, const mpg_rollout_params* p, float* out, void
 /* Kernel family used by mpg_policy_grad / mpg_rollout_forward:
  *   MPG_BACKEND_FFMA  fp32 CUDA-core contractions (every env / shape this build supports)
  *   MPG_BACKEND_TC    tcgen05 tensor-core contractions with split-bf16 operands (fp32-accurate);
- *                     returns MPG_ERR_UNSUPPORTED for configurations it does not cover */
+ *                     returns MPG_ERR_UNSUPPORTED for configurations it does not cover
+ * mpg_create selects MPG_BACKEND_TC whenever it covers the configuration (obs_dim + act_dim + 1 <= 16), else
+ * MPG_BACKEND_FFMA; the environment variable MPG_B200_BACKEND=ffma forces the fp32 path at creation. */
 enum { MPG_BACKEND_FFMA = 0, MPG_BACKEND_TC = 1 };
 int mpg_set_backend(mpg_ctx* ctx, int backend);
 int mpg_get_backend(const mpg_ctx* ctx);

@@ -399,6 +399,10 @@ int mpg_create(const mpg_config* cfg, mpg_ctx** out) {
     mpg_destroy(c);
     return MPG_ERR_CUDA;
   }
+  // default backend: the tensor-core path wherever it covers the configuration, else fp32 FFMA
+  c->backend = c->tc.ready ? MPG_BACKEND_TC : MPG_BACKEND_FFMA;
+  const char* be = getenv("MPG_B200_BACKEND");
+  if (be && !strcmp(be, "ffma")) c->backend = MPG_BACKEND_FFMA;
   const char* ov = getenv("MPG_TAIL_OVERLAP");
   c->tail_overlap = !(ov && ov[0] == '0');
   *out = c;

@@ -104,10 +104,11 @@ class Engine:
         self._check(self.lib.mpg_set_backend(self.h, int(backend)))
 
     def tc_available(self):
-        rc = self.lib.mpg_set_backend(self.h, BACKEND_TC)
-        if rc == 0:
-            return True
-        return False
+        """True when the tensor-core backend covers this configuration (the current backend is left as it was)."""
+        prev = self.backend
+        ok = self.lib.mpg_set_backend(self.h, BACKEND_TC) == 0
+        self.lib.mpg_set_backend(self.h, prev)
+        return ok
 
     def tc_selftest(self, kind, X, W, repeats=1):
         Z = self.empty(128, 16 if kind == 2 else 256)

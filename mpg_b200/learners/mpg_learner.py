@@ -129,4 +129,5 @@ class MPGLearner(LearnerBase):
         ))
         if v2:
             self.stats.update(dict(q_loss2=np.float32(host[ng + 1] / B), q_gradient_norm2=np.float32(norm_vals[1])))
+        self.flat_grad_device = flat[:ng]     # the same clipped gradients, still on the device (apply_gradients takes it)
         return self._split_to_numpy(host[:ng], ['q'] * nql + ['pi'])

@@ -55,8 +55,12 @@ class SingleProcessOffPolicyOptimizer(object):
         with self.timers['grad_apply_timer']:
             if not all(np.isfinite(g).all() for g in grads):            # judge_is_nan -> zero the gradient (optimizer.py:357-361)
                 grads = [np.zeros_like(g) for g in grads]
+                if getattr(self.learner, 'flat_grad_device', None) is not None:
+                    self.learner.flat_grad_device = None
                 logger.info('Grad is nan!, zero it')
-            self.worker.apply_gradients(self.iteration, grads)
+            # one shared PolicyWithQs: hand over the flat device gradient, no host -> device copy of what just came back
+            dev_grads = getattr(self.learner, 'flat_grad_device', None) if self.shared else None
+            self.worker.apply_gradients(self.iteration, grads if dev_grads is None else dev_grads)
         if self.log_dir and self.iteration % getattr(self.args, 'log_interval', 100) == 0:
             os.makedirs(self.log_dir, exist_ok=True)
             rec = {k: (v if not isinstance(v, (list, np.ndarray)) else [float(x) for x in v]) for k, v in learner_stats.items()}

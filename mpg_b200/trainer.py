@@ -53,9 +53,18 @@ def main():
                         max_buffer_size=500000, replay_starts=3000, buffer_log_interval=10 ** 9, num_eval_agent=64,
                         num_eval_episode=1, fixed_steps=100, eval_interval=max(o.iters // 10, 1), log_interval=100,
                         max_iter=o.iters, log_dir=o.log_dir)
-    hist = Trainer(args).train(o.iters)
+    import time
+    trainer = Trainer(args)
+    t0 = time.perf_counter()
+    hist = trainer.train(o.iters)
+    wall = time.perf_counter() - t0
     for it, m in hist:
         print(json.dumps(dict(iteration=it, **m)))
+    st = trainer.optimizer.get_stats()
+    print(json.dumps(dict(iterations=o.iters, wall_s=wall, ms_per_iteration=1e3 * wall / max(o.iters, 1),
+                          sampling_ms=1e3 * st['sampling_time'], replay_ms=1e3 * st['replay_time'],
+                          learning_ms=1e3 * st['learning_time'], grad_apply_ms=1e3 * st['grad_apply_timer'],
+                          eval_ms=1e3 * trainer.evaluator.get_stats()['eval_time'])))
 
 
 if __name__ == '__main__':

@@ -68,14 +68,14 @@ class OffPolicyWorker(object):
             action, _ = self.policy_with_value.compute_action(processed)
             if self.explore_sigma is not None:
                 action = action + self.explore_sigma * torch.randn(action.shape, device=action.device, generator=self.generator)
-            if not torch.isfinite(action).all():
-                raise ValueError('nan/inf action (judge_is_nan, utils/misc.py:27-36)')
             obs = self.obs
             obs_tp1, reward, done, _ = self.env.step(action)
             for c, v in zip(cols, (obs, action, reward, obs_tp1, done.float())):
                 c.append(v)
             self.obs = self.env.reset_done()
         out = [torch.cat(c, 0) for c in cols]
+        if not torch.isfinite(out[1]).all():          # one host sync per sample() instead of one per env step
+            raise ValueError('nan/inf action (judge_is_nan, utils/misc.py:27-36)')
         self.num_sample += out[0].shape[0]
         self.sample_times += 1
         return out

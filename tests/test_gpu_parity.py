@@ -27,6 +27,8 @@ def _learner(kind, args, weights, backend):
         if not learner.engine.tc_available():
             pytest.skip('tensor-core backend does not cover this configuration')
         learner.engine.set_backend(1)
+    else:
+        learner.engine.set_backend(0)
     return learner
 
 
@@ -222,6 +224,8 @@ def test_closed_loop_trajectories_vs_oracle(env_id, nfd, backend):
         if not e.tc_available():
             pytest.skip('tensor-core backend does not cover this configuration')
         e.set_backend(1)
+    else:
+        e.set_backend(0)
     ret, t_obs, t_rew, t_act = e.rollout_forward(e.dev(obs0), [n], noise=e.dev(noise), want_traj=True)
     ro, rr, ra = O.closed_loop(args, w[1], obs0, noise, n, torch.float64)
     worst = 0.0
@@ -315,6 +319,8 @@ def test_full_size_properties(backend):
         if not e.tc_available():
             pytest.skip('tensor-core backend does not cover this configuration')
         e.set_backend(1)
+    else:
+        e.set_backend(0)
     obs = e.dev(synthetic.make_obs(np.random.default_rng(2), PT, B))
     kw = dict(full_bptt=True, use_philox=True, noise_seed=11)
     g1, r1 = e.policy_grad(obs, [0, n], [0.3, 0.7], **kw)

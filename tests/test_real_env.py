@@ -67,8 +67,7 @@ def test_gpu_mpg_v1_n_step_target(backend):
     _, _, args, w, batch = _case_inputs(case)
     learner = MPGLearner(PolicyWithQs, args)
     learner.set_weights(w)
-    if backend == 'tc':
-        learner.engine.set_backend(1)
+    learner.engine.set_backend(1 if backend == 'tc' else 0)
     learner.get_batch_data(batch, None, None)
     got = learner.batch_data['batch_targets'].cpu().numpy()
     assert rel_l2(got, gold['batch_targets__f32']) <= 2e-5
@@ -78,8 +77,7 @@ def test_gpu_mpg_v1_n_step_target(backend):
     batch2 = make_batch(6, PT, B, 0)
     l2 = MPGLearner(PolicyWithQs, args2)
     l2.set_weights(w2)
-    if backend == 'tc':
-        l2.engine.set_backend(1)
+    l2.engine.set_backend(1 if backend == 'tc' else 0)
     grads = l2.compute_gradient(batch2, None, None, 3000)
     ref, _ = O.mpg_v1_n_step_target(args2, w2, batch2, 25, torch.float64)
     assert rel_l2(l2.batch_data['batch_targets'].cpu().numpy(), ref) <= 2e-5
