@@ -311,7 +311,7 @@ float mpg_kernel_ms(mpg_ctx* ctx) {
 }
 
 int mpg_tc_selftest(mpg_ctx* ctx, int kind, const float* X, const float* W, float* Z, int repeats, void* stream) {
-  if (!ctx || !X || !W || !Z || kind < 0 || kind > 4 || repeats < 1) return fail(ctx, MPG_ERR_ARG, "bad argument to mpg_tc_selftest%s");
+  if (!ctx || !X || !W || !Z || kind < 0 || kind > 5 || repeats < 1) return fail(ctx, MPG_ERR_ARG, "bad argument to mpg_tc_selftest%s");
   CUDA_OK(ctx, tc_selftest(ctx->tc, kind, X, W, Z, repeats, (cudaStream_t)stream));
   ctx->launches += 2;
   return MPG_OK;

@@ -1,6 +1,7 @@
 // Tensor-core (tcgen05) path: state owned by the handle, weight-image packing, launchers.
 #pragma once
 #include "tc_kernels.cuh"
+#include "tc_pair_probe.cuh"
 
 namespace mpg {
 
@@ -49,7 +50,8 @@ inline bool tc_init(TcState& t, const mpg_config& cfg, int /*sms*/, size_t& ws_b
        && tc_set_smem(tc::tc_rollout_kernel<MPG_ENV_INVERTED_DOUBLE_PENDULUM, true>, sm)
        && tc_set_smem(tc::tc_rollout_kernel<MPG_ENV_INVERTED_DOUBLE_PENDULUM, false>, sm)
        && tc_set_smem(tc::tc_rollout_kernel<MPG_ENV_PATH_TRACKING_REAL, false>, sm)
-       && tc_set_smem(tc::tc_dw_kernel, tc::DW_SMEM);
+       && tc_set_smem(tc::tc_dw_kernel, tc::DW_SMEM)
+       && tc_set_smem(tc::pair_probe_kernel, tc::PAIR_SMEM);
   t.ready = ok;
   return ok;
 }
@@ -109,6 +111,14 @@ inline cudaError_t tc_launch_rollout(int env, const tc::TcArgs& a, int grid, cud
 // self test of one GEMM kind (see tc_gemm.cuh): W is fp32 [256 x 256] (kind 0), [16 x 256] (kinds 1, 2)
 inline cudaError_t tc_selftest(TcState& t, int kind, const float* X, const float* W, float* Z, int repeats, cudaStream_t st) {
   if (!t.scratch_img) return cudaErrorNotSupported;
+  if (kind == 5) {   // CTA-pair probe: X is [256 x 256], Z is [256 x 256]; MPG_SELFTEST_GRID CTAs (even), default 2
+    const char* g = getenv("MPG_SELFTEST_GRID");
+    int grid = g ? atoi(g) & ~1 : 2;
+    if (grid < 2) grid = 2;
+    tc::pack_big_image<<<32, 256, 0, st>>>(W, H, 1, t.scratch_img);
+    tc::pair_probe_kernel<<<grid, 192, tc::PAIR_SMEM, st>>>(X, t.scratch_img, Z, repeats);
+    return cudaGetLastError();
+  }
   if (kind >= 3) {   // timing probes (tools/gemm_probe.py): MPG_SELFTEST_GRID CTAs run the big GEMM `repeats` times
     const char* g = getenv("MPG_SELFTEST_GRID");
     tc::selftest_kernel<<<g ? atoi(g) : 1, tc::CTA_THREADS, tc::SmemMap::TOTAL + 1024, st>>>(kind, X, t.scratch_img, Z, repeats);

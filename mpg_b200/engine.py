@@ -111,7 +111,7 @@ class Engine:
         return ok
 
     def tc_selftest(self, kind, X, W, repeats=1):
-        Z = self.empty(128, 16 if kind == 2 else 256)
+        Z = self.empty(256 if kind == 5 else 128, 16 if kind == 2 else 256)
         self._check(self.lib.mpg_tc_selftest(self.h, kind, _ptr(X), _ptr(W), _ptr(Z), repeats, self.stream))
         return Z
 

@@ -33,3 +33,16 @@ def test_tc_gemm_kinds(kind, repeats):
     worst = (Z.cpu().double() - ref).abs().max() / ref.abs().max()
     print(kind, repeats, 'rel-L2', float(err), 'scaled Linf', float(worst))
     assert err < 2e-5 and worst < 1e-4
+
+
+def test_cta_pair_probe_matches_fp64():
+    """cta_group::2 building block (tc_pair_probe.cuh): two CTAs of a cluster, each with 128 rows of A and half of every
+    weight stage, one M = 256 UMMA stream issued by the leader; checked like the single-CTA GEMM."""
+    e = _engine()
+    g = torch.Generator(device='cpu').manual_seed(5)
+    X = torch.randn(256, 256, generator=g); W = torch.randn(256, 256, generator=g) / 16
+    Z = e.tc_selftest(5, e.dev(X), e.dev(W), 1)
+    torch.cuda.synchronize()
+    ref = X.double() @ W.double().T
+    err = (Z.cpu().double() - ref).norm() / ref.norm()
+    assert err < 2e-5
