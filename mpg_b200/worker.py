@@ -2,7 +2,6 @@
 ownership of the master weights / optimiser, here on the GPU (real PathTracking env kernel + policy forward kernel)."""
 import logging
 
-import numpy as np
 import torch
 
 from .envs_and_models import PathTrackingEnv

@@ -11,7 +11,7 @@ import numpy as np
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from mpg_b200 import _lib, synthetic  # noqa: E402
+from mpg_b200 import synthetic  # noqa: E402
 from mpg_b200.config import default_args  # noqa: E402
 from mpg_b200.policy import PolicyWithQs  # noqa: E402
 

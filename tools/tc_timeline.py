@@ -1,6 +1,6 @@
 import sys, ctypes, numpy as np, torch
 sys.path.insert(0,'.')
-from mpg_b200 import synthetic, _lib
+from mpg_b200 import synthetic
 from mpg_b200.config import default_args
 from mpg_b200.policy import PolicyWithQs
 B=65536
