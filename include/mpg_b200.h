@@ -167,6 +167,17 @@ int mpg_model_step(mpg_ctx* ctx, int rows, const float* state_in, const float* a
 int mpg_model_step_bwd(mpg_ctx* ctx, int rows, const float* state_in, const float* action, const float* eps,
                        const float* g_obs_out, const float* g_rew_out, const float* g_state_out, float* g_state_in,
                        float* g_action, void* stream);
+/* Fused exploration sampler: OffPolicyWorker.sample (worker.py:91-119) with the real PathTracking environment
+ * (path_tracking_env.py:356-487) in one launch.  Called on the PathTracking POLICY handle (env MPG_ENV_PATH_TRACKING).
+ * For t < steps:  a = pi(obs_scale * obs) + explore_sigma * explore_noise[t] ;  (obs', r, done) = env.step(a) ;
+ * transition t is written to out_* (row t * agents + agent) ;  agents that are done restart from reset_obs[t]
+ * (env.reset() without init_obs re-draws only the finished agents, path_tracking_env.py:422-454).
+ *   explore_noise (steps, agents, act_dim) standard normal or NULL;  reset_obs (steps, agents, obs_dim);
+ *   state (agents, 8) and obs (agents, obs_dim) are the environment's tensors, updated in place. */
+int mpg_env_sample(mpg_ctx* ctx, int policy_net, int agents, int steps, float explore_sigma, const float* explore_noise,
+                   const float* reset_obs, float* state, float* obs, float* out_obs, float* out_act, float* out_rew,
+                   float* out_obs_tp1, float* out_done, void* stream);
+
 /* VehicleDynamics.compute_rewards(states, scaled actions) / Dynamics.compute_rewards(states) */
 int mpg_compute_rewards(mpg_ctx* ctx, int rows, const float* state, const float* scaled_action, float* rew_out,
                         void* stream);

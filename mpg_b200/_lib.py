@@ -19,7 +19,7 @@ SYMBOLS = [
     'mpg_model_reset', 'mpg_model_step', 'mpg_model_step_bwd', 'mpg_compute_rewards', 'mpg_state_dim',
     'mpg_clip_global_norm', 'mpg_philox_noise', 'mpg_launch_count', 'mpg_set_backend', 'mpg_get_backend',
     'mpg_set_timing', 'mpg_kernel_ms', 'mpg_tc_selftest', 'mpg_set_profile_buffer', 'mpg_adam_step', 'mpg_polyak_update', 'mpg_get_adam_state',
-    'mpg_set_adam_state',
+    'mpg_set_adam_state', 'mpg_env_sample',
     'mpg_replay_create', 'mpg_replay_destroy', 'mpg_replay_last_error', 'mpg_replay_size', 'mpg_replay_add',
     'mpg_replay_sample', 'mpg_replay_update_priorities', 'mpg_replay_tree_stats', 'mpg_q_bootstrap', 'mpg_env_step',
 ]
@@ -93,6 +93,7 @@ def load():
         'mpg_polyak_update': (i32, [vp, i32, i32, f32, vp]),
         'mpg_get_adam_state': (i32, [vp, i32, vp, vp, vp]),
         'mpg_set_adam_state': (i32, [vp, i32, vp, vp, vp]),
+        'mpg_env_sample': (i32, [vp, i32, i32, i32, f32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
         'mpg_q_bootstrap': (i32, [vp, i32, vp, f32, vp, vp, vp]),
         'mpg_env_step': (i32, [vp, i32, vp, vp, vp, vp, vp, vp, vp]),
         'mpg_replay_create': (i32, [i32, i32, i32, ctypes.c_double, ctypes.c_double, P(vp)]),

@@ -387,6 +387,7 @@ int mpg_create(const mpg_config* cfg, mpg_ctx** out) {
   rc |= set_smem(c, rollout_kernel<MPG_ENV_PATH_TRACKING_REAL, false>);
   rc |= set_smem(c, q_grad_kernel);
   rc |= set_smem(c, eval_kernel);
+  rc |= set_smem(c, env_sample_kernel);
   if (rc) {
     strncpy(g_create_err, c->err, 512);
     mpg_destroy(c);
@@ -867,6 +868,31 @@ int mpg_env_step(mpg_ctx* ctx, int rows, const float* state_in, const float* act
   if (ctx->cfg.env != MPG_ENV_PATH_TRACKING_REAL) return fail(ctx, MPG_ERR_STATE, "mpg_env_step needs a handle created with MPG_ENV_PATH_TRACKING_REAL%s");
   env_step_kernel<<<(rows + 127) / 128, 128, 0, (cudaStream_t)stream>>>(rows, ctx->cfg.obs_dim, ctx->cfg.num_future_data, state_in,
                                                                         action, state_out, obs_out, rew_out, done_out);
+  ctx->launches++;
+  CUDA_OK(ctx, cudaGetLastError());
+  return MPG_OK;
+}
+
+int mpg_env_sample(mpg_ctx* ctx, int policy_net, int agents, int steps, float explore_sigma, const float* explore_noise,
+                   const float* reset_obs, float* state, float* obs, float* out_obs, float* out_act, float* out_rew,
+                   float* out_obs_tp1, float* out_done, void* stream) {
+  if (!ctx || !reset_obs || !state || !obs || !out_obs || !out_act || !out_rew || !out_obs_tp1 || !out_done || agents <= 0
+      || steps <= 0)
+    return fail(ctx, MPG_ERR_ARG, "bad argument to mpg_env_sample%s");
+  if (ctx->cfg.env != MPG_ENV_PATH_TRACKING)
+    return fail(ctx, MPG_ERR_UNSUPPORTED, "mpg_env_sample: the fused sampler is built for the PathTracking policy handle%s");
+  int rc = check_net(ctx, policy_net);
+  if (rc) return rc;
+  SampleArgs a;
+  memset(&a, 0, sizeof(a));
+  a.agents = agents; a.steps = steps; a.obs_dim = ctx->cfg.obs_dim; a.act_dim = ctx->cfg.act_dim;
+  a.nfd = ctx->cfg.num_future_data; a.policy_out_tanh = ctx->cfg.policy_out_tanh; a.action_range = ctx->cfg.action_range;
+  a.sigma = explore_sigma;
+  for (int i = 0; i < MPG_MAX_OBS; ++i) a.obs_scale[i] = ctx->cfg.obs_scale[i];
+  a.explore_noise = explore_noise; a.reset_obs = reset_obs; a.state = state; a.obs = obs;
+  a.out_obs = out_obs; a.out_act = out_act; a.out_rew = out_rew; a.out_obs_tp1 = out_obs_tp1; a.out_done = out_done;
+  a.net = net_dev(ctx, policy_net);
+  env_sample_kernel<<<(agents + TILE_R - 1) / TILE_R, NT, Smem::FLOATS * 4, (cudaStream_t)stream>>>(a);
   ctx->launches++;
   CUDA_OK(ctx, cudaGetLastError());
   return MPG_OK;

@@ -368,6 +368,72 @@ __global__ void __launch_bounds__(NT, 1) eval_kernel(const __grid_constant__ Eva
 }
 
 // ---------------------------------------------------------------------------------------------
+// Fused exploration sampler (OffPolicyWorker.sample, worker.py:91-119, with the real PathTracking environment):
+// `steps` iterations of  a = pi(sigma obs) + explore_sigma eps ; (obs', r, done) = env.step(a) ; record the
+// transition ; re-draw the agents that are done  -- in ONE launch, one 64-agent tile per CTA, the environment state
+// in the registers of the thread that owns the agent.  eps and the reset observations are drawn by the caller, so
+// the step-by-step path (mpg_policy_forward + mpg_env_step per step) gives the same numbers.
+// ---------------------------------------------------------------------------------------------
+struct SampleArgs {
+  int agents, steps, obs_dim, act_dim, nfd, policy_out_tanh;
+  float action_range, sigma;
+  float obs_scale[MPG_MAX_OBS];
+  const float* explore_noise;   // (steps, agents, act_dim) standard normal, or nullptr
+  const float* reset_obs;       // (steps, agents, obs_dim): observation an agent restarts from when done at that step
+  float* state;                 // (agents, 8)        in/out
+  float* obs;                   // (agents, obs_dim)  in/out
+  float *out_obs, *out_act, *out_rew, *out_obs_tp1, *out_done;   // (steps, agents, ...)
+  NetDev net;
+};
+
+__global__ void __launch_bounds__(NT, 1) env_sample_kernel(const __grid_constant__ SampleArgs a) {
+  using E = Env<MPG_ENV_PT_REAL>;
+  extern __shared__ float4 smem_raw[];
+  Smem sm(reinterpret_cast<float*>(smem_raw));
+  const int tid = threadIdx.x, row = blockIdx.x * TILE_R + tid;
+  const bool rt = tid < TILE_R, valid = rt && row < a.agents;
+  float s[E::S], o[MPG_MAX_OBS];
+#pragma unroll
+  for (int j = 0; j < E::S; ++j) s[j] = valid ? a.state[(size_t)row * E::S + j] : 0.f;
+  for (int i = 0; i < a.obs_dim; ++i) o[i] = valid ? a.obs[(size_t)row * a.obs_dim + i] : 0.f;
+  for (int t = 0; t < a.steps; ++t) {
+    if (rt)
+      for (int i = 0; i < a.obs_dim; ++i) sm.xin[i * RP + tid] = o[i] * a.obs_scale[i];
+    __syncthreads();
+    mlp_forward_tile(a.net, sm, a.act_dim);
+    if (valid) {
+      const size_t tr = (size_t)t * a.agents + row;
+      float act[E::A], o1[MPG_MAX_OBS];
+#pragma unroll
+      for (int j = 0; j < E::A; ++j) {
+        act[j] = head_fwd(sm.y3[j * RP + tid], a.policy_out_tanh, a.action_range);
+        if (a.explore_noise) act[j] += a.sigma * a.explore_noise[tr * E::A + j];
+        a.out_act[tr * E::A + j] = act[j];
+      }
+      for (int i = 0; i < a.obs_dim; ++i) a.out_obs[tr * a.obs_dim + i] = o[i];
+      int done = 0;
+      const float rew = E::step_done(s, act, &done);
+      E::get_obs(s, o1, a.nfd);
+      a.out_rew[tr] = rew;
+      a.out_done[tr] = (float)done;
+      for (int i = 0; i < a.obs_dim; ++i) a.out_obs_tp1[tr * a.obs_dim + i] = o1[i];
+      if (done) {                                   // env.reset(): only the finished agents restart
+        for (int i = 0; i < a.obs_dim; ++i) o[i] = a.reset_obs[tr * a.obs_dim + i];
+        E::reset(o, s);
+      } else {
+        for (int i = 0; i < a.obs_dim; ++i) o[i] = o1[i];
+      }
+    }
+    __syncthreads();
+  }
+  if (valid) {
+#pragma unroll
+    for (int j = 0; j < E::S; ++j) a.state[(size_t)row * E::S + j] = s[j];
+    for (int i = 0; i < a.obs_dim; ++i) a.obs[(size_t)row * a.obs_dim + i] = o[i];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // single model step (backs <Env>Model.rollout_out / reset / compute_rewards and their autograd)
 // ---------------------------------------------------------------------------------------------
 template <int ENV>

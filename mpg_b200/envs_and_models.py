@@ -151,15 +151,16 @@ class PathTrackingEnv(object):
         self.state, self.obs, reward, self.done = self.engine.env_step(self.state, self.action)
         return self.obs, reward, self.done, {}
 
-    def _draw_on_device(self):
-        """The reset law of path_tracking_env.py:426-437 drawn with a device generator (no host round trip):
-        x ~ U(0,600), dy ~ N(0,1), dphi ~ N(0,pi/9), v_x ~ U(15,25), beta ~ N(0,0.15), v_y = v_x tan(beta), r ~ N(0,0.3)."""
+    def _draw_on_device(self, sets=1):
+        """`sets` x num_agent observations from the reset law of path_tracking_env.py:426-437, drawn with a device
+        generator (no host round trip): x ~ U(0,600), dy ~ N(0,1), dphi ~ N(0,pi/9), v_x ~ U(15,25), beta ~ N(0,0.15),
+        v_y = v_x tan(beta), r ~ N(0,0.3)."""
         import math
         import torch
         if self._gen is None:
             self._gen = torch.Generator(device=self.engine.device)
             self._gen.manual_seed(int(self._rng.integers(1 << 31)))
-        n, g, dev = self.num_agent, self._gen, self.engine.device
+        n, g, dev = self.num_agent * sets, self._gen, self.engine.device
         u = torch.rand(2, n, device=dev, generator=g)
         z = torch.randn(4, n, device=dev, generator=g)
         vx = 15.0 + 10.0 * u[1]
@@ -167,13 +168,15 @@ class PathTrackingEnv(object):
         cols = [vx - 20.0, vx * torch.tan(0.15 * z[2]), 0.3 * z[3], dy, (math.pi / 9) * z[1], 600.0 * u[0]]
         return torch.stack(cols + [dy] * self.num_future_data, 1).contiguous()
 
-    def reset_done(self):
+    def reset_done(self, fresh=None):
         """reset() of the reference without init_obs (path_tracking_env.py:422-454): agents whose `done` flag is set
-        are re-drawn from the reset law, the others keep their state.  Everything stays on the device."""
+        are re-drawn from the reset law (or take the rows of `fresh`), the others keep their state.  Everything stays
+        on the device."""
         import torch
         if self.done is None:
             return self.reset()
-        fresh = self._draw_on_device()
+        if fresh is None:
+            fresh = self._draw_on_device()
         fresh_state = self.engine.model_reset(fresh)
         m = (self.done != 0).unsqueeze(1)
         self.state = torch.where(m, fresh_state, self.state)

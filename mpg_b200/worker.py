@@ -59,20 +59,33 @@ class OffPolicyWorker(object):
     def set_ppc_params(self, params):
         self.preprocessor.set_params(params)
 
-    def sample_arrays(self):
-        """worker.py:91-119 on device tensors: -> (obs, act, rew, obs_tp1, done), each batch_size rows."""
-        cols = [[] for _ in range(5)]
-        for _ in range(int(self.batch_size / self.num_agent)):
-            processed = self.preprocessor.torch_process_obses(self.obs)
-            action, _ = self.policy_with_value.compute_action(processed)
-            if self.explore_sigma is not None:
-                action = action + self.explore_sigma * torch.randn(action.shape, device=action.device, generator=self.generator)
-            obs = self.obs
-            obs_tp1, reward, done, _ = self.env.step(action)
-            for c, v in zip(cols, (obs, action, reward, obs_tp1, done.float())):
-                c.append(v)
-            self.obs = self.env.reset_done()
-        out = [torch.cat(c, 0) for c in cols]
+    def sample_arrays(self, fused=True):
+        """worker.py:91-119 on device tensors: -> (obs, act, rew, obs_tp1, done), each batch_size rows.
+        The exploration noise and the reset observations of all steps are drawn up front; `fused` runs the whole
+        loop as one kernel (mpg_env_sample), otherwise step by step through the same kernels a gym-style caller uses
+        (identical numbers, tests/test_trainer.py)."""
+        steps, n = int(self.batch_size / self.num_agent), self.num_agent
+        act_dim, dev = self.args.act_dim, self.env.engine.device
+        eps = torch.randn(steps, n, act_dim, device=dev, generator=self.generator) if self.explore_sigma is not None else None
+        fresh = self.env._draw_on_device(steps).view(steps, n, -1)
+        if fused:
+            out = self.policy_with_value.engine.env_sample(self.env.state, self.env.obs, fresh, eps,
+                                                           self.explore_sigma or 0.0)
+            self.obs = self.env.obs
+            self.env.done = torch.zeros(n, dtype=torch.int32, device=dev)   # every finished agent has been restarted
+        else:
+            cols = [[] for _ in range(5)]
+            for t in range(steps):
+                processed = self.preprocessor.torch_process_obses(self.obs)
+                action, _ = self.policy_with_value.compute_action(processed)
+                if eps is not None:
+                    action = action + self.explore_sigma * eps[t]
+                obs = self.obs
+                obs_tp1, reward, done, _ = self.env.step(action)
+                for c, v in zip(cols, (obs, action, reward, obs_tp1, done.float())):
+                    c.append(v)
+                self.obs = self.env.reset_done(fresh[t])
+            out = [torch.cat(c, 0) for c in cols]
         if not torch.isfinite(out[1]).all():          # one host sync per sample() instead of one per env step
             raise ValueError('nan/inf action (judge_is_nan, utils/misc.py:27-36)')
         self.num_sample += out[0].shape[0]

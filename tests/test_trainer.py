@@ -69,3 +69,23 @@ def test_checkpoint_round_trip_resumes_bit_exactly(tmp_path):
     for wa, wb in zip(a.get_weights(), b.get_weights()):
         for x, y in zip(wa, wb):
             assert np.array_equal(x, y)
+
+
+@pytest.mark.parametrize('sigma', [0.3, 0.0])
+def test_fused_sampler_matches_step_by_step(sigma):
+    """mpg_env_sample (one launch for the whole sample() loop) against the step-by-step path through
+    mpg_policy_forward + mpg_env_step + reset of done agents, same pre-drawn exploration noise and reset states.
+    The two paths run the same device functions in different kernels (FMA contraction may differ by an ulp), so
+    values are compared to 1e-5 relative and the done flags / restart pattern exactly."""
+    from mpg_b200.policy import PolicyWithQs
+    from mpg_b200.worker import OffPolicyWorker
+    args = _args('MPG-v2', num_agent=70, batch_size=70 * 40, explore_sigma=sigma)
+    outs = []
+    for fused in (True, False):
+        w = OffPolicyWorker(PolicyWithQs, args.env_id, args, 0)
+        outs.append([t.cpu().numpy() for t in w.sample_arrays(fused=fused)] + [w.env.state.cpu().numpy(), w.obs.cpu().numpy()])
+    assert outs[0][4].sum() > 0, 'the case must contain finished agents (reset path)'
+    assert np.array_equal(outs[0][4], outs[1][4])
+    for a, b in zip(*outs):
+        assert a.shape == b.shape
+        assert np.abs(a - b).max() <= 1e-5 * max(np.abs(b).max(), 1.0)
