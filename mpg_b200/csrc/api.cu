@@ -777,6 +777,29 @@ int mpg_q_forward(mpg_ctx* ctx, int net, int rows, const float* obs, const float
   return launch_eval(ctx, a, stream);
 }
 
+// ---- tensor-core evaluation of Q(sigma obs, a), a = given actions or pi(sigma obs): the forward rollout kernel with
+// horizon 0 (one policy forward + one Q forward per row) -- 0.07 ms per 65,536 rows instead of 0.4 ms per MLP on the
+// FFMA tile engine.  Used by the target / TD-error / bootstrap entry points when the handle runs the TC backend.
+__global__ void affine_q_kernel(int n, const float* __restrict__ base, float shift, float scale, float coef,
+                                const float* __restrict__ q1, const float* __restrict__ q2, const float* __restrict__ sub,
+                                float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float q = q2 ? fminf(q1[i], q2[i]) : q1[i];
+  out[i] = (base[i] + shift) * scale + coef * q - (sub ? sub[i] : 0.f);
+}
+static bool tc_eval_ok(const mpg_ctx* ctx, int rows) {
+  return ctx->backend == MPG_BACKEND_TC && ctx->tc.ready && rows <= ctx->cfg.max_rows;
+}
+static int tc_q_eval(mpg_ctx* ctx, int q_net, int policy_net, int rows, const float* obs, const float* actions, float* out,
+                     void* stream) {
+  mpg_rollout_params p;
+  memset(&p, 0, sizeof(p));
+  p.rows = rows; p.M = 1; p.horizon = 0; p.n_list = 1; p.list[0] = 0; p.list_w[0] = 1.f;
+  p.q_net = q_net; p.policy_net = policy_net;
+  return mpg_rollout_forward(ctx, &p, obs, actions, nullptr, out, nullptr, nullptr, nullptr, stream);
+}
+
 int mpg_q_target(mpg_ctx* ctx, int double_q, int rows, const float* rew, const float* obs_tp1, float* target_out,
                  void* stream) {
   if (!ctx || !rew || !obs_tp1 || !target_out || rows <= 0) return fail(ctx, MPG_ERR_ARG, "bad argument to mpg_q_target%s");
@@ -784,6 +807,17 @@ int mpg_q_target(mpg_ctx* ctx, int double_q, int rows, const float* rew, const f
   if (!rc) rc = check_net(ctx, MPG_NET_Q1_TARGET);
   if (!rc && double_q) rc = check_net(ctx, MPG_NET_Q2_TARGET);
   if (rc) return rc;
+  if (tc_eval_ok(ctx, rows)) {
+    const mpg_config& c = ctx->cfg;
+    rc = tc_q_eval(ctx, MPG_NET_Q1_TARGET, MPG_NET_POLICY_TARGET, rows, obs_tp1, nullptr, ctx->tc.qtmp, stream);
+    if (!rc && double_q) rc = tc_q_eval(ctx, MPG_NET_Q2_TARGET, MPG_NET_POLICY_TARGET, rows, obs_tp1, nullptr, ctx->tc.qtmp2, stream);
+    if (rc) return rc;
+    affine_q_kernel<<<(rows + 255) / 256, 256, 0, (cudaStream_t)stream>>>(rows, rew, c.rew_shift, c.rew_scale, c.gamma, ctx->tc.qtmp,
+                                                                         double_q ? ctx->tc.qtmp2 : nullptr, nullptr, target_out);
+    ctx->launches++;
+    CUDA_OK(ctx, cudaGetLastError());
+    return MPG_OK;
+  }
   EvalArgs a;
   memset(&a, 0, sizeof(a));
   a.mode = 2; a.rows = rows; a.obs = obs_tp1; a.rew = rew; a.out = target_out; a.n_q = double_q ? 2 : 1;
@@ -797,6 +831,14 @@ int mpg_q_bootstrap(mpg_ctx* ctx, int rows, const float* base, float coef, const
   int rc = check_net(ctx, MPG_NET_POLICY_TARGET);
   if (!rc) rc = check_net(ctx, MPG_NET_Q1_TARGET);
   if (rc) return rc;
+  if (tc_eval_ok(ctx, rows)) {
+    rc = tc_q_eval(ctx, MPG_NET_Q1_TARGET, MPG_NET_POLICY_TARGET, rows, obs, nullptr, ctx->tc.qtmp, stream);
+    if (rc) return rc;
+    affine_q_kernel<<<(rows + 255) / 256, 256, 0, (cudaStream_t)stream>>>(rows, base, 0.f, 1.f, coef, ctx->tc.qtmp, nullptr, nullptr, out);
+    ctx->launches++;
+    CUDA_OK(ctx, cudaGetLastError());
+    return MPG_OK;
+  }
   EvalArgs a;
   memset(&a, 0, sizeof(a));
   a.mode = 4; a.rows = rows; a.obs = obs; a.rew = base; a.out = out; a.gamma = coef;
@@ -812,6 +854,17 @@ int mpg_td_error(mpg_ctx* ctx, int rows, const float* obs, const float* act, con
   if (!rc) rc = check_net(ctx, MPG_NET_Q1_TARGET);
   if (!rc) rc = check_net(ctx, MPG_NET_Q1);
   if (rc) return rc;
+  if (tc_eval_ok(ctx, rows)) {
+    const mpg_config& c = ctx->cfg;
+    rc = tc_q_eval(ctx, MPG_NET_Q1_TARGET, MPG_NET_POLICY_TARGET, rows, obs_tp1, nullptr, ctx->tc.qtmp, stream);
+    if (!rc) rc = tc_q_eval(ctx, MPG_NET_Q1, MPG_NET_POLICY, rows, obs, act, ctx->tc.qtmp2, stream);
+    if (rc) return rc;
+    affine_q_kernel<<<(rows + 255) / 256, 256, 0, (cudaStream_t)stream>>>(rows, rew, c.rew_shift, c.rew_scale, c.gamma, ctx->tc.qtmp,
+                                                                         nullptr, ctx->tc.qtmp2, td_out);
+    ctx->launches++;
+    CUDA_OK(ctx, cudaGetLastError());
+    return MPG_OK;
+  }
   EvalArgs a;
   memset(&a, 0, sizeof(a));
   a.mode = 3; a.rows = rows; a.obs = obs; a.obs2 = obs_tp1; a.act = act; a.rew = rew; a.out = td_out;

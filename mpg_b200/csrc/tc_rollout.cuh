@@ -17,7 +17,8 @@ struct TcState {
   TcNetImages nets[MPG_NUM_NETS];
   uint8_t* scratch_img = nullptr;   // self-test image
   float* act_ckpt = nullptr;        // [MPG_MAX_LIST][max_rows][MAX_A]
-  float* qtmp = nullptr;            // [max_rows] Q values of the regression pass
+  float* qtmp = nullptr;            // [max_rows] Q values of the regression pass / of the target evaluations
+  float* qtmp2 = nullptr;           // [max_rows] second Q value (double-Q minimum, TD error)
   uint8_t* store = nullptr;         // dW operand store (allocated on first use, grows)
   size_t store_bytes = 0;
 };
@@ -36,7 +37,8 @@ inline bool tc_init(TcState& t, const mpg_config& cfg, int /*sms*/, size_t& ws_b
   };
   bool ok = alloc((void**)&t.scratch_img, tc::BIG_IMAGE_BYTES)
             && alloc((void**)&t.act_ckpt, (size_t)MPG_MAX_LIST * cfg.max_rows * MAX_A * sizeof(float))
-            && alloc((void**)&t.qtmp, (size_t)cfg.max_rows * sizeof(float));
+            && alloc((void**)&t.qtmp, (size_t)cfg.max_rows * sizeof(float))
+            && alloc((void**)&t.qtmp2, (size_t)cfg.max_rows * sizeof(float));
   for (int n = 0; n < MPG_NUM_NETS && ok; ++n)
     ok = alloc((void**)&t.nets[n].big_fwd, tc::BIG_IMAGE_BYTES) && alloc((void**)&t.nets[n].big_dx, tc::BIG_IMAGE_BYTES)
          && alloc((void**)&t.nets[n].l1, 16384) && alloc((void**)&t.nets[n].in, 16384);
@@ -57,7 +59,7 @@ inline bool tc_init(TcState& t, const mpg_config& cfg, int /*sms*/, size_t& ws_b
 }
 
 inline void tc_destroy(TcState& t) {
-  cudaFree(t.scratch_img); cudaFree(t.act_ckpt); cudaFree(t.qtmp); cudaFree(t.store);
+  cudaFree(t.scratch_img); cudaFree(t.act_ckpt); cudaFree(t.qtmp); cudaFree(t.qtmp2); cudaFree(t.store);
   for (int n = 0; n < MPG_NUM_NETS; ++n) {
     cudaFree(t.nets[n].big_fwd); cudaFree(t.nets[n].big_dx); cudaFree(t.nets[n].l1); cudaFree(t.nets[n].in);
   }
