@@ -25,6 +25,18 @@ def rule_based_weights(ite, total_ite, eta, rollout_list):
     return (e / e.sum(dtype=f)).astype(f)
 
 
+class _LazyDev(dict):
+    """Device copies of the batch; a key whose upload was deferred is uploaded on first access."""
+
+    def __init__(self, owner):
+        super().__init__()
+        self._owner = owner
+
+    def __missing__(self, k):
+        self._owner._finish_upload(consumer_waits=True)
+        return dict.__getitem__(self, k)
+
+
 class LearnerBase(object):
     """What MPGLearner and NADPLearner share (mpg_learner.py:30-64,171-178; nadp.py:29-53,78-85)."""
 
@@ -52,6 +64,7 @@ class LearnerBase(object):
         self.noise_seed = int(getattr(self.args, 'noise_seed', 7))
         self._noise_q = self._noise_p = None
         self._dev, self._pinned, self.h2d_bytes = {}, {}, 0
+        self._pending, self._copy_stream, self._copy_pending = [], None, False
         # data parallel: each rank holds a contiguous shard of the global batch
         self.world_size, self.rank = parallel.dist_info()
 
@@ -85,18 +98,42 @@ class LearnerBase(object):
             self.batch_data = {k: v for k, v in zip(names, batch_data)}
             self._dev = {k: self.engine.dev(v) for k, v in self.batch_data.items() if k != 'batch_dones'}
             self.h2d_bytes = 0
+            self._pending = []
             return
         self.batch_data = {k: np.asarray(v, dtype=np.float32) for k, v in zip(names, batch_data)}   # mpg_learner.py:66-72
-        self._dev = {}
-        for k, v in self.batch_data.items():
-            if k == 'batch_dones':  # ignored by every learner (mpg_learner.py:71)
-                continue
-            pin = self._pinned.get(k)
-            if pin is None or pin.shape != v.shape:
-                pin = self._pinned[k] = torch.empty(v.shape, dtype=torch.float32, pin_memory=True)
-            pin.numpy()[...] = v
-            self._dev[k] = pin.to(self.engine.device, non_blocking=True)
-        self.h2d_bytes = sum(t.numel() * 4 for t in self._dev.values())
+        # obs and actions feed the first kernels: staged and enqueued now.  rewards / obs_tp1 are needed later (targets,
+        # TD errors) or not at all (NADP with a uniform buffer): their staging copy and H2D transfer run on a side
+        # stream while the GPU is already busy -- on first use, at the latest before compute_gradient returns.
+        self._dev = _LazyDev(self)
+        self._pending = [k for k in ('batch_rewards', 'batch_obs_tp1')]
+        for k in ('batch_obs', 'batch_actions'):
+            self._dev[k] = self._stage(k).to(self.engine.device, non_blocking=True)
+        self.h2d_bytes = sum(v.size * 4 for k, v in self.batch_data.items() if k != 'batch_dones')   # batch_dones: ignored (mpg_learner.py:71)
+
+    def _stage(self, k):
+        v = self.batch_data[k]
+        pin = self._pinned.get(k)
+        if pin is None or pin.shape != v.shape:
+            pin = self._pinned[k] = torch.empty(v.shape, dtype=torch.float32, pin_memory=True)
+        pin.numpy()[...] = v
+        return pin
+
+    def _finish_upload(self, consumer_waits=True):
+        """Upload what _upload_batch deferred.  consumer_waits: the current stream is about to read the tensors."""
+        pending = getattr(self, '_pending', None)
+        if pending:
+            self._pending = []
+            if self._copy_stream is None:
+                self._copy_stream = torch.cuda.Stream(device=self.engine.device)
+            with torch.cuda.stream(self._copy_stream):
+                for k in pending:
+                    dict.__setitem__(self._dev, k, self._stage(k).to(self.engine.device, non_blocking=True))
+            self._copy_pending = True
+        if consumer_waits and getattr(self, '_copy_pending', False):
+            torch.cuda.current_stream(self.engine.device).wait_stream(self._copy_stream)
+            for k in ('batch_rewards', 'batch_obs_tp1'):
+                self._dev[k].record_stream(torch.cuda.current_stream(self.engine.device))
+            self._copy_pending = False
 
     @property
     def global_rows(self):

@@ -102,6 +102,7 @@ class MPGLearner(LearnerBase):
             norms.append(e.clip_global_norm(flat[pos:pos + n], clip))
             pos += n
         ng = pos
+        self._finish_upload()
         host = torch.cat([flat] + norms).cpu().numpy()
         B = float(self.global_rows)
         nql = len(q_res)

@@ -76,6 +76,7 @@ class NADPLearner(LearnerBase):
         self._allreduce(flat)
         q_norm = e.clip_global_norm(flat[:nq], clip)
         p_norm = e.clip_global_norm(flat[nq:nq + p_grad.numel()], clip)
+        self._finish_upload()                                     # deferred H2D (rewards / obs_tp1) has overlapped the kernels
         host = torch.cat([flat, q_norm, p_norm]).cpu().numpy()   # the only device->host copy of the update
         ng = nq + p_grad.numel()
         B = float(self.global_rows)
