@@ -75,7 +75,8 @@ class Engine:
         if rows <= self.cfg.max_rows and horizon <= self.cfg.max_horizon:
             return
         backend = self.backend
-        saved = {net: self.get_net_weights(net) for net in self._weights}   # Adam moments are reset by a re-create
+        saved = {net: self.get_net_weights(net) for net in self._weights}
+        moments = {net: self.get_adam_state(net) for net in self._weights}   # the optimiser state moves to the new handle
         self.close()
         self.cfg.max_rows = max(int(rows), self.cfg.max_rows)
         self.cfg.max_horizon = max(int(horizon), self.cfg.max_horizon)
@@ -85,8 +86,10 @@ class Engine:
             raise RuntimeError('mpg_create failed: ' + self.lib.mpg_last_error(None).decode())
         for net, w in saved.items():
             self.set_net_weights(net, w)
-        if backend != BACKEND_FFMA:
-            self.set_backend(backend)
+            m, v = moments[net]
+            if m.any() or v.any():
+                self.set_adam_state(net, m, v)
+        self.set_backend(backend)
 
     def _check(self, rc):
         if rc != 0:

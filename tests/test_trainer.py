@@ -89,3 +89,19 @@ def test_fused_sampler_matches_step_by_step(sigma):
     for a, b in zip(*outs):
         assert a.shape == b.shape
         assert np.abs(a - b).max() <= 1e-5 * max(np.abs(b).max(), 1.0)
+
+
+def test_capacity_growth_keeps_weights_and_optimizer_state():
+    """Engine.ensure_capacity re-creates the handle for a bigger batch; weights AND Adam moments must move over."""
+    from mpg_b200.policy import PolicyWithQs
+    args = _args('NADP', replay_batch_size=64)
+    rng = np.random.default_rng(1)
+    a, b = PolicyWithQs(**vars(args)), PolicyWithQs(**vars(args))
+    n = sum(a.engine.param_count(s) for s in a.model_slots)
+    g0, g1 = [rng.standard_normal(n).astype(np.float32) for _ in range(2)]
+    a.apply_gradients(0, [g0]); b.apply_gradients(0, [g0])
+    a.engine.ensure_capacity(5000, 30)                # grows: new handle
+    a.apply_gradients(1, [g1]); b.apply_gradients(1, [g1])
+    for wa, wb in zip(a.get_weights(), b.get_weights()):
+        for x, y in zip(wa, wb):
+            assert np.array_equal(x, y)
