@@ -147,6 +147,14 @@ def test_nadp_pathtracking_vs_oracle(B, n, M, nfd, backend):
     _nadp_vs_oracle(PT, B, n, M, nfd, backend, buffer_type='priority' if B == 48 else 'normal', tol_scalar=tol_scalar)
 
 
+def test_tc_multi_tile_and_tail_split_vs_oracle():
+    """More tiles than SMs (several tiles per CTA + the full-waves / tail-wave split with the side-stream weight
+    gradient GEMMs) against the fp64 oracle, not only against itself: 20,011 rows = 157 tiles."""
+    # scalar tolerance 1e-4: the means over 20,011 returns are small numbers (n = 3) carrying the ~1e-5 per-row error
+    learner = _nadp_vs_oracle(PT, 20011, 3, 1, 0, 'tc', seed=9, tol_scalar=1e-4)
+    assert learner.engine.num_sms < 157, 'the case is meant to exceed one wave'
+
+
 @pytest.mark.parametrize('backend', BACKENDS)
 def test_nadp_inverted_pendulum_vs_oracle(backend):
     _nadp_vs_oracle(IP, 200, 25, 1, 0, backend)
