@@ -60,3 +60,20 @@ def test_host_rule_based_weights_match_reference():
         for i, ite in enumerate(case['iterations']):
             w = rule_based_weights(ite, 9000, 0.1, case['rollout_list'])
             assert np.allclose(w, gold['ws__f32'][i], rtol=2e-5, atol=1e-9), (name, ite, w, gold['ws__f32'][i])
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason='checks the no-GPU behaviour')
+def test_trainer_stack_imports_and_fails_loudly_without_gpu():
+    """The callers either side of the path (worker / optimizer / evaluator / trainer / buffer) import on a CPU-only
+    box and refuse to run there instead of silently falling back."""
+    import mpg_b200.buffer  # noqa: F401
+    import mpg_b200.evaluator  # noqa: F401
+    import mpg_b200.optimizer  # noqa: F401
+    import mpg_b200.worker  # noqa: F401
+    from mpg_b200.config import default_args
+    from mpg_b200.trainer import Trainer
+    args = default_args('MPG-v2', 'PathTracking-v0', batch_size=64, num_agent=8, explore_sigma=0.1, max_buffer_size=1000,
+                        replay_starts=64, buffer_log_interval=10 ** 9, num_eval_agent=8, num_eval_episode=1,
+                        fixed_steps=5, eval_interval=10 ** 9, log_interval=10 ** 9, max_iter=1, log_dir=None)
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        Trainer(args)
