@@ -172,7 +172,8 @@ int mpg_model_step_bwd(mpg_ctx* ctx, int rows, const float* state_in, const floa
  * For t < steps:  a = pi(obs_scale * obs) + explore_sigma * explore_noise[t] ;  (obs', r, done) = env.step(a) ;
  * transition t is written to out_* (row t * agents + agent) ;  agents that are done restart from reset_obs[t]
  * (env.reset() without init_obs re-draws only the finished agents, path_tracking_env.py:422-454).
- *   explore_noise (steps, agents, act_dim) standard normal or NULL;  reset_obs (steps, agents, obs_dim);
+ *   explore_noise (steps, agents, act_dim) standard normal or NULL;  reset_obs (steps, agents, obs_dim), or NULL:
+ *   nobody restarts (the evaluator's fixed-step episodes, evaluator.py run_an_episode with fixed_steps);
  *   state (agents, 8) and obs (agents, obs_dim) are the environment's tensors, updated in place. */
 int mpg_env_sample(mpg_ctx* ctx, int policy_net, int agents, int steps, float explore_sigma, const float* explore_noise,
                    const float* reset_obs, float* state, float* obs, float* out_obs, float* out_act, float* out_rew,

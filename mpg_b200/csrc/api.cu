@@ -757,26 +757,6 @@ static int launch_eval(mpg_ctx* ctx, EvalArgs& a, void* stream) {
   return MPG_OK;
 }
 
-int mpg_policy_forward(mpg_ctx* ctx, int net, int rows, const float* obs, float* act_out, void* stream) {
-  if (!ctx || !obs || !act_out || rows <= 0) return fail(ctx, MPG_ERR_ARG, "bad argument to mpg_policy_forward%s");
-  int rc = check_net(ctx, net);
-  if (rc) return rc;
-  EvalArgs a;
-  memset(&a, 0, sizeof(a));
-  a.mode = 0; a.rows = rows; a.obs = obs; a.out = act_out; a.net0 = net_dev(ctx, net);
-  return launch_eval(ctx, a, stream);
-}
-
-int mpg_q_forward(mpg_ctx* ctx, int net, int rows, const float* obs, const float* act, float* q_out, void* stream) {
-  if (!ctx || !obs || !act || !q_out || rows <= 0) return fail(ctx, MPG_ERR_ARG, "bad argument to mpg_q_forward%s");
-  int rc = check_net(ctx, net);
-  if (rc) return rc;
-  EvalArgs a;
-  memset(&a, 0, sizeof(a));
-  a.mode = 1; a.rows = rows; a.obs = obs; a.act = act; a.out = q_out; a.net0 = net_dev(ctx, net);
-  return launch_eval(ctx, a, stream);
-}
-
 // ---- tensor-core evaluation of Q(sigma obs, a), a = given actions or pi(sigma obs): the forward rollout kernel with
 // horizon 0 (one policy forward + one Q forward per row) -- 0.07 ms per 65,536 rows instead of 0.4 ms per MLP on the
 // FFMA tile engine.  Used by the target / TD-error / bootstrap entry points when the handle runs the TC backend.
@@ -798,6 +778,35 @@ static int tc_q_eval(mpg_ctx* ctx, int q_net, int policy_net, int rows, const fl
   p.rows = rows; p.M = 1; p.horizon = 0; p.n_list = 1; p.list[0] = 0; p.list_w[0] = 1.f;
   p.q_net = q_net; p.policy_net = policy_net;
   return mpg_rollout_forward(ctx, &p, obs, actions, nullptr, out, nullptr, nullptr, nullptr, stream);
+}
+
+int mpg_policy_forward(mpg_ctx* ctx, int net, int rows, const float* obs, float* act_out, void* stream) {
+  if (!ctx || !obs || !act_out || rows <= 0) return fail(ctx, MPG_ERR_ARG, "bad argument to mpg_policy_forward%s");
+  int rc = check_net(ctx, net);
+  if (rc) return rc;
+  if (tc_eval_ok(ctx, rows) && (net == MPG_NET_POLICY || net == MPG_NET_POLICY_TARGET)) {
+    // tensor-core forward kernel, horizon 0, no Q: the action of step 0 is the output (traj_act)
+    mpg_rollout_params p;
+    memset(&p, 0, sizeof(p));
+    p.rows = rows; p.M = 1; p.horizon = 0; p.n_list = 0; p.q_net = -1; p.policy_net = net;
+    return mpg_rollout_forward(ctx, &p, obs, nullptr, nullptr, nullptr, nullptr, nullptr, act_out, stream);
+  }
+  EvalArgs a;
+  memset(&a, 0, sizeof(a));
+  a.mode = 0; a.rows = rows; a.obs = obs; a.out = act_out; a.net0 = net_dev(ctx, net);
+  return launch_eval(ctx, a, stream);
+}
+
+int mpg_q_forward(mpg_ctx* ctx, int net, int rows, const float* obs, const float* act, float* q_out, void* stream) {
+  if (!ctx || !obs || !act || !q_out || rows <= 0) return fail(ctx, MPG_ERR_ARG, "bad argument to mpg_q_forward%s");
+  int rc = check_net(ctx, net);
+  if (rc) return rc;
+  if (tc_eval_ok(ctx, rows) && net != MPG_NET_POLICY && net != MPG_NET_POLICY_TARGET && ctx->nets[MPG_NET_POLICY].set)
+    return tc_q_eval(ctx, net, MPG_NET_POLICY, rows, obs, act, q_out, stream);
+  EvalArgs a;
+  memset(&a, 0, sizeof(a));
+  a.mode = 1; a.rows = rows; a.obs = obs; a.act = act; a.out = q_out; a.net0 = net_dev(ctx, net);
+  return launch_eval(ctx, a, stream);
 }
 
 int mpg_q_target(mpg_ctx* ctx, int double_q, int rows, const float* rew, const float* obs_tp1, float* target_out,
@@ -929,7 +938,7 @@ int mpg_env_step(mpg_ctx* ctx, int rows, const float* state_in, const float* act
 int mpg_env_sample(mpg_ctx* ctx, int policy_net, int agents, int steps, float explore_sigma, const float* explore_noise,
                    const float* reset_obs, float* state, float* obs, float* out_obs, float* out_act, float* out_rew,
                    float* out_obs_tp1, float* out_done, void* stream) {
-  if (!ctx || !reset_obs || !state || !obs || !out_obs || !out_act || !out_rew || !out_obs_tp1 || !out_done || agents <= 0
+  if (!ctx || !state || !obs || !out_obs || !out_act || !out_rew || !out_obs_tp1 || !out_done || agents <= 0
       || steps <= 0)
     return fail(ctx, MPG_ERR_ARG, "bad argument to mpg_env_sample%s");
   if (ctx->cfg.env != MPG_ENV_PATH_TRACKING)

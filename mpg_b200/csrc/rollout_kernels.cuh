@@ -379,7 +379,8 @@ struct SampleArgs {
   float action_range, sigma;
   float obs_scale[MPG_MAX_OBS];
   const float* explore_noise;   // (steps, agents, act_dim) standard normal, or nullptr
-  const float* reset_obs;       // (steps, agents, obs_dim): observation an agent restarts from when done at that step
+  const float* reset_obs;       // (steps, agents, obs_dim): observation an agent restarts from when done at that step;
+                                // nullptr: never restart (fixed-step evaluation episodes, evaluator.py run_an_episode)
   float* state;                 // (agents, 8)        in/out
   float* obs;                   // (agents, obs_dim)  in/out
   float *out_obs, *out_act, *out_rew, *out_obs_tp1, *out_done;   // (steps, agents, ...)
@@ -417,7 +418,7 @@ __global__ void __launch_bounds__(NT, 1) env_sample_kernel(const __grid_constant
       a.out_rew[tr] = rew;
       a.out_done[tr] = (float)done;
       for (int i = 0; i < a.obs_dim; ++i) a.out_obs_tp1[tr * a.obs_dim + i] = o1[i];
-      if (done) {                                   // env.reset(): only the finished agents restart
+      if (done && a.reset_obs) {                    // env.reset(): only the finished agents restart
         for (int i = 0; i < a.obs_dim; ++i) o[i] = a.reset_obs[tr * a.obs_dim + i];
         E::reset(o, s);
       } else {

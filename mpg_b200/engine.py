@@ -316,14 +316,16 @@ class Engine:
         return norm
 
     # ------------------------------------------------------------------ single model step
-    def env_sample(self, state, obs, reset_obs, explore_noise=None, explore_sigma=0.0, policy_net=_lib.NET_POLICY):
-        """Fused sampler (mpg_env_sample): reset_obs (steps, agents, obs_dim); state / obs are updated in place.
-        Returns (obs, act, rew, obs_tp1, done), each with steps * agents rows."""
-        steps, agents = reset_obs.shape[0], reset_obs.shape[1]
+    def env_sample(self, state, obs, reset_obs, explore_noise=None, explore_sigma=0.0, policy_net=_lib.NET_POLICY, steps=None):
+        """Fused sampler (mpg_env_sample): reset_obs (steps, agents, obs_dim) or None (nobody restarts; give `steps`);
+        state / obs are updated in place.  Returns (obs, act, rew, obs_tp1, done), each with steps * agents rows."""
+        agents = state.shape[0]
+        steps = reset_obs.shape[0] if reset_obs is not None else int(steps)
         n = steps * agents
         out = [self.empty(n, self.obs_dim), self.empty(n, self.act_dim), self.empty(n), self.empty(n, self.obs_dim), self.empty(n)]
         self._check(self.lib.mpg_env_sample(self.h, policy_net, agents, steps, float(explore_sigma),
-                                            _ptr(explore_noise) if explore_noise is not None else None, _ptr(reset_obs),
+                                            _ptr(explore_noise) if explore_noise is not None else None,
+                                            _ptr(reset_obs) if reset_obs is not None else None,
                                             _ptr(state), _ptr(obs), *[_ptr(t) for t in out], self.stream))
         return out
 

@@ -33,20 +33,26 @@ class Evaluator(object):
     def set_ppc_params(self, params):
         self.preprocessor.set_params(params)
 
-    def run_n_episodes(self, n=None, seed=777):
-        """num_eval_agent parallel episodes of args.fixed_steps steps with the deterministic policy (compute_mode)."""
+    def run_n_episodes(self, n=None, seed=777, fused=True):
+        """num_eval_agent parallel episodes of args.fixed_steps steps with the deterministic policy (compute_mode).
+        fused: the whole episode is one launch (mpg_env_sample without exploration noise and without restarts)."""
         self.env._rng = np.random.default_rng(seed)      # same start states at every evaluation
         obs = self.env.reset()
-        ret = torch.zeros(obs.shape[0], device=obs.device)
-        dy, dphi, dv = [], [], []
-        for _ in range(self.args.fixed_steps):
-            action = self.policy_with_value.compute_mode(self.preprocessor.torch_process_obses(obs))
-            obs, reward, done, _ = self.env.step(action)
-            ret += reward
-            dy.append(obs[:, 3].abs().mean()); dphi.append(obs[:, 4].abs().mean()); dv.append(obs[:, 0].abs().mean())
-        return dict(episode_return=float(ret.mean()), episode_len=self.args.fixed_steps,
-                    delta_y_mean=float(torch.stack(dy).mean()), delta_phi_mean=float(torch.stack(dphi).mean()),
-                    delta_v_mean=float(torch.stack(dv).mean()))
+        steps, agents = self.args.fixed_steps, obs.shape[0]
+        if fused:
+            _, _, rew, obs_tp1, _ = self.policy_with_value.engine.env_sample(self.env.state, self.env.obs, None, None, 0.0,
+                                                                             steps=steps)
+            rew, o = rew.view(steps, agents), obs_tp1.view(steps, agents, -1)
+        else:
+            rews, obss = [], []
+            for _ in range(steps):
+                action = self.policy_with_value.compute_mode(self.preprocessor.torch_process_obses(obs))
+                obs, reward, done, _ = self.env.step(action)
+                rews.append(reward); obss.append(obs)
+            rew, o = torch.stack(rews), torch.stack(obss)
+        return dict(episode_return=float(rew.sum(0).mean()), episode_len=steps,
+                    delta_y_mean=float(o[:, :, 3].abs().mean()), delta_phi_mean=float(o[:, :, 4].abs().mean()),
+                    delta_v_mean=float(o[:, :, 0].abs().mean()))
 
     def run_evaluation(self, iteration):
         with self.eval_timer:

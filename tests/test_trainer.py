@@ -83,6 +83,7 @@ def test_fused_sampler_matches_step_by_step(sigma):
     outs = []
     for fused in (True, False):
         w = OffPolicyWorker(PolicyWithQs, args.env_id, args, 0)
+        w.policy_with_value.engine.set_backend(0)      # like for like: the fused kernel runs the fp32 tile MLP
         outs.append([t.cpu().numpy() for t in w.sample_arrays(fused=fused)] + [w.env.state.cpu().numpy(), w.obs.cpu().numpy()])
     assert outs[0][4].sum() > 0, 'the case must contain finished agents (reset path)'
     assert np.array_equal(outs[0][4], outs[1][4])
@@ -105,3 +106,14 @@ def test_capacity_growth_keeps_weights_and_optimizer_state():
     for wa, wb in zip(a.get_weights(), b.get_weights()):
         for x, y in zip(wa, wb):
             assert np.array_equal(x, y)
+
+
+def test_fused_evaluation_matches_step_by_step():
+    from mpg_b200.evaluator import Evaluator
+    from mpg_b200.policy import PolicyWithQs
+    args = _args('MPG-v2', num_eval_agent=70, fixed_steps=30)
+    ev = Evaluator(PolicyWithQs, args.env_id, args)
+    ev.policy_with_value.engine.set_backend(0)         # like for like: the fused kernel runs the fp32 tile MLP
+    a, b = ev.run_n_episodes(fused=True), ev.run_n_episodes(fused=False)
+    for k in a:
+        assert abs(a[k] - b[k]) <= 1e-4 * max(abs(b[k]), 1.0), (k, a[k], b[k])
