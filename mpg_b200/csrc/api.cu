@@ -558,6 +558,10 @@ int mpg_policy_grad(mpg_ctx* ctx, const mpg_rollout_params* p, const float* obs,
     const size_t need = (size_t)ntiles * ta.store_steps * tc::SLOT_BYTES;
     if (!tc_ensure_store(ctx->tc, need)) return fail(ctx, MPG_ERR_CUDA, "cudaMalloc of the dW operand store failed%s");
     ta.store = ctx->tc.store;
+    if (!tc_ensure_h2store(ctx->tc, (size_t)ntiles * (p->horizon + 1) * 2 * tc::ACT_SPLIT))
+      return fail(ctx, MPG_ERR_CUDA, "cudaMalloc of the h2 image store failed%s");
+    ta.h2store = ctx->tc.h2store;
+    ta.z_ckpt = ctx->tc.z_ckpt;
     ta.prof = ctx->prof;
     const size_t dw_smem = tc::DW_SMEM;
     auto dw_args = [&](int tile0, int tiles, int part_row) {

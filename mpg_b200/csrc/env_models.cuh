@@ -33,12 +33,16 @@ struct Env<MPG_ENV_PATH_TRACKING> {
   }
   __device__ static void get_obs(const float* s, float* o, int nfd) {  // _get_obs (:265-271)
     o[0] = s[0] - 20.f; o[1] = s[1]; o[2] = s[2]; o[3] = s[3]; o[4] = s[4]; o[5] = s[5];
-    for (int i = 0; i < nfd; ++i) o[6 + i] = s[3];
+#pragma unroll
+    for (int i = 0; i < MPG_MAX_OBS - 6; ++i)      // fixed trip count + predicate: o[] stays in registers
+      if (i < nfd) o[6 + i] = s[3];
   }
   // d obs -> d state (E of SURVEY 8(a)); go already multiplied by obs_scale
   __device__ static void obs_grad_to_state(const float*, const float* go, int nfd, float* gs) {
     gs[0] += go[0]; gs[1] += go[1]; gs[2] += go[2]; gs[3] += go[3]; gs[4] += go[4]; gs[5] += go[5];
-    for (int i = 0; i < nfd; ++i) gs[3] += go[6 + i];
+#pragma unroll
+    for (int i = 0; i < MPG_MAX_OBS - 6; ++i)
+      if (i < nfd) gs[3] += go[6 + i];
   }
   __device__ static float reward_pre(const float* s, float steer, float ax) {  // compute_rewards (:181-199)
     float dv = s[0] - 20.f;
@@ -72,11 +76,14 @@ struct Env<MPG_ENV_PATH_TRACKING> {
   }
   // adjoint of one step. lam = d L / d s_{t+1}; rc = coefficient on the RAW reward r_t.
   // gs += (df/ds)^T lam + rc dr/ds ; ga += scale * ((df/du)^T lam + rc dr/du)
+  // FAST: MUFU sin / cos / reciprocal (|phi| <= pi: absolute error ~5e-7, far inside the 1e-4 gradient tolerance);
+  // used by the tensor-core kernel, where this per-row chain sits on the critical path of every BPTT step
+  template <bool FAST = false>
   __device__ static void step_bwd(const float* s, const float* act, const float* lam, float rc, float* gs, float* ga) {
     float steer = act[0] * STEER_SCALE, ax = act[1] * ACC_SCALE;
     float vx = s[0], vy = s[1], r = s[2], phi = s[4];
     float sn, cs;
-    sincosf(phi, &sn, &cs);
+    if (FAST) __sincosf(phi, &sn, &cs); else sincosf(phi, &sn, &cs);
     float vx1 = vx + TAU * (ax + vy * r);
     float Lvx = (vx1 >= 1.f && vx1 <= 35.f) ? lam[0] : 0.f;  // ClipByValue grad: inclusive pass-through
     float Lvy = lam[1], Lr = lam[2], Ldy = lam[3], Lphi = lam[4], Lx = lam[5];
@@ -84,7 +91,7 @@ struct Env<MPG_ENV_PATH_TRACKING> {
     float N1 = m * vy * vx + TAU * K * r - TAU * Cf * steer * vx - TAU * m * vx * vx * r;
     float D2 = TAU * A2 - Iz * vx;
     float N2 = -Iz * r * vx - TAU * K * vy + TAU * a * Cf * steer * vx;
-    float iD1 = 1.f / D1, iD2 = 1.f / D2;
+    float iD1 = FAST ? __fdividef(1.f, D1) : 1.f / D1, iD2 = FAST ? __fdividef(1.f, D2) : 1.f / D2;
     gs[0] += Lvx + Lvy * ((m * vy - TAU * Cf * steer - 2.f * TAU * m * vx * r) * iD1 - N1 * m * iD1 * iD1)
              + Lr * ((-Iz * r + TAU * a * Cf * steer) * iD2 + N2 * Iz * iD2 * iD2)
              + Ldy * TAU * sn + Lx * TAU * cs
@@ -142,6 +149,7 @@ struct Env<MPG_ENV_INVERTED_PENDULUM> {
     return reward_post(s);  // reward on the POST-step state (:92-93)
   }
   // lam = dL/ds_{t+1} (without this step's reward); s1 = post-step state (for the reward term)
+  template <bool FAST = false>
   __device__ static void step_bwd(const float* s, const float* act, const float* lam, float rc, float* gs, float* ga,
                                   const float* s1) {
     float L0 = lam[0] + rc * (-0.02f * s1[0]);
@@ -151,11 +159,11 @@ struct Env<MPG_ENV_INVERTED_PENDULUM> {
     float u = ACT_SCALE * act[0];
     float th = s[1], thd = s[3];
     float sn, c;
-    sincosf(th, &sn, &c);
+    sincosf(th, &sn, &c);          // theta is unbounded here: keep the accurate range reduction
     float f0 = d2 * sn * thd * thd + u, f1v = f1c * sn;
     float det = d1 * d4 - d2 * c * d2 * c;
     float N0 = d4 * f0 - d2 * c * f1v, N1 = -d2 * c * f0 + d1 * f1v;
-    float idet = 1.f / det;
+    float idet = FAST ? __fdividef(1.f, det) : 1.f / det;
     float Aq = L2 * TAU, Bq = L3 * TAU;   // adjoints of pdd, thdd
     float aN0 = Aq * idet, aN1 = Bq * idet;
     float adet = -(Aq * N0 + Bq * N1) * idet * idet;
@@ -352,9 +360,13 @@ struct Env<MPG_ENV_PT_REAL> {
   __device__ static void get_obs(const float* s, float* o, int nfd) {   // _get_obs (:384-402)
     o[0] = s[0] - 20.f; o[1] = s[1]; o[2] = s[2]; o[3] = s[3]; o[4] = s[4]; o[5] = s[5];
     float x_ = s[5];
+#pragma unroll 1
     for (int i = 0; i < nfd; ++i) {
       x_ += s[0] * 1.f / FREQ * (float)SUBSTEPS * 2.f;
-      o[6 + i] = s[6] - path_y(x_);
+      const float v = s[6] - path_y(x_);
+#pragma unroll
+      for (int k = 0; k < MPG_MAX_OBS - 6; ++k)
+        if (k == i) o[6 + k] = v;
     }
   }
   // step (:456-472); returns the RAW reward (pre-step state, clipped scaled action); *done gets judge_done (:474-487)
@@ -409,11 +421,12 @@ struct Env<MPG_ENV_PT_REAL> {
 };
 
 // uniform wrapper so the rollout kernel does not care whether the reward is pre- or post-step
-template <int ENV>
+template <int ENV, bool FAST = false>
 __device__ __forceinline__ void env_step_bwd(const float* s, const float* act, const float* lam, float rc, float* gs,
                                              float* ga, const float* s1) {
-  if constexpr (ENV == MPG_ENV_PATH_TRACKING) Env<ENV>::step_bwd(s, act, lam, rc, gs, ga);
+  if constexpr (ENV == MPG_ENV_PATH_TRACKING) Env<ENV>::template step_bwd<FAST>(s, act, lam, rc, gs, ga);
   else if constexpr (ENV == MPG_ENV_PT_REAL) { }   // the real environment is never differentiated
+  else if constexpr (ENV == MPG_ENV_INVERTED_PENDULUM) Env<ENV>::template step_bwd<FAST>(s, act, lam, rc, gs, ga, s1);
   else Env<ENV>::step_bwd(s, act, lam, rc, gs, ga, s1);
 }
 

@@ -48,6 +48,14 @@ __device__ __forceinline__ float head_grad(float z, int out_tanh, float range) {
   return g;
 }
 
+// action and d action / d z in one evaluation (same operations as head_fwd / head_grad)
+__device__ __forceinline__ void head_fwd_grad(float z, int out_tanh, float range, float& act, float& g) {
+  const float m = out_tanh ? tanhf(z) : z;
+  g = out_tanh ? 1.f - m * m : 1.f;
+  act = m;
+  if (range > 0.f) { const float th = tanhf(m); g *= range * (1.f - th * th); act = range * th; }
+}
+
 template <int ENV, bool BWD>
 __global__ void __launch_bounds__(NT, 1) rollout_kernel(const __grid_constant__ RolloutArgs a) {
   extern __shared__ float4 smem_raw[];

@@ -54,6 +54,9 @@ struct Bars {
   uint64_t z_empty[2];   // chunk buffer j has been read out (epilogue -> mma)
   uint64_t acc_done;     // the D1 accumulation UMMAs have read the delta1 / [p|1] images
   uint64_t kb_done[4];   // big GEMM: the UMMAs of K-block kb are complete (block kb of the A image is no longer read)
+  uint64_t p_full;       // BPTT: the [p|1] image of this step is written (row threads -> mma, first-layer recompute)
+  uint64_t img_empty;    // BPTT: nothing reads the activation image any more (mma commit + elected epilogue thread)
+  uint64_t img_full;     // BPTT: the h2 image of this step has landed in the activation image (TMA complete_tx)
   uint32_t tmem_base;
 };
 static_assert(sizeof(Bars) <= 256, "BARS region too small");
@@ -66,6 +69,8 @@ struct Sync {
   uint32_t d_cnt = 0;    // d_full phases seen
   uint32_t acc_cnt = 0;  // acc_done phases seen (epilogue side)
   uint32_t k_cnt = 0;    // big GEMMs issued so far (kb_done[] phases, epilogue side)
+  uint32_t p_cnt = 0;    // p_full phases seen
+  uint32_t i_cnt = 0;    // img_empty / img_full phases seen (h2 image loads)
 };
 
 enum Role { ROLE_EPI = 0, ROLE_PRODUCER = 1, ROLE_MMA = 2 };
@@ -165,13 +170,17 @@ __device__ __forceinline__ void epi_release_chunk(Bars* b, int c) {
 // IMG[:, half]^T . R16, IMG = activation image read MN-major (K = rows), R16 = [p|1] or [delta3|0] image read
 // MN-major.  24 UMMAs per half (8 row steps x 3 split products); a half needs only its two 64-feature blocks of the
 // image, so it can be issued as soon as those are written and lets the image be overwritten half by half.
-__device__ __forceinline__ void mma_acc16_half(uint32_t act_addr, uint32_t r16_addr, uint32_t d_tmem, int half, bool started) {
+// lin: the image is in the row-interleaved no-swizzle layout [chunk][row][16 B] (h2 images loaded from the h2 store):
+// MN-major INTERLEAVE, 8-row groups 128 B apart (LBO), 8-feature chunks 2048 B apart (SBO), 16 rows = 256 B per k-step.
+__device__ __forceinline__ void mma_acc16_half(uint32_t act_addr, uint32_t r16_addr, uint32_t d_tmem, int half, bool started,
+                                               bool lin = false) {
   constexpr uint32_t idesc = make_idesc(128, 16, 1, 1);
   const uint32_t d = d_tmem + half * 16;
 #pragma unroll
   for (int ks = 0; ks < ACT_ROWS / 16; ++ks) {
-    const uint32_t a = act_addr + half * 2 * ACT_BLOCK + ks * 2048;
-    const uint64_t dah = make_desc(a, ACT_BLOCK, 1024, LAYOUT_SW128), dal = make_desc(a + ACT_SPLIT, ACT_BLOCK, 1024, LAYOUT_SW128);
+    const uint32_t a = act_addr + half * 2 * ACT_BLOCK + (lin ? ks * 256 : ks * 2048);
+    const uint64_t dah = lin ? make_desc(a, 128, 2048, LAYOUT_NONE) : make_desc(a, ACT_BLOCK, 1024, LAYOUT_SW128);
+    const uint64_t dal = lin ? make_desc(a + ACT_SPLIT, 128, 2048, LAYOUT_NONE) : make_desc(a + ACT_SPLIT, ACT_BLOCK, 1024, LAYOUT_SW128);
     const uint64_t dbh = make_desc(r16_addr + ks * 512, 256, 128, LAYOUT_NONE), dbl = make_desc(r16_addr + 4096 + ks * 512, 256, 128, LAYOUT_NONE);
     umma_bf16(d, dah, dbh, idesc, (started || ks) ? 1u : 0u);
     umma_bf16(d, dal, dbh, idesc, 1u);
@@ -304,13 +313,17 @@ __device__ __forceinline__ void fwd_pair_issue(Bars* b, uint8_t* smem, Sync& s, 
 template <int ROLE>
 __device__ __forceinline__ void bwd_tail_issue(Bars* b, uint8_t* smem, Sync& s, const uint8_t* l1_img, const uint8_t* in_img,
                                                bool do_gp, bool do_d1, bool& d1_started, uint32_t tm_z1c, uint32_t tm_gp,
-                                               uint32_t tm_d1) {
+                                               uint32_t tm_d1, bool wait_p = false) {
   if (ROLE == ROLE_PRODUCER) {
     produce(b, smem + SmemMap::RING, s, l1_img, 1, 16384);
     produce_pad(b, s);
     if (do_gp) { produce(b, smem + SmemMap::RING, s, in_img, 1, 16384); produce_pad(b, s); }
   } else if (ROLE == ROLE_MMA) {
     const uint32_t base = smem_u32(smem), p_addr = base + SmemMap::PIMG, ring = base + SmemMap::RING;
+    if (wait_p) {                                 // the [p|1] image of this step was written at the start of the step
+      mbar_wait(&b->p_full, s.p_cnt & 1);
+      ++s.p_cnt;
+    }
     const uint32_t slot = s.stage & (NSLOT - 1), par = (s.stage / NSLOT) & 1;
     mbar_wait(&b->full[slot], par);
     tc_fence_after();
@@ -319,8 +332,10 @@ __device__ __forceinline__ void bwd_tail_issue(Bars* b, uint8_t* smem, Sync& s, 
     umma_commit(&b->empty[slot]);
     ++s.stage;
     consume_pad(b, s);
-    // g_p K-block kb follows delta1 block kb; the D1 UMMAs are issued after g_p has been committed, so they run
-    // under the epilogue's lambda update and the start of the next step (acc_done gates the next image writes)
+    // g_p K-block kb follows delta1 block kb.  D1 += delta1^T [p|1] is issued per 128-feature half: half 0 as soon as
+    // delta1 blocks 0, 1 exist (it runs under the second half of the delta1 epilogue, when the tensor pipe has nothing
+    // else to do), half 1 after g_p has been committed, so that it runs under the epilogue's lambda update and the start
+    // of the next step (acc_done gates the next image writes)
     constexpr uint32_t idesc_in = make_idesc(128, 16, 0, 0);
     const uint32_t act_addr = base + SmemMap::ACT;
     const uint32_t islot = s.stage & (NSLOT - 1), ipar = (s.stage / NSLOT) & 1;
@@ -343,6 +358,7 @@ __device__ __forceinline__ void bwd_tail_issue(Bars* b, uint8_t* smem, Sync& s, 
       } else {
         tc_fence_after();
       }
+      if (do_d1 && kb == 1) mma_acc16_half(act_addr, p_addr, tm_d1, 0, d1_started);
     }
     ++s.g_cnt;
     if (do_gp) {
@@ -352,7 +368,6 @@ __device__ __forceinline__ void bwd_tail_issue(Bars* b, uint8_t* smem, Sync& s, 
       mma_publish_d(b);
     }
     if (do_d1) {
-      mma_acc16_half(act_addr, p_addr, tm_d1, 0, d1_started);
       mma_acc16_half(act_addr, p_addr, tm_d1, 1, d1_started);
       d1_started = true;
       umma_commit(&b->acc_done);
@@ -362,15 +377,16 @@ __device__ __forceinline__ void bwd_tail_issue(Bars* b, uint8_t* smem, Sync& s, 
 // D3 += h2^T [delta3|0]: the epilogue publishes (h2 image + delta3 image written); the UMMAs complete on d_full
 // twice, once per 128-feature half, so that the delta2 epilogue can start on the first half of the image
 template <int ROLE>
-__device__ __forceinline__ void d3_issue(Bars* b, uint8_t* smem, Sync& s, uint32_t d3_off, bool& d3_started, uint32_t tm_d3) {
+__device__ __forceinline__ void d3_issue(Bars* b, uint8_t* smem, Sync& s, uint32_t d3_off, bool& d3_started, uint32_t tm_d3,
+                                         bool lin = false) {
   if (ROLE == ROLE_MMA) {
     const uint32_t base = smem_u32(smem);
     mbar_wait(&b->a_full, s.a_cnt & 1);
     ++s.a_cnt;
     tc_fence_after();
-    mma_acc16_half(base + SmemMap::ACT, base + d3_off, tm_d3, 0, d3_started);
+    mma_acc16_half(base + SmemMap::ACT, base + d3_off, tm_d3, 0, d3_started, lin);
     mma_publish_d(b);                      // blocks 0, 1 of the h2 image may be overwritten
-    mma_acc16_half(base + SmemMap::ACT, base + d3_off, tm_d3, 1, d3_started);
+    mma_acc16_half(base + SmemMap::ACT, base + d3_off, tm_d3, 1, d3_started, lin);
     mma_publish_d(b);                      // blocks 2, 3
     d3_started = true;
   } else if (ROLE == ROLE_EPI) {
@@ -398,6 +414,9 @@ __device__ __forceinline__ Bars* cta_setup(uint8_t* smem) {
     for (int i = 0; i < 2; ++i) { mbar_init(&b->z_full[i], 1); mbar_init(&b->z_empty[i], EPI_THREADS); }
     mbar_init(&b->acc_done, 1);
     for (int i = 0; i < 4; ++i) mbar_init(&b->kb_done[i], 1);
+    mbar_init(&b->p_full, ACT_ROWS);
+    mbar_init(&b->img_empty, 2);
+    mbar_init(&b->img_full, 1);
     fence_barrier_init();
   }
   if (warp == EPI_WARPS + 1) tmem_alloc(&b->tmem_base, TMEM_COLS);

@@ -5,8 +5,11 @@
 // tensor cores with split-bf16 operands (3 products, fp32 accumulation in TMEM); weights are streamed from
 // L2 through a shared-memory ring by the TMA engine; the per-row vehicle / pendulum dynamics, rewards,
 // output heads and adjoints stay in registers of the thread that owns the row (TMEM lane = row).
-// Backward = BPTT with recompute from the 24-byte state checkpoints.  The dX chain (what the recurrence
-// needs) is fully fused.  The weight-gradient contractions (K = rows) cannot be accumulated in place: the
+// Backward = BPTT from the 24-byte state checkpoints.  The forward pass of the gradient kernel leaves the second
+// hidden activation of every step behind as a ready-made operand image (1 KB per row and step, written straight
+// from the epilogue registers); BPTT pulls it back with one bulk copy per step instead of re-running layer 1 + layer 2
+// (one third of the contraction work and two of the five epilogues of a backward step).  elu'(z1) still comes from
+// the cheap K = 16 first-layer recompute.  The dX chain (what the recurrence needs) is fully fused.  The weight-gradient contractions (K = rows) cannot be accumulated in place: the
 // fp32 accumulator of dW2 alone is 256 KB = all of TMEM.  Their operand tiles (h1, h2, delta1, delta2 as
 // split-bf16 images, written to shared memory anyway as UMMA operands) are bulk-stored once and consumed
 // by tc_dw_kernel, a split-K tcgen05 GEMM with MN-major operands.
@@ -43,6 +46,9 @@ struct TcArgs {
   RolloutArgs r;            // config, lists, pointers (r.pol / r.q unused here)
   TcNet pol, q;
   float* act_ckpt;          // [n_list][M*rows][A] actions at the list steps (for the Q input gradient)
+  float* z_ckpt;            // [horizon+1][M*rows][2A] action and head derivative d act / d z of every step (BPTT re-reads them)
+  uint8_t* h2store;         // [tile][horizon+1][2*ACT_SPLIT] h2 images of the forward pass (BPTT loads them instead of
+                            //    recomputing layer 2)
   uint8_t* store;           // dW operand store: [tile][step][SLOT_BYTES]
   int store_steps;          // steps recorded per tile: horizon+1 (full BPTT) or 1 (first action only)
   int tile0, tile1;         // tile range of this launch (tile1 == 0: all tiles); CTA c owns tile0 + c, tile0 + c + grid, ...
@@ -155,7 +161,38 @@ __device__ MPG_EPI_INLINE void epi_hidden2(uint32_t tm_lane, const float* b2, co
     }
   }
 }
-// same, and keep h2 as an image (backward pass: delta2 and the dW3 operand are derived from it)
+// same, and leave h2 behind in global memory as an operand image in the row-interleaved layout
+//   [split hi|lo][16-byte chunk cc = 8 features][row][16 B]
+// (the canonical no-swizzle UMMA layout: K-major with LBO = 2048, SBO = 128, and MN-major with LBO = 128, SBO = 2048).
+// A warp (32 consecutive rows, one chunk) writes 512 contiguous bytes per store instruction.
+__device__ __forceinline__ uint32_t lin_chunk_off(int r, int cc) { return (uint32_t)(cc * (ACT_ROWS * 16) + r * 16); }
+__device__ MPG_EPI_INLINE void epi_hidden2_gstore(uint32_t tm_lane, const float* b2, const float* W3, uint8_t* gimg, int row,
+                                                  int hc, float& p0, float& p1) {
+  p0 = 0.f; p1 = 0.f;
+  for (int c0 = hc * COLS_PER_WARP; c0 < (hc + 1) * COLS_PER_WARP; c0 += 16) {
+    float v[16];
+    tmem_ld16(tm_lane + c0, v);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      v[i] = elu_fast(v[i] + b2[c0 + i]);
+      const float2 w = *reinterpret_cast<const float2*>(W3 + 2 * (c0 + i));
+      p0 = fmaf(v[i], w.x, p0);
+      p1 = fmaf(v[i], w.y, p1);
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      uint4 hi, lo;
+      split2(v[8 * h + 0], v[8 * h + 1], hi.x, lo.x);
+      split2(v[8 * h + 2], v[8 * h + 3], hi.y, lo.y);
+      split2(v[8 * h + 4], v[8 * h + 5], hi.z, lo.z);
+      split2(v[8 * h + 6], v[8 * h + 7], hi.w, lo.w);
+      const uint32_t off = lin_chunk_off(row, (c0 >> 3) + h);
+      *reinterpret_cast<uint4*>(gimg + off) = hi;
+      *reinterpret_cast<uint4*>(gimg + ACT_SPLIT + off) = lo;
+    }
+  }
+}
+// same, and keep h2 as an image (Q part of the backward pass: delta2 and the dW3 operand are derived from it)
 __device__ MPG_EPI_INLINE void epi_hidden2_img(uint32_t tm_lane, const float* b2, const float* W3, uint8_t* act, int row,
                                                int hc, float& p0, float& p1, bool draining = false, bool elected = false) {
   p0 = 0.f; p1 = 0.f;
@@ -184,6 +221,40 @@ __device__ MPG_EPI_INLINE void epi_delta2_blocks(Bars* b, const float* W3, float
     float v[16];
     act_load8(act, act + ACT_SPLIT, row, c0 >> 3, v);
     act_load8(act, act + ACT_SPLIT, row, (c0 >> 3) + 1, v + 8);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float2 w = *reinterpret_cast<const float2*>(W3 + 2 * (c0 + i));
+      const float g = fmaf(d30, w.x, d31 * w.y);
+      v[i] = g * (v[i] > 0.f ? 1.f : v[i] + 1.f);     // elu'(z) expressed through the output h2
+    }
+    act_store8(act, act + ACT_SPLIT, row, c0 >> 3, v);
+    act_store8(act, act + ACT_SPLIT, row, (c0 >> 3) + 1, v + 8);
+    epi_block_done(b, kb);
+  }
+}
+// BPTT variant: h2 arrives from the h2 store in the row-interleaved layout (lin_chunk_off); delta2 is written as the
+// SW128 K-major image the dX UMMAs and the dW2 record expect.  Both layouts keep 64-feature block kb inside the same
+// 16 KB per split, so the conversion is in place block by block: every thread reads its part of block kb, barrier,
+// every thread writes.
+__device__ MPG_EPI_INLINE void epi_delta2_from_h2(Bars* b, const float* W3, float d30, float d31, uint8_t* act, int row, int hc,
+                                                  Sync* wait_half1 = nullptr) {
+  for (int kb = 0; kb < 4; ++kb) {
+    const int c0 = kb * 64 + hc * 16;
+    if (kb == 2 && wait_half1) epi_wait_d(b, *wait_half1);   // the D3 UMMAs have read blocks 2, 3 of the h2 image
+    float v[16];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const uint32_t off = lin_chunk_off(row, (c0 >> 3) + h);
+      const uint4 hv = *reinterpret_cast<const uint4*>(act + off);
+      const uint4 lv = *reinterpret_cast<const uint4*>(act + ACT_SPLIT + off);
+      const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w}, lw[4] = {lv.x, lv.y, lv.z, lv.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        v[8 * h + 2 * i] = __uint_as_float(hw[i] << 16) + __uint_as_float(lw[i] << 16);
+        v[8 * h + 2 * i + 1] = __uint_as_float(hw[i] & 0xFFFF0000u) + __uint_as_float(lw[i] & 0xFFFF0000u);
+      }
+    }
+    epi_bar();                                               // block kb has been read by everybody
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
       const float2 w = *reinterpret_cast<const float2*>(W3 + 2 * (c0 + i));
@@ -257,6 +328,7 @@ __device__ __forceinline__ void run_rollout(const TcArgs& A, uint8_t* smem, Bars
   Sync sy;
   bool d1_started = false, d3_started = false;   // mma role: the persistent accumulators hold a value
   bool d1_pending = false, any_dw = false;       // epilogue role: D1 UMMAs in flight / accumulators were used
+  bool store_pending = false;                    // epilogue role: a record store still reads the activation image
   // the D1 UMMAs of the previous step read the delta1 and [p|1] images: wait before either is rewritten
   auto acc_wait = [&]() {
     if (ROLE == ROLE_EPI && d1_pending) {
@@ -279,48 +351,56 @@ __device__ __forceinline__ void run_rollout(const TcArgs& A, uint8_t* smem, Bars
     const int m_idx = valid ? grow / a.rows : 0, i_idx = valid ? grow % a.rows : 0;
     const unsigned long long noise_row = (unsigned long long)m_idx * (unsigned long long)a.global_rows
                                          + (unsigned long long)(a.row_offset + i_idx);
+    uint8_t* h2tile = (BWD && A.h2store) ? A.h2store + (size_t)tile * (size_t)(a.horizon + 1) * (2 * ACT_SPLIT) : nullptr;
     float s[S];
 #pragma unroll
     for (int j = 0; j < S; ++j) s[j] = 0.f;
     if (valid) {
       float o[MPG_MAX_OBS];
-      for (int i = 0; i < a.obs_dim; ++i) o[i] = a.obs[(size_t)i_idx * a.obs_dim + i];
+#pragma unroll
+      for (int i = 0; i < MPG_MAX_OBS; ++i) o[i] = i < a.obs_dim ? a.obs[(size_t)i_idx * a.obs_dim + i] : 0.f;
       E::reset(o, s);
     }
     float rsum = 0.f, gpow = 1.f;
 
     // [sigma*obs(s) | act | 0.. | 1] -> p image
     auto write_pimg = [&](const float* st, const float* act_or_null, uint8_t* gimg = nullptr) {
+      // every index below is a compile-time constant (fixed trip counts + predicates): x[] and o[] stay in registers
       float x[16], o[MPG_MAX_OBS];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) x[i] = 0.f;
+      for (int i = 0; i < MPG_MAX_OBS; ++i) o[i] = 0.f;
       E::get_obs(st, o, a.nfd);
-      for (int i = 0; i < a.obs_dim; ++i) x[i] = o[i] * a.obs_scale[i];
-      if (act_or_null)
-        for (int j = 0; j < NA; ++j) x[a.obs_dim + j] = act_or_null[j];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        float v = i < a.obs_dim ? o[i] * a.obs_scale[i] : 0.f;
+        if (act_or_null) {
+#pragma unroll
+          for (int j = 0; j < NA; ++j)
+            if (i == a.obs_dim + j) v = act_or_null[j];
+        }
+        x[i] = v;
+      }
       x[BIAS_K] = 1.f;
       write_row16(p_img, row, x, gimg);
     };
     // policy forward on the current p image: returns pre-activations of the head for the row thread.
-    // The layer-2 UMMAs are issued K-block by K-block while the epilogue is still producing h1.
-    auto policy_forward = [&](float* zpre, bool bwd_pass, bool rec_, uint8_t* slot) {
-      if (ROLE == ROLE_MMA && bwd_pass) stamp(0);
+    // The layer-2 UMMAs are issued K-block by K-block while the epilogue is still producing h1.  In the gradient
+    // kernel h2 goes to the h2 store of this (tile, step) and, for the steps whose weight gradient is wanted (slot),
+    // the h1 image leaves for the dW operand store behind the K-blocks of the GEMM.
+    auto policy_forward = [&](float* zpre, uint8_t* h2slot, uint8_t* slot) {
       fwd_pair_issue<ROLE>(b, smem, sy, A.pol.l1, A.pol.big_fwd, tm_z1c, tm_work);
-      if (ROLE == ROLE_MMA && bwd_pass) stamp(2);
       if (ROLE == ROLE_EPI) {
-        stamp(bwd_pass ? 2 : 17);
-        epi_hidden1_blocks(b, tm_z1c + lane_off, act_img, row, hc);   // follows the z1 chunk stream
-        stamp(bwd_pass ? 3 : 18);
-        if (rec_) store_image_follow(elected, b, sy, slot + SLOT_H1, act_img);   // h1 blocks leave behind their K-blocks
-        epi_wait_d(b, sy);                                   // z2 (all layer-2 UMMAs done: h1 image free)
-        stamp(bwd_pass ? 4 : 19);
+        stamp(17);
+        if (store_pending) { store_wait(elected); store_pending = false; }   // the previous step's h1 record has left long ago
+        epi_hidden1_blocks(b, tm_z1c + lane_off, act_img, row, hc);          // follows the z1 chunk stream
+        stamp(18);
+        if (slot) { store_image_follow(elected, b, sy, slot + SLOT_H1, act_img); store_pending = true; }
+        epi_wait_d(b, sy);                                   // z2 (all layer-2 UMMAs done)
+        stamp(19);
         float p0, p1;
-        if (bwd_pass) {
-          epi_hidden2_img(tm_work + lane_off, mf->b2p, mf->W3p, act_img, row, hc, p0, p1, rec_, elected);
-        } else {
-          epi_hidden2(tm_work + lane_off, mf->b2p, mf->W3p, hc, p0, p1);
-        }
-        stamp(bwd_pass ? 5 : 20);
+        if (BWD) epi_hidden2_gstore(tm_work + lane_off, mf->b2p, mf->W3p, h2slot, row, hc, p0, p1);
+        else epi_hidden2(tm_work + lane_off, mf->b2p, mf->W3p, hc, p0, p1);
+        stamp(20);
         mf->part[(hc * 2 + 0) * ACT_ROWS + row] = p0;
         mf->part[(hc * 2 + 1) * ACT_ROWS + row] = p1;
         epi_bar();
@@ -337,6 +417,7 @@ __device__ __forceinline__ void run_rollout(const TcArgs& A, uint8_t* smem, Bars
       float qv = 0.f;
       fwd_pair_issue<ROLE>(b, smem, sy, A.q.l1, A.q.big_fwd, tm_z1c, tm_work);
       if (ROLE == ROLE_EPI) {
+        if (store_pending) { store_wait(elected); store_pending = false; }
         epi_hidden1_blocks(b, tm_z1c + lane_off, act_img, row, hc);
         if (qslot) store_image(elected, qslot + SLOT_H1, act_img, 2 * ACT_SPLIT);
         epi_wait_d(b, sy);
@@ -362,6 +443,9 @@ __device__ __forceinline__ void run_rollout(const TcArgs& A, uint8_t* smem, Bars
 #pragma unroll
       for (int j = 0; j < NA; ++j) act[j] = 0.f;
       const bool given = (t == 0 && a.use_start_actions);
+      // steps whose weight gradient is wanted leave their dW2 operands (h1 now, delta2 during BPTT) in the operand store
+      const bool rec_f = store_dw && !A.q_regress && (a.full_bptt || t == 0);
+      uint8_t* slot = rec_f ? A.store + ((size_t)tile * A.store_steps + (a.full_bptt ? t : 0)) * SLOT_BYTES : nullptr;
       if (ROLE == ROLE_EPI) {
         if (tile == A.tile0 + (int)blockIdx.x && t == 2) { prof_t = t; stamp(16); }
         else if (prof_t >= 0) { stamp(22); prof_t = -1; }
@@ -372,15 +456,23 @@ __device__ __forceinline__ void run_rollout(const TcArgs& A, uint8_t* smem, Bars
 #pragma unroll
           for (int j = 0; j < S; ++j) c[j] = s[j];
         }
-        if (!given) write_pimg(s, nullptr);
+        if (!given) write_pimg(s, nullptr, slot ? slot + SLOT_P : nullptr);
       }
       if (!given) {
         float zpre[NA];
-        policy_forward(zpre, false, false, nullptr);
+        policy_forward(zpre, BWD ? h2tile + (size_t)t * (2 * ACT_SPLIT) : nullptr, slot);
         stamp(21);
-        if (rowthread)
+        if (rowthread) {
+          float hg[NA];
 #pragma unroll
-          for (int j = 0; j < NA; ++j) act[j] = head_fwd(zpre[j], a.policy_out_tanh, a.action_range);
+          for (int j = 0; j < NA; ++j) head_fwd_grad(zpre[j], a.policy_out_tanh, a.action_range, act[j], hg[j]);
+          if (BWD && valid)
+#pragma unroll
+            for (int j = 0; j < NA; ++j) {
+              A.z_ckpt[((size_t)t * MB + grow) * (2 * NA) + j] = act[j];
+              A.z_ckpt[((size_t)t * MB + grow) * (2 * NA) + NA + j] = hg[j];
+            }
+        }
       } else if (rowthread && valid) {
 #pragma unroll
         for (int j = 0; j < NA; ++j) act[j] = a.start_actions[(size_t)i_idx * NA + j];
@@ -415,15 +507,20 @@ __device__ __forceinline__ void run_rollout(const TcArgs& A, uint8_t* smem, Bars
         if (a.traj_obs) {
           float o[MPG_MAX_OBS];
           E::get_obs(s, o, a.nfd);
-          for (int i = 0; i < a.obs_dim; ++i) a.traj_obs[((size_t)t * MB + grow) * a.obs_dim + i] = o[i];
+#pragma unroll
+          for (int i = 0; i < MPG_MAX_OBS; ++i)
+            if (i < a.obs_dim) a.traj_obs[((size_t)t * MB + grow) * a.obs_dim + i] = o[i];
         }
       }
     }
     // =========================================== backward ==========================================
     if (BWD) {
-      float lam[S], snext[S], spre[S];
+      float lam[S], snext[S], spre[S], zpre_n[2 * NA];   // zpre_n: action and head derivative of the next step to process
 #pragma unroll
       for (int j = 0; j < S; ++j) { lam[j] = 0.f; snext[j] = s[j]; spre[j] = s[j]; }   // s == s_horizon here
+#pragma unroll
+      for (int j = 0; j < 2 * NA; ++j)
+        zpre_n[j] = (rowthread && valid && !A.q_regress) ? A.z_ckpt[((size_t)a.horizon * MB + grow) * (2 * NA) + j] : 0.f;
       for (int t = a.horizon; t >= 0; --t) {
         float gp = 1.f;
         for (int i = 0; i < t; ++i) gp *= a.gamma;
@@ -432,20 +529,23 @@ __device__ __forceinline__ void run_rollout(const TcArgs& A, uint8_t* smem, Bars
         prof_t = (tile == A.tile0 + (int)blockIdx.x && t == a.horizon - 1) ? t : -1;
         stamp(0);
         uint8_t* slot = rec ? A.store + ((size_t)tile * A.store_steps + (a.full_bptt ? t : 0)) * SLOT_BYTES : nullptr;
-        float g_a[NA], g_s[S], act[NA], zpre[NA];
+        float g_a[NA], g_s[S], act[NA], hgrad[NA];
 #pragma unroll
-        for (int j = 0; j < NA; ++j) { g_a[j] = 0.f; act[j] = 0.f; zpre[j] = 0.f; }
+        for (int j = 0; j < NA; ++j) { g_a[j] = 0.f; act[j] = zpre_n[j]; hgrad[j] = zpre_n[NA + j]; }
 #pragma unroll
         for (int j = 0; j < S; ++j) g_s[j] = 0.f;
         if (rowthread && valid) {
-          // s_t was prefetched during the previous iteration; issue the loads of s_{t-1} now so that their
-          // global-memory latency hides behind this step
+          // s_t and the head pre-activations were prefetched during the previous iteration; issue the loads of step
+          // t-1 now so that their global-memory latency hides behind this step
 #pragma unroll
           for (int j = 0; j < S; ++j) s[j] = spre[j];
           if (t > 0) {
             const float* c = a.ckpt + ((size_t)(t - 1) * MB + grow) * S;
 #pragma unroll
             for (int j = 0; j < S; ++j) spre[j] = c[j];
+            if (!A.q_regress)
+#pragma unroll
+              for (int j = 0; j < 2 * NA; ++j) zpre_n[j] = A.z_ckpt[((size_t)(t - 1) * MB + grow) * (2 * NA) + j];
           }
         }
         int kidx = -1;
@@ -503,24 +603,47 @@ __device__ __forceinline__ void run_rollout(const TcArgs& A, uint8_t* smem, Bars
             tmem_ld16(tm_gp + lane_off, gin);
             if (valid) {
               float go[MPG_MAX_OBS];
-              for (int i = 0; i < a.obs_dim; ++i) go[i] = gin[i] * a.obs_scale[i];
+#pragma unroll
+              for (int i = 0; i < MPG_MAX_OBS; ++i) go[i] = i < a.obs_dim ? gin[i] * a.obs_scale[i] : 0.f;
               E::obs_grad_to_state(s, go, a.nfd, g_s);
 #pragma unroll
-              for (int j = 0; j < NA; ++j) g_a[j] += gin[a.obs_dim + j];
+              for (int j = 0; j < NA; ++j)
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
+                  if (i == a.obs_dim + j) g_a[j] += gin[i];
             }
           }
         }
         if (A.q_regress) continue;   // Q regression: no policy part
-        // ---- policy recompute ----
-        if (rowthread) write_pimg(s, nullptr, rec ? slot + SLOT_P : nullptr);
-        policy_forward(zpre, true, rec, slot);
+        // ---- [p|1] image of step t (first-layer recompute for elu'(z1), D1 operand, db2 record) ----
         if (rowthread) {
+          write_pimg(s, nullptr, rec ? slot + SLOT_P : nullptr);
+          tc_fence_before();
+          fence_proxy_async();
+          mbar_arrive(&b->p_full);
+        }
+        // ---- h2 image of step t: store of the forward pass -> activation image.  The image is free once every UMMA
+        // issued so far has completed (previous step's g_p / D1, or the Q part above) and no record store reads it ----
+        if (ROLE == ROLE_MMA) umma_commit(&b->img_empty);
+        if (elected) {
+          bulk_wait_read_all();
+          mbar_arrive(&b->img_empty);
+        }
+        store_pending = false;
+        if (ROLE == ROLE_PRODUCER) {
+          const uint8_t* src = h2tile + (size_t)t * (2 * ACT_SPLIT);
+          mbar_wait(&b->img_empty, sy.i_cnt & 1);
+          mbar_expect_tx(&b->img_full, 2 * ACT_SPLIT);
 #pragma unroll
-          for (int j = 0; j < NA; ++j) act[j] = head_fwd(zpre[j], a.policy_out_tanh, a.action_range);
+          for (int i = 0; i < 8; ++i) bulk_g2s(act_img + i * ACT_BLOCK, src + (size_t)i * ACT_BLOCK, ACT_BLOCK, &b->img_full);
+        }
+        stamp(1);
+        // ---- per-row head and environment adjoint (needs only the checkpoints), under the image load ----
+        if (rowthread) {
           if (t < a.horizon && valid) {
             float Wt = 0.f;
             for (int k = 0; k < a.n_list; ++k) if (a.list[k] > t) Wt += a.list_w[k];
-            env_step_bwd<ENV>(s, act, lam, cscale * Wt * gp * a.rew_scale, g_s, g_a, snext);
+            env_step_bwd<ENV, true>(s, act, lam, cscale * Wt * gp * a.rew_scale, g_s, g_a, snext);
           }
         }
         // ---- delta3, its image, db3 ----
@@ -528,7 +651,7 @@ __device__ __forceinline__ void run_rollout(const TcArgs& A, uint8_t* smem, Bars
           float d3[2] = {0.f, 0.f};
 #pragma unroll
           for (int j = 0; j < NA; ++j) {
-            d3[j] = valid ? g_a[j] * head_grad(zpre[j], a.policy_out_tanh, a.action_range) : 0.f;
+            d3[j] = valid ? g_a[j] * hgrad[j] : 0.f;
             mf->d3s[j * ACT_ROWS + row] = d3[j];
           }
           if (NA == 1) mf->d3s[ACT_ROWS + row] = 0.f;
@@ -544,7 +667,13 @@ __device__ __forceinline__ void run_rollout(const TcArgs& A, uint8_t* smem, Bars
             if (lane == 0) { mf->wsum[warp * 2] = s0; mf->wsum[warp * 2 + 1] = s1; }
           }
         }
-        if (want_dw) d3_issue<ROLE>(b, smem, sy, SM_D3IMG, d3_started, tm_d3);   // dW3 += h2^T delta3
+        if (ROLE == ROLE_EPI) {
+          stamp(2);
+          mbar_wait(&b->img_full, sy.i_cnt & 1);            // h2 image landed
+          stamp(3);
+        }
+        ++sy.i_cnt;
+        if (want_dw) d3_issue<ROLE>(b, smem, sy, SM_D3IMG, d3_started, tm_d3, true);   // dW3 += h2^T delta3
         if (ROLE == ROLE_EPI) {
           if (want_dw) epi_wait_d(b, sy);                   // blocks 0, 1 of the h2 image read by the D3 UMMAs
           epi_bar();
@@ -559,14 +688,14 @@ __device__ __forceinline__ void run_rollout(const TcArgs& A, uint8_t* smem, Bars
         if (ROLE == ROLE_MMA) stamp(4);
         if (ROLE == ROLE_EPI) {
           stamp(6);
-          epi_delta2_blocks(b, mf->W3p, mf->d3s[row], mf->d3s[ACT_ROWS + row], act_img, row, hc, want_dw ? &sy : nullptr);
+          epi_delta2_from_h2(b, mf->W3p, mf->d3s[row], mf->d3s[ACT_ROWS + row], act_img, row, hc, want_dw ? &sy : nullptr);
           stamp(7);
           if (rec) store_image_follow(elected, b, sy, slot + SLOT_D2, act_img);   // delta2 blocks leave behind their K-blocks
           epi_wait_d(b, sy);                                       // g_h1 complete, delta2 image consumed
           stamp(8);
         }
         // z1 recompute stream, g_p following the delta1 blocks, D1 += delta1^T [p|1]
-        bwd_tail_issue<ROLE>(b, smem, sy, A.pol.l1, A.pol.in, t > 0, want_dw, d1_started, tm_z1c, tm_gp, tm_d1);
+        bwd_tail_issue<ROLE>(b, smem, sy, A.pol.l1, A.pol.in, t > 0, want_dw, d1_started, tm_z1c, tm_gp, tm_d1, true);
         if (ROLE == ROLE_EPI) {
           epi_delta1_blocks(b, tm_work + lane_off, tm_z1c + lane_off, act_img, row, hc, rec, elected);
           stamp(9);
@@ -581,7 +710,8 @@ __device__ __forceinline__ void run_rollout(const TcArgs& A, uint8_t* smem, Bars
 #pragma unroll
             for (int j = 0; j < S; ++j) { lam[j] = g_s[j]; snext[j] = s[j]; }
             float go[MPG_MAX_OBS];
-            for (int i = 0; i < a.obs_dim; ++i) go[i] = gin[i] * a.obs_scale[i];
+#pragma unroll
+            for (int i = 0; i < MPG_MAX_OBS; ++i) go[i] = i < a.obs_dim ? gin[i] * a.obs_scale[i] : 0.f;
             E::obs_grad_to_state(s, go, a.nfd, lam);
           }
         }

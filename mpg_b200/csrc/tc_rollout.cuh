@@ -19,8 +19,11 @@ struct TcState {
   float* act_ckpt = nullptr;        // [MPG_MAX_LIST][max_rows][MAX_A]
   float* qtmp = nullptr;            // [max_rows] Q values of the regression pass / of the target evaluations
   float* qtmp2 = nullptr;           // [max_rows] second Q value (double-Q minimum, TD error)
+  float* z_ckpt = nullptr;          // [max_horizon+1][max_rows][2 MAX_A] action and head derivative of every step (BPTT)
   uint8_t* store = nullptr;         // dW operand store (allocated on first use, grows)
   size_t store_bytes = 0;
+  uint8_t* h2store = nullptr;       // h2 images of the forward pass, [tile][step][128 KB] (allocated on first use, grows)
+  size_t h2store_bytes = 0;
 };
 
 template <typename K>
@@ -37,6 +40,7 @@ inline bool tc_init(TcState& t, const mpg_config& cfg, int /*sms*/, size_t& ws_b
   };
   bool ok = alloc((void**)&t.scratch_img, tc::BIG_IMAGE_BYTES)
             && alloc((void**)&t.act_ckpt, (size_t)MPG_MAX_LIST * cfg.max_rows * MAX_A * sizeof(float))
+            && alloc((void**)&t.z_ckpt, (size_t)(cfg.max_horizon + 1) * cfg.max_rows * 2 * MAX_A * sizeof(float))
             && alloc((void**)&t.qtmp, (size_t)cfg.max_rows * sizeof(float))
             && alloc((void**)&t.qtmp2, (size_t)cfg.max_rows * sizeof(float));
   for (int n = 0; n < MPG_NUM_NETS && ok; ++n)
@@ -59,7 +63,7 @@ inline bool tc_init(TcState& t, const mpg_config& cfg, int /*sms*/, size_t& ws_b
 }
 
 inline void tc_destroy(TcState& t) {
-  cudaFree(t.scratch_img); cudaFree(t.act_ckpt); cudaFree(t.qtmp); cudaFree(t.qtmp2); cudaFree(t.store);
+  cudaFree(t.scratch_img); cudaFree(t.act_ckpt); cudaFree(t.z_ckpt); cudaFree(t.h2store); cudaFree(t.qtmp); cudaFree(t.qtmp2); cudaFree(t.store);
   for (int n = 0; n < MPG_NUM_NETS; ++n) {
     cudaFree(t.nets[n].big_fwd); cudaFree(t.nets[n].big_dx); cudaFree(t.nets[n].l1); cudaFree(t.nets[n].in);
   }
@@ -85,14 +89,16 @@ inline tc::TcNet tc_net(const TcState& t, int net, const float* flat, int in_dim
   return n;
 }
 
-inline bool tc_ensure_store(TcState& t, size_t bytes) {
-  if (bytes <= t.store_bytes) return true;
-  cudaFree(t.store);
-  t.store = nullptr; t.store_bytes = 0;
-  if (cudaMalloc((void**)&t.store, bytes) != cudaSuccess) { cudaGetLastError(); return false; }
-  t.store_bytes = bytes;
+inline bool tc_ensure_buf(uint8_t*& buf, size_t& have, size_t bytes) {
+  if (bytes <= have) return true;
+  cudaFree(buf);
+  buf = nullptr; have = 0;
+  if (cudaMalloc((void**)&buf, bytes) != cudaSuccess) { cudaGetLastError(); return false; }
+  have = bytes;
   return true;
 }
+inline bool tc_ensure_store(TcState& t, size_t bytes) { return tc_ensure_buf(t.store, t.store_bytes, bytes); }
+inline bool tc_ensure_h2store(TcState& t, size_t bytes) { return tc_ensure_buf(t.h2store, t.h2store_bytes, bytes); }
 
 template <bool BWD>
 inline cudaError_t tc_launch_rollout(int env, const tc::TcArgs& a, int grid, cudaStream_t st) {

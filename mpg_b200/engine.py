@@ -141,8 +141,22 @@ class Engine:
         return torch.empty(*shape, dtype=torch.float32, device=self.device)
 
     # ------------------------------------------------------------------ weights
+    def net_shapes(self, net):
+        """Keras shapes [W1,b1,W2,b2,W3,b3] of slot `net` (model.py:20-43: kernels are (in, out))."""
+        is_pol = net in (_lib.NET_POLICY, _lib.NET_POLICY_TARGET)
+        i, o, h = (self.obs_dim, 2 * self.act_dim, self.cfg.hidden) if is_pol else (self.obs_dim + self.act_dim, 1, self.cfg.hidden)
+        return [(i, h), (h,), (h, h), (h,), (h, o), (o,)]
+
     def set_net_weights(self, net, weights):
-        """weights: [W1,b1,W2,b2,W3,b3] numpy arrays or tensors in Keras layout (model.py:20-43)."""
+        """weights: [W1,b1,W2,b2,W3,b3] numpy arrays or tensors in Keras layout (model.py:20-43).
+        Like Keras' set_weights, a wrong count or shape raises ValueError (the C side copies fixed sizes)."""
+        weights = list(weights)
+        want = self.net_shapes(net)
+        if len(weights) != 6:
+            raise ValueError(f'net {net}: expected 6 weight arrays [W1,b1,W2,b2,W3,b3], got {len(weights)}')
+        for k, (w, shp) in enumerate(zip(weights, want)):
+            if tuple(np.shape(w)) != shp:
+                raise ValueError(f'net {net}: weight {k} has shape {tuple(np.shape(w))}, expected {shp}')
         ts = [self.dev(w) for w in weights]
         arr = (ctypes.c_void_p * 6)(*[t.data_ptr() for t in ts])
         self._check(self.lib.mpg_set_weights(self.h, net, arr, self.stream))

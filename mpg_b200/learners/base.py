@@ -6,7 +6,7 @@ import torch
 from ..engine import Engine  # noqa: F401  (documentation of the dependency)
 from .. import parallel
 from ..preprocessor import Preprocessor
-from ..utils.misc import TimerStat
+from ..utils.misc import CudaTimerStat
 
 
 def rule_based_weights(ite, total_ite, eta, rollout_list):
@@ -54,9 +54,10 @@ class LearnerBase(object):
         self.preprocessor = Preprocessor(self.args.obs_dim, self.args.obs_ptype, self.args.rew_ptype,
                                          self.args.obs_scale, self.args.rew_scale, self.args.rew_shift,
                                          gamma=self.args.gamma)
-        self.policy_gradient_timer = TimerStat()
-        self.q_gradient_timer = TimerStat()
-        self.target_timer = TimerStat()
+        # device time of each section (CUDA events), read after the update's single D2H copy
+        self.policy_gradient_timer = CudaTimerStat()
+        self.q_gradient_timer = CudaTimerStat()
+        self.target_timer = CudaTimerStat()
         self.stats = {}
         self.info_for_buffer = {}
         # noise of the model rollout: None -> in-kernel Philox keyed by (seed, global row, step);
