@@ -55,8 +55,10 @@ struct Bars {
   uint64_t acc_done;     // the D1 accumulation UMMAs have read the delta1 / [p|1] images
   uint64_t kb_done[4];   // big GEMM: the UMMAs of K-block kb are complete (block kb of the A image is no longer read)
   uint64_t p_full;       // BPTT: the [p|1] image of this step is written (row threads -> mma, first-layer recompute)
-  uint64_t img_empty;    // BPTT: nothing reads the activation image any more (mma commit + elected epilogue thread)
-  uint64_t img_full;     // BPTT: the h2 image of this step has landed in the activation image (TMA complete_tx)
+  uint64_t img_empty[2]; // BPTT: nothing reads 128-feature half h of the activation image any more (mma commit + elected
+                         // epilogue thread): the h2 image of the next step may land there
+  uint64_t img_full[2];  // BPTT: half h of the h2 image of this step has landed (TMA complete_tx)
+  uint64_t gp_full;      // the input gradient g_p is complete (mma -> row warps; the epilogue warps use d_full)
   uint32_t tmem_base;
 };
 static_assert(sizeof(Bars) <= 256, "BARS region too small");
@@ -71,9 +73,10 @@ struct Sync {
   uint32_t k_cnt = 0;    // big GEMMs issued so far (kb_done[] phases, epilogue side)
   uint32_t p_cnt = 0;    // p_full phases seen
   uint32_t i_cnt = 0;    // img_empty / img_full phases seen (h2 image loads)
+  uint32_t gp_cnt = 0;   // gp_full phases seen (row warps)
 };
 
-enum Role { ROLE_EPI = 0, ROLE_PRODUCER = 1, ROLE_MMA = 2 };
+enum Role { ROLE_EPI = 0, ROLE_PRODUCER = 1, ROLE_MMA = 2, ROLE_ROW = 3 };
 
 // ---- producer: stream `nstages` stages of `bytes` each ------------------------------------------------
 __device__ __forceinline__ void produce(Bars* b, uint8_t* ring, Sync& s, const uint8_t* gsrc, int nstages, uint32_t bytes) {
@@ -269,7 +272,7 @@ __device__ __forceinline__ void gemm_issue(int kind, Bars* b, uint8_t* smem, Syn
     else mma_in(b, base + SmemMap::ACT, base + SmemMap::RING, s, d_tmem);
     mma_publish_d(b);
   } else {
-    if (kind == 1) epi_publish_a(b);
+    if (kind == 1) epi_publish_a(b);     // epilogue warps: TMEM reads done; row warps: [p|a|1] image written
     if (kind == 0) ++s.k_cnt;
   }
 }
@@ -313,7 +316,7 @@ __device__ __forceinline__ void fwd_pair_issue(Bars* b, uint8_t* smem, Sync& s, 
 template <int ROLE>
 __device__ __forceinline__ void bwd_tail_issue(Bars* b, uint8_t* smem, Sync& s, const uint8_t* l1_img, const uint8_t* in_img,
                                                bool do_gp, bool do_d1, bool& d1_started, uint32_t tm_z1c, uint32_t tm_gp,
-                                               uint32_t tm_d1, bool wait_p = false) {
+                                               uint32_t tm_d1, bool wait_p = false, bool release_img = false) {
   if (ROLE == ROLE_PRODUCER) {
     produce(b, smem + SmemMap::RING, s, l1_img, 1, 16384);
     produce_pad(b, s);
@@ -358,7 +361,10 @@ __device__ __forceinline__ void bwd_tail_issue(Bars* b, uint8_t* smem, Sync& s, 
       } else {
         tc_fence_after();
       }
-      if (do_d1 && kb == 1) mma_acc16_half(act_addr, p_addr, tm_d1, 0, d1_started);
+      if (kb == 1) {
+        if (do_d1) mma_acc16_half(act_addr, p_addr, tm_d1, 0, d1_started);
+        if (release_img) umma_commit(&b->img_empty[0]);   // blocks 0, 1 of the image have been read for the last time
+      }
     }
     ++s.g_cnt;
     if (do_gp) {
@@ -366,12 +372,14 @@ __device__ __forceinline__ void bwd_tail_issue(Bars* b, uint8_t* smem, Sync& s, 
       ++s.stage;
       consume_pad(b, s);
       mma_publish_d(b);
+      umma_commit(&b->gp_full);
     }
     if (do_d1) {
       mma_acc16_half(act_addr, p_addr, tm_d1, 1, d1_started);
       d1_started = true;
       umma_commit(&b->acc_done);
     }
+    if (release_img) umma_commit(&b->img_empty[1]);
   }
 }
 // D3 += h2^T [delta3|0]: the epilogue publishes (h2 image + delta3 image written); the UMMAs complete on d_full
@@ -386,11 +394,15 @@ __device__ __forceinline__ void d3_issue(Bars* b, uint8_t* smem, Sync& s, uint32
     tc_fence_after();
     mma_acc16_half(base + SmemMap::ACT, base + d3_off, tm_d3, 0, d3_started, lin);
     mma_publish_d(b);                      // blocks 0, 1 of the h2 image may be overwritten
+    if (lin) {                             // BPTT: the second half of the h2 image arrives separately
+      mbar_wait(&b->img_full[1], (s.i_cnt - 1) & 1);
+      tc_fence_after();
+    }
     mma_acc16_half(base + SmemMap::ACT, base + d3_off, tm_d3, 1, d3_started, lin);
     mma_publish_d(b);                      // blocks 2, 3
     d3_started = true;
-  } else if (ROLE == ROLE_EPI) {
-    epi_publish_a(b);
+  } else if (ROLE == ROLE_EPI || ROLE == ROLE_ROW) {
+    epi_publish_a(b);                      // epilogue warps: h2 image in place; row warps: delta3 image written
   }
 }
 // compatibility wrapper: issue + wait, A image published as a whole (self test)
@@ -403,32 +415,32 @@ __device__ __forceinline__ void gemm(int kind, Bars* b, uint8_t* smem, Sync& s, 
 }
 
 // ---- CTA prologue / epilogue -----------------------------------------------------------------------------
-__device__ __forceinline__ Bars* cta_setup(uint8_t* smem) {
+__device__ __forceinline__ Bars* cta_setup(uint8_t* smem, int a_full_count = EPI_THREADS, int mma_warp = EPI_WARPS + 1) {
   Bars* b = reinterpret_cast<Bars*>(smem + SmemMap::BARS);
   const int warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) {
     for (int i = 0; i < NSLOT; ++i) { mbar_init(&b->full[i], 1); mbar_init(&b->empty[i], 1); }
-    mbar_init(&b->a_full, EPI_THREADS);
+    mbar_init(&b->a_full, a_full_count);
     for (int i = 0; i < 4; ++i) mbar_init(&b->a_blk[i], EPI_THREADS);
     mbar_init(&b->d_full, 1);
     for (int i = 0; i < 2; ++i) { mbar_init(&b->z_full[i], 1); mbar_init(&b->z_empty[i], EPI_THREADS); }
     mbar_init(&b->acc_done, 1);
     for (int i = 0; i < 4; ++i) mbar_init(&b->kb_done[i], 1);
     mbar_init(&b->p_full, ACT_ROWS);
-    mbar_init(&b->img_empty, 2);
-    mbar_init(&b->img_full, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&b->img_empty[i], 2); mbar_init(&b->img_full[i], 1); }
+    mbar_init(&b->gp_full, 1);
     fence_barrier_init();
   }
-  if (warp == EPI_WARPS + 1) tmem_alloc(&b->tmem_base, TMEM_COLS);
+  if (warp == mma_warp) tmem_alloc(&b->tmem_base, TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   return b;
 }
-__device__ __forceinline__ void cta_teardown(Bars* b) {
+__device__ __forceinline__ void cta_teardown(Bars* b, int mma_warp = EPI_WARPS + 1) {
   tc_fence_before();
   __syncthreads();
-  if ((threadIdx.x >> 5) == EPI_WARPS + 1) tmem_dealloc(b->tmem_base, TMEM_COLS);
+  if ((threadIdx.x >> 5) == mma_warp) tmem_dealloc(b->tmem_base, TMEM_COLS);
 }
 
 // ---- global weight-image packing (run once per set_weights) ------------------------------------------------

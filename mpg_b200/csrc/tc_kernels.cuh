@@ -237,10 +237,13 @@ __device__ MPG_EPI_INLINE void epi_delta2_blocks(Bars* b, const float* W3, float
 // 16 KB per split, so the conversion is in place block by block: every thread reads its part of block kb, barrier,
 // every thread writes.
 __device__ MPG_EPI_INLINE void epi_delta2_from_h2(Bars* b, const float* W3, float d30, float d31, uint8_t* act, int row, int hc,
-                                                  Sync* wait_half1 = nullptr) {
+                                                  uint32_t img_parity, Sync* wait_half1 = nullptr) {
   for (int kb = 0; kb < 4; ++kb) {
     const int c0 = kb * 64 + hc * 16;
-    if (kb == 2 && wait_half1) epi_wait_d(b, *wait_half1);   // the D3 UMMAs have read blocks 2, 3 of the h2 image
+    if (kb == 2) {
+      mbar_wait(&b->img_full[1], img_parity);                 // second half of the h2 image has landed
+      if (wait_half1) epi_wait_d(b, *wait_half1);             // the D3 UMMAs have read blocks 2, 3 of the h2 image
+    }
     float v[16];
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
@@ -268,7 +271,7 @@ __device__ MPG_EPI_INLINE void epi_delta2_from_h2(Bars* b, const float* W3, floa
 }
 // delta1 = g_h1 (TMEM work) * elu'(z1) (recomputed, streamed through the chunk buffers) -> delta1 image
 __device__ MPG_EPI_INLINE void epi_delta1_blocks(Bars* b, uint32_t tm_work_lane, uint32_t tm_zc_lane, uint8_t* act, int row,
-                                                 int hc, bool draining = false, bool elected = false) {
+                                                 int hc, bool draining = false, bool elected = false, bool release_img = false) {
   for (int kb = 0; kb < 4; ++kb) {
     const int c0 = kb * 64 + hc * 16;
     float g[16], z[16];
@@ -282,6 +285,9 @@ __device__ MPG_EPI_INLINE void epi_delta1_blocks(Bars* b, uint32_t tm_work_lane,
     act_store8(act, act + ACT_SPLIT, row, c0 >> 3, g);
     act_store8(act, act + ACT_SPLIT, row, (c0 >> 3) + 1, g + 8);
     epi_block_done(b, kb);
+    // the record store has read blocks 0..kb of the old image (store_wait_block above): with the mma thread's commit
+    // behind the UMMAs that read the new one, half kb / 2 is free for the h2 image of the next step
+    if (release_img && elected && (kb & 1)) mbar_arrive(&b->img_empty[kb >> 1]);
   }
 }
 // [x0..x15] -> INTERLEAVE image row (hi | lo 4 KB apart)
@@ -304,15 +310,35 @@ __device__ __forceinline__ void write_row16(uint8_t* img, int row, const float* 
   }
 }
 
+// [d0, d1, 0 ...] -> first 16-byte chunk of row `row` of the delta3 image (hi | lo); the second chunk stays zero
+__device__ __forceinline__ void write_d3(uint8_t* img, int row, float d0, float d1) {
+  uint4 h = make_uint4(0u, 0u, 0u, 0u), l = make_uint4(0u, 0u, 0u, 0u);
+  split2(d0, d1, h.x, l.x);
+  *reinterpret_cast<uint4*>(img + il_chunk_off(row, 0)) = h;
+  *reinterpret_cast<uint4*>(img + 4096 + il_chunk_off(row, 0)) = l;
+}
 
+// named barriers between the epilogue warps (512 threads) and the row warps (128 threads)
+__device__ __forceinline__ void bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+constexpr int BAR_PART = 2;   // epilogue -> row: partial output-layer dots (MiscF::part) written
+constexpr int BAR_D3 = 3;     // row -> epilogue: delta3 (MiscF::d3s) written
+constexpr int BAR_ROW = 4;    // row warps among themselves
+constexpr int ROW_THREADS = ACT_ROWS;
+constexpr int XCHG_THREADS = EPI_THREADS + ROW_THREADS;
+
+// One schedule, four roles.  ROLE_EPI: 16 warps, thread = (row, 64-column quarter), all 128 x 256 element-wise work.
+// ROLE_ROW: 4 warps, thread = trajectory: environment step and adjoint, output head, [p|a|1] / delta3 images,
+// checkpoints, returns -- the scalar recurrence lives in registers of threads that hold nothing else.
+// ROLE_PRODUCER / ROLE_MMA: one thread each.
 template <int ENV, bool BWD, int ROLE>
 __device__ __forceinline__ void run_rollout(const TcArgs& A, uint8_t* smem, Bars* b) {
   using E = Env<ENV>;
   constexpr int S = E::S, NA = E::A;
   const RolloutArgs& a = A.r;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int row = (warp & 3) * 32 + lane, hc = (warp >> 2) & 3;   // hc: column quarter of this warp
-  const bool rowthread = (ROLE == ROLE_EPI) && hc == 0;
+  const int row = (warp & 3) * 32 + lane, hc = (warp >> 2) & 3;   // hc: column quarter of an epilogue warp
+  const bool rowthread = (ROLE == ROLE_ROW);
   const bool elected = (ROLE == ROLE_EPI) && tid == 0;
   const int MB = a.rows * a.M;
   const int ntiles = (MB + ACT_ROWS - 1) / ACT_ROWS;
@@ -327,21 +353,25 @@ __device__ __forceinline__ void run_rollout(const TcArgs& A, uint8_t* smem, Bars
   const bool store_dw = BWD && A.store != nullptr;
   Sync sy;
   bool d1_started = false, d3_started = false;   // mma role: the persistent accumulators hold a value
-  bool d1_pending = false, any_dw = false;       // epilogue role: D1 UMMAs in flight / accumulators were used
+  bool d1_pending = false, any_dw = false;       // D1 UMMAs in flight / accumulators were used
   bool store_pending = false;                    // epilogue role: a record store still reads the activation image
-  // the D1 UMMAs of the previous step read the delta1 and [p|1] images: wait before either is rewritten
+  // The D1 UMMAs of a step read the delta1 and [p|1] images.  The activation image is protected by img_empty (mma commit);
+  // the [p|1] image is rewritten by the row warps, which wait for acc_done right before they do.  The epilogue warps only
+  // count the phases and wait for the last one before they read the accumulators out.
+  uint32_t acc_issued = 0;
   auto acc_wait = [&]() {
-    if (ROLE == ROLE_EPI && d1_pending) {
+    if (ROLE == ROLE_ROW && d1_pending) {
       mbar_wait(&b->acc_done, sy.acc_cnt & 1);
       ++sy.acc_cnt;
-      d1_pending = false;
     }
+    d1_pending = false;
   };
-  float db3acc[2] = {0.f, 0.f};
+  float db3acc[2] = {0.f, 0.f};                  // row warps: sum of this row's delta3 over steps and tiles
   int prof_t = -1;   // step being traced
   auto stamp = [&](int id) {
-    if (A.prof && blockIdx.x == 0 && prof_t >= 0 && ((ROLE == ROLE_EPI && tid == 0) || ROLE == ROLE_MMA))
-      A.prof[(ROLE == ROLE_MMA ? 32 : 0) + id] = clock64();
+    if (A.prof && blockIdx.x == 0 && prof_t >= 0
+        && ((ROLE == ROLE_EPI && tid == 0) || ROLE == ROLE_MMA || (ROLE == ROLE_ROW && tid == EPI_THREADS)))
+      A.prof[(ROLE == ROLE_MMA ? 32 : (ROLE == ROLE_ROW ? 64 : 0)) + id] = clock64();
   };
 
   const int tile_end = A.tile1 > 0 && A.tile1 < ntiles ? A.tile1 : ntiles;
@@ -363,27 +393,43 @@ __device__ __forceinline__ void run_rollout(const TcArgs& A, uint8_t* smem, Bars
     }
     float rsum = 0.f, gpow = 1.f;
 
-    // [sigma*obs(s) | act | 0.. | 1] -> p image
+    // [sigma*obs(s) | act | 0.. | 1] -> p image (row warps)
     auto write_pimg = [&](const float* st, const float* act_or_null, uint8_t* gimg = nullptr) {
-      // every index below is a compile-time constant (fixed trip counts + predicates): x[] and o[] stay in registers
-      float x[16], o[MPG_MAX_OBS];
+      // every index below is a compile-time constant (fixed trip counts + predicates): o[] stays in registers, and the
+      // image row is produced one 8-element chunk at a time
+      float o[MPG_MAX_OBS];
 #pragma unroll
       for (int i = 0; i < MPG_MAX_OBS; ++i) o[i] = 0.f;
       E::get_obs(st, o, a.nfd);
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        float v = i < a.obs_dim ? o[i] * a.obs_scale[i] : 0.f;
-        if (act_or_null) {
+      for (int kh = 0; kh < 2; ++kh) {
+        float x[8];
 #pragma unroll
-          for (int j = 0; j < NA; ++j)
-            if (i == a.obs_dim + j) v = act_or_null[j];
+        for (int e = 0; e < 8; ++e) {
+          const int i = kh * 8 + e;
+          float v = i < a.obs_dim ? o[i] * a.obs_scale[i] : 0.f;
+          if (act_or_null) {
+#pragma unroll
+            for (int j = 0; j < NA; ++j)
+              if (i == a.obs_dim + j) v = act_or_null[j];
+          }
+          x[e] = i == BIAS_K ? 1.f : v;
         }
-        x[i] = v;
+        uint4 h, l;
+        split2(x[0], x[1], h.x, l.x);
+        split2(x[2], x[3], h.y, l.y);
+        split2(x[4], x[5], h.z, l.z);
+        split2(x[6], x[7], h.w, l.w);
+        const uint32_t off = il_chunk_off(row, kh);
+        *reinterpret_cast<uint4*>(p_img + off) = h;
+        *reinterpret_cast<uint4*>(p_img + 4096 + off) = l;
+        if (gimg) {
+          *reinterpret_cast<uint4*>(gimg + off) = h;
+          *reinterpret_cast<uint4*>(gimg + 4096 + off) = l;
+        }
       }
-      x[BIAS_K] = 1.f;
-      write_row16(p_img, row, x, gimg);
     };
-    // policy forward on the current p image: returns pre-activations of the head for the row thread.
+    // policy forward on the current p image: the row thread gets the pre-activations of the head.
     // The layer-2 UMMAs are issued K-block by K-block while the epilogue is still producing h1.  In the gradient
     // kernel h2 goes to the h2 store of this (tile, step) and, for the steps whose weight gradient is wanted (slot),
     // the h1 image leaves for the dW operand store behind the K-blocks of the GEMM.
@@ -403,13 +449,14 @@ __device__ __forceinline__ void run_rollout(const TcArgs& A, uint8_t* smem, Bars
         stamp(20);
         mf->part[(hc * 2 + 0) * ACT_ROWS + row] = p0;
         mf->part[(hc * 2 + 1) * ACT_ROWS + row] = p1;
-        epi_bar();
-        if (rowthread) {
+        bar_arrive(BAR_PART, XCHG_THREADS);
+      }
+      if (rowthread) {
+        bar_sync(BAR_PART, XCHG_THREADS);
 #pragma unroll
-          for (int j = 0; j < NA; ++j)
-            zpre[j] = mf->b3[j] + ((mf->part[(0 * 2 + j) * ACT_ROWS + row] + mf->part[(1 * 2 + j) * ACT_ROWS + row])
-                                   + (mf->part[(2 * 2 + j) * ACT_ROWS + row] + mf->part[(3 * 2 + j) * ACT_ROWS + row]));
-        }
+        for (int j = 0; j < NA; ++j)
+          zpre[j] = mf->b3[j] + ((mf->part[(0 * 2 + j) * ACT_ROWS + row] + mf->part[(1 * 2 + j) * ACT_ROWS + row])
+                                 + (mf->part[(2 * 2 + j) * ACT_ROWS + row] + mf->part[(3 * 2 + j) * ACT_ROWS + row]));
       }
     };
     // Q forward on the current [p|a|1] image: returns Q for the row thread
@@ -429,9 +476,12 @@ __device__ __forceinline__ void run_rollout(const TcArgs& A, uint8_t* smem, Bars
           epi_hidden2(tm_work + lane_off, mf->b2q, mf->W3q, hc, p0, p1);
         }
         mf->part[(hc * 2 + 0) * ACT_ROWS + row] = p0;
-        epi_bar();
-        if (rowthread) qv = mf->b3[2] + ((mf->part[0 * ACT_ROWS + row] + mf->part[2 * ACT_ROWS + row])
-                                         + (mf->part[4 * ACT_ROWS + row] + mf->part[6 * ACT_ROWS + row]));
+        bar_arrive(BAR_PART, XCHG_THREADS);
+      }
+      if (rowthread) {
+        bar_sync(BAR_PART, XCHG_THREADS);
+        qv = mf->b3[2] + ((mf->part[0 * ACT_ROWS + row] + mf->part[2 * ACT_ROWS + row])
+                          + (mf->part[4 * ACT_ROWS + row] + mf->part[6 * ACT_ROWS + row]));
       }
       return qv;
     };
@@ -446,7 +496,7 @@ __device__ __forceinline__ void run_rollout(const TcArgs& A, uint8_t* smem, Bars
       // steps whose weight gradient is wanted leave their dW2 operands (h1 now, delta2 during BPTT) in the operand store
       const bool rec_f = store_dw && !A.q_regress && (a.full_bptt || t == 0);
       uint8_t* slot = rec_f ? A.store + ((size_t)tile * A.store_steps + (a.full_bptt ? t : 0)) * SLOT_BYTES : nullptr;
-      if (ROLE == ROLE_EPI) {
+      if (ROLE == ROLE_EPI || ROLE == ROLE_ROW) {
         if (tile == A.tile0 + (int)blockIdx.x && t == 2) { prof_t = t; stamp(16); }
         else if (prof_t >= 0) { stamp(22); prof_t = -1; }
       }
@@ -473,18 +523,19 @@ __device__ __forceinline__ void run_rollout(const TcArgs& A, uint8_t* smem, Bars
               A.z_ckpt[((size_t)t * MB + grow) * (2 * NA) + NA + j] = hg[j];
             }
         }
-      } else if (rowthread && valid) {
+      } else if (valid) {
 #pragma unroll
         for (int j = 0; j < NA; ++j) act[j] = a.start_actions[(size_t)i_idx * NA + j];
       }
-      if (rowthread && valid && a.traj_act)
+      if (valid && a.traj_act)
 #pragma unroll
         for (int j = 0; j < NA; ++j) a.traj_act[((size_t)t * MB + grow) * NA + j] = act[j];
-      int kidx = -1;
-      for (int k = 0; k < a.n_list; ++k) if (a.list[k] == t) kidx = k;
+      int kidx = -1;   // fixed trip count: the list is read with immediate constant-bank offsets (an indexed LDC is slow)
+#pragma unroll
+      for (int k = 0; k < MPG_MAX_LIST; ++k) if (k < a.n_list && a.list[k] == t) kidx = k;
       if (kidx >= 0) {
         float qv = 0.f;
-        if (BWD && rowthread && valid)
+        if (BWD && valid)
 #pragma unroll
           for (int j = 0; j < NA; ++j) A.act_ckpt[((size_t)kidx * MB + grow) * NA + j] = act[j];
         if (a.has_q) {
@@ -520,7 +571,7 @@ __device__ __forceinline__ void run_rollout(const TcArgs& A, uint8_t* smem, Bars
       for (int j = 0; j < S; ++j) { lam[j] = 0.f; snext[j] = s[j]; spre[j] = s[j]; }   // s == s_horizon here
 #pragma unroll
       for (int j = 0; j < 2 * NA; ++j)
-        zpre_n[j] = (rowthread && valid && !A.q_regress) ? A.z_ckpt[((size_t)a.horizon * MB + grow) * (2 * NA) + j] : 0.f;
+        zpre_n[j] = (valid && !A.q_regress) ? A.z_ckpt[((size_t)a.horizon * MB + grow) * (2 * NA) + j] : 0.f;
       for (int t = a.horizon; t >= 0; --t) {
         float gp = 1.f;
         for (int i = 0; i < t; ++i) gp *= a.gamma;
@@ -534,8 +585,8 @@ __device__ __forceinline__ void run_rollout(const TcArgs& A, uint8_t* smem, Bars
         for (int j = 0; j < NA; ++j) { g_a[j] = 0.f; act[j] = zpre_n[j]; hgrad[j] = zpre_n[NA + j]; }
 #pragma unroll
         for (int j = 0; j < S; ++j) g_s[j] = 0.f;
-        if (rowthread && valid) {
-          // s_t and the head pre-activations were prefetched during the previous iteration; issue the loads of step
+        if (valid) {
+          // s_t and the head values were prefetched during the previous iteration; issue the loads of step
           // t-1 now so that their global-memory latency hides behind this step
 #pragma unroll
           for (int j = 0; j < S; ++j) s[j] = spre[j];
@@ -549,41 +600,63 @@ __device__ __forceinline__ void run_rollout(const TcArgs& A, uint8_t* smem, Bars
           }
         }
         int kidx = -1;
-        for (int k = 0; k < a.n_list; ++k) if (a.list[k] == t) kidx = k;
-        acc_wait();
+#pragma unroll
+        for (int k = 0; k < MPG_MAX_LIST; ++k) if (k < a.n_list && a.list[k] == t) kidx = k;
         if (want_dw) any_dw = true;
         // ---- Q input gradient at the list steps: upstream c w_k gamma^t on Q1(p_t, a_t) ----
-        if (kidx >= 0 && a.has_q && (a.list_w[kidx] != 0.f || A.q_regress)) {
+        float w_k = 0.f;
+#pragma unroll
+        for (int k = 0; k < MPG_MAX_LIST; ++k) if (k == kidx) w_k = a.list_w[k];
+        // does step tt start with a Q part (which uses the activation image before the policy part does)?
+        auto q_part_at = [&](int tt) {
+          bool q = false;
+#pragma unroll
+          for (int k = 0; k < MPG_MAX_LIST; ++k) if (k < a.n_list && a.list[k] == tt && a.list_w[k] != 0.f) q = true;
+          return q && a.has_q;
+        };
+        // early: the h2 image of this step was requested during the previous one; early_next: request the next one
+        const bool early = t < a.horizon && !q_part_at(t);
+        const bool early_next = t > 0 && !q_part_at(t - 1) && !A.q_regress;
+        auto load_h2 = [&](int tt) {      // producer: both halves of the h2 image of step tt, each as soon as it is free
+          const uint8_t* src = h2tile + (size_t)tt * (2 * ACT_SPLIT);
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            mbar_wait(&b->img_empty[h], sy.i_cnt & 1);
+            mbar_expect_tx(&b->img_full[h], ACT_SPLIT);
+#pragma unroll
+            for (int sp = 0; sp < 2; ++sp)
+#pragma unroll
+              for (int k = 0; k < 2; ++k) {
+                const size_t off = (size_t)sp * ACT_SPLIT + (size_t)(2 * h + k) * ACT_BLOCK;
+                bulk_g2s(act_img + off, src + off, ACT_BLOCK, &b->img_full[h]);
+              }
+          }
+        };
+        if (kidx >= 0 && a.has_q && (w_k != 0.f || A.q_regress)) {
           const bool reg = A.q_regress != 0;      // regression: weight gradients of the Q net, no input gradient
           uint8_t* qslot = (reg && store_dw) ? A.store + (size_t)tile * SLOT_BYTES : nullptr;
           if (rowthread) {
             float ak[NA];
 #pragma unroll
             for (int j = 0; j < NA; ++j) ak[j] = valid ? A.act_ckpt[((size_t)kidx * MB + grow) * NA + j] : 0.f;
+            acc_wait();
             write_pimg(s, ak, qslot ? qslot + SLOT_P : nullptr);
           }
           const float qv = q_forward(true, qslot);         // h2q image in ACT
-          if (ROLE == ROLE_EPI && rowthread) {
+          if (rowthread) {
             // upstream on Q: policy loss c w_k gamma^t, or the regression residual (Q - target) / B_global
-            const float up = !valid ? 0.f : (reg ? (qv - A.q_target[i_idx]) * A.q_inv_rows : cscale * a.list_w[kidx] * gp);
+            const float up = !valid ? 0.f : (reg ? (qv - A.q_target[i_idx]) * A.q_inv_rows : cscale * w_k * gp);
             mf->d3s[row] = up;
             if (reg) {
-              float x[16];
-#pragma unroll
-              for (int i = 0; i < 16; ++i) x[i] = 0.f;
-              x[0] = up;
-              write_row16(d3_img, row, x);
-              float s0 = up;
-#pragma unroll
-              for (int o = 16; o > 0; o >>= 1) s0 += __shfl_xor_sync(0xffffffffu, s0, o);
-              if (lane == 0) mf->wsum[warp * 2] = s0;
+              write_d3(d3_img, row, up, 0.f);
+              db3acc[0] += up;
             }
+            bar_arrive(BAR_D3, XCHG_THREADS);
           }
           if (reg) d3_issue<ROLE>(b, smem, sy, SM_D3IMG, d3_started, tm_d3);   // dW3q += h2q^T delta3
           if (ROLE == ROLE_EPI) {
             if (reg) epi_wait_d(b, sy);                    // blocks 0, 1 of the h2q image read by the D3 UMMAs
-            epi_bar();
-            if (reg && tid == 0) db3acc[0] += (mf->wsum[0] + mf->wsum[2]) + (mf->wsum[4] + mf->wsum[6]);
+            bar_sync(BAR_D3, XCHG_THREADS);
           }
           gemm_issue<ROLE>(0, b, smem, sy, A.q.big_dx, tm_work);  // g_h1q, K-blocks issued as delta2 blocks appear
           if (ROLE == ROLE_EPI) {
@@ -596,9 +669,12 @@ __device__ __forceinline__ void run_rollout(const TcArgs& A, uint8_t* smem, Bars
             if (qslot) store_wait(elected);                // delta2 image read out before it is overwritten
             epi_delta1_blocks(b, tm_work + lane_off, tm_z1c + lane_off, act_img, row, hc);
             if (!reg) epi_wait_d(b, sy);
-            else d1_pending = true;
           }
+          if (reg) { d1_pending = true; ++acc_issued; }
           if (rowthread && !reg) {
+            mbar_wait(&b->gp_full, sy.gp_cnt & 1);
+            ++sy.gp_cnt;
+            tc_fence_after();
             float gin[16];
             tmem_ld16(tm_gp + lane_off, gin);
             if (valid) {
@@ -615,39 +691,17 @@ __device__ __forceinline__ void run_rollout(const TcArgs& A, uint8_t* smem, Bars
           }
         }
         if (A.q_regress) continue;   // Q regression: no policy part
-        // ---- [p|1] image of step t (first-layer recompute for elu'(z1), D1 operand, db2 record) ----
+        // ---- per-row environment adjoint and delta3: they need only lambda and the checkpoints, so the row warps
+        // run them first; the dX chain of the epilogue warps hangs on delta3 ----
         if (rowthread) {
-          write_pimg(s, nullptr, rec ? slot + SLOT_P : nullptr);
-          tc_fence_before();
-          fence_proxy_async();
-          mbar_arrive(&b->p_full);
-        }
-        // ---- h2 image of step t: store of the forward pass -> activation image.  The image is free once every UMMA
-        // issued so far has completed (previous step's g_p / D1, or the Q part above) and no record store reads it ----
-        if (ROLE == ROLE_MMA) umma_commit(&b->img_empty);
-        if (elected) {
-          bulk_wait_read_all();
-          mbar_arrive(&b->img_empty);
-        }
-        store_pending = false;
-        if (ROLE == ROLE_PRODUCER) {
-          const uint8_t* src = h2tile + (size_t)t * (2 * ACT_SPLIT);
-          mbar_wait(&b->img_empty, sy.i_cnt & 1);
-          mbar_expect_tx(&b->img_full, 2 * ACT_SPLIT);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) bulk_g2s(act_img + i * ACT_BLOCK, src + (size_t)i * ACT_BLOCK, ACT_BLOCK, &b->img_full);
-        }
-        stamp(1);
-        // ---- per-row head and environment adjoint (needs only the checkpoints), under the image load ----
-        if (rowthread) {
+          tc_fence_before();         // the g_p read of the previous step precedes the next g_p UMMAs (ordered through p_full)
           if (t < a.horizon && valid) {
             float Wt = 0.f;
-            for (int k = 0; k < a.n_list; ++k) if (a.list[k] > t) Wt += a.list_w[k];
+#pragma unroll
+            for (int k = 0; k < MPG_MAX_LIST; ++k) if (k < a.n_list && a.list[k] > t) Wt += a.list_w[k];
             env_step_bwd<ENV, true>(s, act, lam, cscale * Wt * gp * a.rew_scale, g_s, g_a, snext);
           }
-        }
-        // ---- delta3, its image, db3 ----
-        if (ROLE == ROLE_EPI && rowthread) {
+          stamp(14);
           float d3[2] = {0.f, 0.f};
 #pragma unroll
           for (int j = 0; j < NA; ++j) {
@@ -656,31 +710,46 @@ __device__ __forceinline__ void run_rollout(const TcArgs& A, uint8_t* smem, Bars
           }
           if (NA == 1) mf->d3s[ACT_ROWS + row] = 0.f;
           if (want_dw) {
-            float x[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) x[i] = 0.f;
-            x[0] = d3[0]; x[1] = d3[1];
-            write_row16(d3_img, row, x);
-            float s0 = d3[0], s1 = d3[1];
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) { s0 += __shfl_xor_sync(0xffffffffu, s0, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o); }
-            if (lane == 0) { mf->wsum[warp * 2] = s0; mf->wsum[warp * 2 + 1] = s1; }
+            write_d3(d3_img, row, d3[0], d3[1]);
+            db3acc[0] += d3[0]; db3acc[1] += d3[1];
           }
-        }
-        if (ROLE == ROLE_EPI) {
+          bar_arrive(BAR_D3, XCHG_THREADS);
           stamp(2);
-          mbar_wait(&b->img_full, sy.i_cnt & 1);            // h2 image landed
+        }
+        // ---- h2 image of step t: store of the forward pass -> activation image, in two 128-feature halves.  A half is
+        // free once the UMMAs that read it have completed and no record store reads it.  In the steady state both were
+        // released during the previous step (bwd_tail_issue / epi_delta1_blocks) and the loads are already in flight;
+        // the first step of a tile and steps with a Q part release them here ----
+        if (!early) {
+          if (ROLE == ROLE_MMA) { umma_commit(&b->img_empty[0]); umma_commit(&b->img_empty[1]); }
+          if (elected) {
+            bulk_wait_read_all();
+            mbar_arrive(&b->img_empty[0]);
+            mbar_arrive(&b->img_empty[1]);
+          }
+          if (ROLE == ROLE_PRODUCER) load_h2(t);
+        }
+        store_pending = false;
+        stamp(1);
+        if (ROLE == ROLE_EPI) {
+          mbar_wait(&b->img_full[0], sy.i_cnt & 1);         // first half of the h2 image landed
           stamp(3);
         }
         ++sy.i_cnt;
         if (want_dw) d3_issue<ROLE>(b, smem, sy, SM_D3IMG, d3_started, tm_d3, true);   // dW3 += h2^T delta3
+        // ---- [p|1] image of step t (first-layer recompute for elu'(z1), D1 operand, db2 record); the D1 UMMAs of the
+        // previous step still read the old one ----
+        if (rowthread) {
+          acc_wait();
+          stamp(12);
+          write_pimg(s, nullptr, rec ? slot + SLOT_P : nullptr);
+          fence_proxy_async();
+          mbar_arrive(&b->p_full);
+          stamp(13);
+        }
         if (ROLE == ROLE_EPI) {
           if (want_dw) epi_wait_d(b, sy);                   // blocks 0, 1 of the h2 image read by the D3 UMMAs
-          epi_bar();
-          if (tid == 0 && want_dw) {
-            db3acc[0] += (mf->wsum[0] + mf->wsum[2]) + (mf->wsum[4] + mf->wsum[6]);
-            db3acc[1] += (mf->wsum[1] + mf->wsum[3]) + (mf->wsum[5] + mf->wsum[7]);
-          }
+          bar_sync(BAR_D3, XCHG_THREADS);                   // delta3 of every row is in MiscF::d3s
         }
         // ---- delta2 image (in place over h2) feeding the dX UMMAs block by block ----
         if (ROLE == ROLE_MMA) stamp(3);
@@ -688,22 +757,28 @@ __device__ __forceinline__ void run_rollout(const TcArgs& A, uint8_t* smem, Bars
         if (ROLE == ROLE_MMA) stamp(4);
         if (ROLE == ROLE_EPI) {
           stamp(6);
-          epi_delta2_from_h2(b, mf->W3p, mf->d3s[row], mf->d3s[ACT_ROWS + row], act_img, row, hc, want_dw ? &sy : nullptr);
+          epi_delta2_from_h2(b, mf->W3p, mf->d3s[row], mf->d3s[ACT_ROWS + row], act_img, row, hc, (sy.i_cnt - 1) & 1,
+                             want_dw ? &sy : nullptr);
           stamp(7);
           if (rec) store_image_follow(elected, b, sy, slot + SLOT_D2, act_img);   // delta2 blocks leave behind their K-blocks
           epi_wait_d(b, sy);                                       // g_h1 complete, delta2 image consumed
           stamp(8);
         }
         // z1 recompute stream, g_p following the delta1 blocks, D1 += delta1^T [p|1]
-        bwd_tail_issue<ROLE>(b, smem, sy, A.pol.l1, A.pol.in, t > 0, want_dw, d1_started, tm_z1c, tm_gp, tm_d1, true);
+        bwd_tail_issue<ROLE>(b, smem, sy, A.pol.l1, A.pol.in, t > 0, want_dw, d1_started, tm_z1c, tm_gp, tm_d1, true, early_next);
+        if (ROLE == ROLE_PRODUCER && early_next) load_h2(t - 1);
         if (ROLE == ROLE_EPI) {
-          epi_delta1_blocks(b, tm_work + lane_off, tm_z1c + lane_off, act_img, row, hc, rec, elected);
+          epi_delta1_blocks(b, tm_work + lane_off, tm_z1c + lane_off, act_img, row, hc, rec, elected, early_next);
           stamp(9);
           if (t > 0) epi_wait_d(b, sy);
-          if (want_dw) d1_pending = true;
           stamp(10);
         }
+        if (want_dw) { d1_pending = true; ++acc_issued; }
         if (t > 0 && rowthread) {
+          mbar_wait(&b->gp_full, sy.gp_cnt & 1);
+          ++sy.gp_cnt;
+          tc_fence_after();
+          stamp(10);
           float gin[16];
           tmem_ld16(tm_gp + lane_off, gin);
           if (valid) {
@@ -719,17 +794,27 @@ __device__ __forceinline__ void run_rollout(const TcArgs& A, uint8_t* smem, Bars
       }
     }
   }
-  acc_wait();
+  if (rowthread && BWD) {
+    // db3: per-row partial sums -> per-warp (shuffle tree) -> fixed-order total
+    float s0 = db3acc[0], s1 = db3acc[1];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { s0 += __shfl_xor_sync(0xffffffffu, s0, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o); }
+    if (lane == 0) { mf->wsum[(warp & 3) * 2] = s0; mf->wsum[(warp & 3) * 2 + 1] = s1; }
+    bar_sync(BAR_ROW, ROW_THREADS);
+    if (tid == EPI_THREADS) {
+      const GradLayout L(A.pol.in_dim, A.pol.out_dim);
+      float* partial = a.partial + (size_t)blockIdx.x * a.partial_stride;
+      partial[L.ob3 + 0] = (mf->wsum[0] + mf->wsum[2]) + (mf->wsum[4] + mf->wsum[6]);
+      if (NA > 1) partial[L.ob3 + 1] = (mf->wsum[1] + mf->wsum[3]) + (mf->wsum[5] + mf->wsum[7]);
+    }
+  }
+  if (ROLE == ROLE_EPI && acc_issued > 0) mbar_wait(&b->acc_done, (acc_issued - 1) & 1);   // last D1 accumulation complete
   if (ROLE == ROLE_EPI) {
     tc_fence_before();
     if (elected) bulk_wait_all();
     if (BWD) {
       const GradLayout L(A.pol.in_dim, A.pol.out_dim);
       float* partial = a.partial + (size_t)blockIdx.x * a.partial_stride;
-      if (tid == 0) {
-        partial[L.ob3 + 0] = db3acc[0];
-        if (NA > 1) partial[L.ob3 + 1] = db3acc[1];
-      }
       if (any_dw && hc == 0) {
         // D1 / D3: TMEM lane = feature inside the 128-feature half, columns = input index (BIAS_K: bias) / action
         tc_fence_after();
@@ -739,18 +824,34 @@ __device__ __forceinline__ void run_rollout(const TcArgs& A, uint8_t* smem, Bars
           const int f = half * 128 + row;
           float v[16];
           tmem_ld16(tm_d1 + half * 16 + lane_off, v);
-          for (int i = 0; i < A.pol.in_dim; ++i) partial[L.oW1 + (size_t)i * H + f] = v[i];
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            if (i < A.pol.in_dim) partial[L.oW1 + (size_t)i * H + f] = v[i];
           partial[L.ob1 + f] = v[BIAS_K];
           tmem_ld16(tm_d3 + half * 16 + lane_off, v);
-          for (int j = 0; j < ncol3; ++j) partial[L.oW3 + (size_t)f * A.pol.out_dim + j] = v[j];
+#pragma unroll
+          for (int j = 0; j < 2; ++j)
+            if (j < ncol3) partial[L.oW3 + (size_t)f * A.pol.out_dim + j] = v[j];
         }
       }
     }
   }
 }
 
+// The rollout kernel is launched with SIX warpgroups: four epilogue warpgroups (16 warps), the row warpgroup (4 warps,
+// thread = trajectory) and one that holds the producer warp, the mma warp and two idle warps.  setmaxnreg moves registers
+// inside the CTA's launch allocation (768 threads x 80 registers) from the last warpgroup to the row warpgroup.  Why it
+// matters: with 221 KB of shared memory in use only ~7 KB of L1 is left, so every register spill is an L2 round trip
+// (~270 cycles) -- and the scalar recurrence of a row (state, adjoint, checkpoints) used to be spilled around the 16-wide
+// epilogue vectors when the same threads did both jobs.
+constexpr int ROLLOUT_THREADS = EPI_THREADS + ROW_THREADS + 128;
+constexpr int ROW_WARP0 = EPI_WARPS, PRODUCER_WARP = EPI_WARPS + 4, MMA_WARP = EPI_WARPS + 5;
+constexpr int LAUNCH_REGS = 80, EPI_REGS = 80, ROW_REGS = 96, AUX_REGS = 64;
+static_assert(EPI_THREADS * EPI_REGS + ROW_THREADS * ROW_REGS + 128 * AUX_REGS <= ROLLOUT_THREADS * LAUNCH_REGS,
+              "setmaxnreg only redistributes the register pool of the CTA");
+
 template <int ENV, bool BWD>
-__global__ void __launch_bounds__(CTA_THREADS, 1) tc_rollout_kernel(const __grid_constant__ TcArgs A) {
+__global__ void __launch_bounds__(ROLLOUT_THREADS, 1) tc_rollout_kernel(const __grid_constant__ TcArgs A) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   MiscF* mf = reinterpret_cast<MiscF*>(smem + SmemMap::MISC);
@@ -764,17 +865,25 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) tc_rollout_kernel(const __grid
       mf->W3q[2 * i + 1] = 0.f;
     }
   }
+  for (int i = threadIdx.x; i < 8192 / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem + SM_D3IMG)[i] = make_uint4(0u, 0u, 0u, 0u);
   if (threadIdx.x == 0) {
     mf->b3[0] = A.pol.b3[0];
     mf->b3[1] = Env<ENV>::A > 1 ? A.pol.b3[1] : 0.f;
     mf->b3[2] = A.r.has_q ? A.q.b3[0] : 0.f;
   }
-  Bars* b = cta_setup(smem);   // contains __syncthreads()
+  Bars* b = cta_setup(smem, XCHG_THREADS, MMA_WARP);   // contains __syncthreads()
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (warp < EPI_WARPS) run_rollout<ENV, BWD, ROLE_EPI>(A, smem, b);
-  else if (warp == EPI_WARPS) { if (lane == 0) run_rollout<ENV, BWD, ROLE_PRODUCER>(A, smem, b); }
-  else { if (lane == 0) run_rollout<ENV, BWD, ROLE_MMA>(A, smem, b); }
-  cta_teardown(b);
+  if (warp < EPI_WARPS) {
+    run_rollout<ENV, BWD, ROLE_EPI>(A, smem, b);
+  } else if (warp < PRODUCER_WARP) {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(ROW_REGS));
+    run_rollout<ENV, BWD, ROLE_ROW>(A, smem, b);
+  } else {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(AUX_REGS));
+    if (warp == PRODUCER_WARP) { if (lane == 0) run_rollout<ENV, BWD, ROLE_PRODUCER>(A, smem, b); }
+    else if (warp == MMA_WARP) { if (lane == 0) run_rollout<ENV, BWD, ROLE_MMA>(A, smem, b); }
+  }
+  cta_teardown(b, MMA_WARP);
 }
 
 // =================================================================================================

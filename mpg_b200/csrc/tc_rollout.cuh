@@ -105,13 +105,13 @@ inline cudaError_t tc_launch_rollout(int env, const tc::TcArgs& a, int grid, cud
   const size_t smem = tc::SM_TOTAL + 1024;
   if (env == MPG_ENV_PATH_TRACKING_REAL) {
     if (BWD) return cudaErrorNotSupported;
-    tc::tc_rollout_kernel<MPG_ENV_PATH_TRACKING_REAL, false><<<grid, tc::CTA_THREADS, smem, st>>>(a);
+    tc::tc_rollout_kernel<MPG_ENV_PATH_TRACKING_REAL, false><<<grid, tc::ROLLOUT_THREADS, smem, st>>>(a);
     return cudaGetLastError();
   }
   switch (env) {
-    case MPG_ENV_PATH_TRACKING: tc::tc_rollout_kernel<MPG_ENV_PATH_TRACKING, BWD><<<grid, tc::CTA_THREADS, smem, st>>>(a); break;
-    case MPG_ENV_INVERTED_PENDULUM: tc::tc_rollout_kernel<MPG_ENV_INVERTED_PENDULUM, BWD><<<grid, tc::CTA_THREADS, smem, st>>>(a); break;
-    default: tc::tc_rollout_kernel<MPG_ENV_INVERTED_DOUBLE_PENDULUM, BWD><<<grid, tc::CTA_THREADS, smem, st>>>(a); break;
+    case MPG_ENV_PATH_TRACKING: tc::tc_rollout_kernel<MPG_ENV_PATH_TRACKING, BWD><<<grid, tc::ROLLOUT_THREADS, smem, st>>>(a); break;
+    case MPG_ENV_INVERTED_PENDULUM: tc::tc_rollout_kernel<MPG_ENV_INVERTED_PENDULUM, BWD><<<grid, tc::ROLLOUT_THREADS, smem, st>>>(a); break;
+    default: tc::tc_rollout_kernel<MPG_ENV_INVERTED_DOUBLE_PENDULUM, BWD><<<grid, tc::ROLLOUT_THREADS, smem, st>>>(a); break;
   }
   return cudaGetLastError();
 }
