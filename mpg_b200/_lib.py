@@ -18,7 +18,7 @@ SYMBOLS = [
     'mpg_returns_tile_mean', 'mpg_q_grad', 'mpg_policy_forward', 'mpg_q_forward', 'mpg_q_target', 'mpg_td_error',
     'mpg_model_reset', 'mpg_model_step', 'mpg_model_step_bwd', 'mpg_compute_rewards', 'mpg_state_dim',
     'mpg_clip_global_norm', 'mpg_philox_noise', 'mpg_launch_count', 'mpg_set_backend', 'mpg_get_backend',
-    'mpg_set_timing', 'mpg_kernel_ms', 'mpg_tc_selftest', 'mpg_set_profile_buffer', 'mpg_adam_step', 'mpg_polyak_update', 'mpg_get_adam_state',
+    'mpg_set_timing', 'mpg_kernel_ms', 'mpg_tc_selftest', 'mpg_set_profile_buffer', 'mpg_wait_debug', 'mpg_adam_step', 'mpg_polyak_update', 'mpg_get_adam_state',
     'mpg_set_adam_state', 'mpg_env_sample',
     'mpg_replay_create', 'mpg_replay_destroy', 'mpg_replay_last_error', 'mpg_replay_size', 'mpg_replay_add',
     'mpg_replay_sample', 'mpg_replay_update_priorities', 'mpg_replay_tree_stats', 'mpg_q_bootstrap', 'mpg_env_step',
@@ -89,6 +89,7 @@ def load():
         'mpg_kernel_ms': (f32, [vp]),
         'mpg_tc_selftest': (i32, [vp, i32, vp, vp, vp, i32, vp]),
         'mpg_set_profile_buffer': (i32, [vp, vp]),
+        'mpg_wait_debug': (i32, [vp]),
         'mpg_adam_step': (i32, [vp, i32, vp, f32, i64, f32, f32, f32, vp]),
         'mpg_polyak_update': (i32, [vp, i32, i32, f32, vp]),
         'mpg_get_adam_state': (i32, [vp, i32, vp, vp, vp]),
@@ -110,3 +111,13 @@ def load():
         fn.restype, fn.argtypes = res, args
     _lib = lib
     return lib
+
+
+def wait_debug():
+    """Watchdog record of the kernels' mbarrier waits: None, or dict(site=source line (+10000 tc_gemm.cuh, +20000
+    tc_kernels.cuh), block, thread, parity) of the wait that timed out and made the launch trap."""
+    out = (ctypes.c_uint64 * 5)()
+    load().mpg_wait_debug(out)
+    if not out[0]:
+        return None
+    return dict(site=int(out[1]), block=int(out[2]), thread=int(out[3]), parity=int(out[4]))

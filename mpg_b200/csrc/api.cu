@@ -26,6 +26,21 @@ struct NetStore {
 
 thread_local char g_create_err[512] = "";
 
+// watchdog record of the mbarrier waits (tc_common.cuh: g_wait_dbg): pinned, mapped host memory, one per process and device
+unsigned long long* g_wait_host = nullptr;
+bool wait_dbg_init() {
+  if (g_wait_host) return true;
+  unsigned long long* h = nullptr; unsigned long long* d = nullptr;
+  if (cudaHostAlloc((void**)&h, 64, cudaHostAllocMapped) != cudaSuccess) { cudaGetLastError(); return false; }
+  memset(h, 0, 64);
+  if (cudaHostGetDevicePointer((void**)&d, h, 0) != cudaSuccess
+      || cudaMemcpyToSymbol(mpg::tc::g_wait_dbg, &d, sizeof(d)) != cudaSuccess) {
+    cudaGetLastError(); cudaFreeHost(h); return false;
+  }
+  g_wait_host = h;
+  return true;
+}
+
 }  // namespace
 
 struct mpg_ctx {
@@ -288,6 +303,13 @@ int mpg_set_backend(mpg_ctx* ctx, int backend) {
   return MPG_OK;
 }
 
+// {flag, site, block, thread, parity} of the mbarrier wait that timed out (flag == 0: none); see tc_common.cuh
+int mpg_wait_debug(unsigned long long out[5]) {
+  if (!out) return MPG_ERR_ARG;
+  for (int i = 0; i < 5; ++i) out[i] = g_wait_host ? ((volatile unsigned long long*)g_wait_host)[i] : 0ull;
+  return MPG_OK;
+}
+
 int mpg_set_profile_buffer(mpg_ctx* ctx, long long* buf) {
   if (!ctx) return MPG_ERR_ARG;
   ctx->prof = buf;
@@ -372,6 +394,7 @@ int mpg_create(const mpg_config* cfg, mpg_ctx** out) {
        && alloc(&c->partial, (size_t)2 * c->sms * c->partial_stride) && alloc(&c->loss_partial, c->sms)
        && alloc(&c->stats_part, (size_t)MPG_MAX_LIST * 64 * 2);
   if (ok) ok = tc_init(c->tc, c->cfg, c->sms, c->ws_bytes);
+  wait_dbg_init();   // best effort: without it a timed-out wait still traps, only the record is missing
   if (!ok) {
     snprintf(g_create_err, 512, "cudaMalloc of the workspace failed: %s", cudaGetErrorString(cudaGetLastError()));
     mpg_destroy(c);

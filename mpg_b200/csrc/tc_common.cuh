@@ -39,11 +39,34 @@ __device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
       "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680) : "memory");
   return ok != 0;
 }
+// Watchdog of the mbarrier waits: a protocol error must not hang the GPU.  g_wait_dbg points to pinned, mapped host
+// memory (set once per process by the library); a wait that does not complete within MPG_WAIT_LIMIT_CYCLES records
+// {site (source line), block, thread, parity} there and traps, so that the launch fails with an error the host can report.
+__device__ unsigned long long* g_wait_dbg = nullptr;
+#ifndef MPG_WAIT_LIMIT_CYCLES
+#define MPG_WAIT_LIMIT_CYCLES 4000000000ll    /* ~2 s at 1.965 GHz; the longest legitimate wait is a few hundred microseconds */
+#endif
+__device__ __noinline__ void mbar_timeout(int site, uint32_t parity) {
+  if (g_wait_dbg) {
+    g_wait_dbg[1] = (unsigned long long)site;
+    g_wait_dbg[2] = (unsigned long long)blockIdx.x;
+    g_wait_dbg[3] = (unsigned long long)threadIdx.x;
+    g_wait_dbg[4] = (unsigned long long)parity;
+    g_wait_dbg[0] = 1ull;
+    __threadfence_system();
+  }
+  __trap();
+}
 // try_wait suspends the thread in hardware (up to the time hint) and wakes it on phase completion, so
 // waiting warps do not burn issue slots of the warps doing the per-row math on the same sub-partition
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  while (!mbar_try(bar, parity)) {}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int site = 0) {
+  if (mbar_try(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try(bar, parity)) {
+    if (clock64() - t0 > MPG_WAIT_LIMIT_CYCLES) mbar_timeout(site, parity);
+  }
 }
+#define MBAR_WAIT(bar, parity) mbar_wait((bar), (parity), __LINE__)
 // 2^x, flush-to-zero approximate (one MUFU, no denormal fix-up code)
 __device__ __forceinline__ float ex2_ftz(float x) {
   float y;
@@ -186,6 +209,12 @@ __device__ __forceinline__ void act_store8(uint8_t* act_hi, uint8_t* act_lo, int
 }
 // INTERLEAVE K-major image of R rows x 16 elements: byte offset of the 16-byte chunk (k half kh) of row r
 __device__ __forceinline__ uint32_t il_chunk_off(int r, int kh) { return (uint32_t)((r >> 3) * 256 + kh * 128 + (r & 7) * 16); }
+// [p|a|1] image: R rows x (16 hi | 16 lo) elements, the four 16-byte chunks (hi0, hi1, lo0, lo1) of an 8-row group next to
+// each other (512 B per group).  Read K-major it is two R x 16 INTERLEAVE operands (hi at +0, lo at +256; LBO 128, SBO 512);
+// read MN-major (K = rows) it is ONE operand with N = 32 = [p_hi | p_lo] (SBO 128, LBO 512), so that delta1^T [p_hi | p_lo]
+// needs two UMMAs per row step (delta1_hi, delta1_lo) instead of three products.
+constexpr int P_GROUP = 512, P_LO = 256;
+__device__ __forceinline__ uint32_t p_chunk_off(int r, int c) { return (uint32_t)((r >> 3) * P_GROUP + c * 128 + (r & 7) * 16); }
 
 }  // namespace tc
 }  // namespace mpg

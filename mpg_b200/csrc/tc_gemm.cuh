@@ -31,7 +31,15 @@ constexpr int TMEM_COLS = 512;
 // TMEM column regions: two 64-column first-layer chunk buffers (z1 is streamed, never resident), the 256-column
 // working accumulator (z2 / g_h1), the 16-column input gradient, and the persistent weight-gradient accumulators
 // D1 = delta1^T [p|1] and D3 = h2^T [delta3|0] (two 128-feature halves x 16 columns each)
-constexpr int TM_Z1C = 0, TM_WORK = 128, TM_GP = 384, TM_D1 = 400, TM_D3 = 432;
+// Small-N UMMAs that accumulate into the same tile form a dependent chain and pay the tensor pipe's latency (~150 cycles)
+// each instead of its throughput, so g_p and D3 (both on the critical path of a BPTT step) are split over TWO accumulator
+// sets (32 columns apart) that the reader adds up.
+// The small contractions put the hi and lo halves of their B operand side by side in N, so that one UMMA per A split does
+// the work of the three split products (and keeps the lo.lo term):
+//   g_p [128 x 32]     = delta1 . [W1_hi ; W1_lo]^T      -> g_p = columns [0,16) + [16,32)
+//   D1  [2 x 128 x 32] = delta1^T . [p_hi | p_lo]         -> dW1 = columns [0,16) + [16,32)
+//   D3  [2 x 128 x 16] = h2^T . [d3_hi | d3_lo | 0]       -> dW3[:, j] = column j + column 2 + j
+constexpr int TM_Z1C = 0, TM_WORK = 128, TM_GP = 384, TM_D1 = 416, TM_D3 = 480;
 
 // shared memory map (bytes, 1024-aligned base)
 struct SmemMap {
@@ -82,7 +90,7 @@ enum Role { ROLE_EPI = 0, ROLE_PRODUCER = 1, ROLE_MMA = 2, ROLE_ROW = 3 };
 __device__ __forceinline__ void produce(Bars* b, uint8_t* ring, Sync& s, const uint8_t* gsrc, int nstages, uint32_t bytes) {
   for (int i = 0; i < nstages; ++i, ++s.stage) {
     const uint32_t slot = s.stage & (NSLOT - 1), par = (s.stage / NSLOT) & 1;
-    mbar_wait(&b->empty[slot], par ^ 1);
+    mbar_wait(&b->empty[slot], par ^ 1, 10000 + __LINE__);
     mbar_expect_tx(&b->full[slot], bytes);
     bulk_g2s(ring + slot * STAGE_BYTES, gsrc + (size_t)i * bytes, bytes, &b->full[slot]);
   }
@@ -93,13 +101,13 @@ __device__ __forceinline__ void produce(Bars* b, uint8_t* ring, Sync& s, const u
 // mbarrier phases of all four slots advance in lock step.
 __device__ __forceinline__ void produce_pad(Bars* b, Sync& s) {
   const uint32_t slot = s.stage & (NSLOT - 1), par = (s.stage / NSLOT) & 1;
-  mbar_wait(&b->empty[slot], par ^ 1);
+  mbar_wait(&b->empty[slot], par ^ 1, 10000 + __LINE__);
   mbar_arrive(&b->full[slot]);
   ++s.stage;
 }
 __device__ __forceinline__ void consume_pad(Bars* b, Sync& s) {
   const uint32_t slot = s.stage & (NSLOT - 1), par = (s.stage / NSLOT) & 1;
-  mbar_wait(&b->full[slot], par);
+  mbar_wait(&b->full[slot], par, 10000 + __LINE__);
   umma_commit(&b->empty[slot]);
   ++s.stage;
 }
@@ -116,15 +124,15 @@ __device__ __forceinline__ void mma_big(Bars* b, uint32_t act_addr, uint32_t rin
                                         Hook hook = Hook(), bool wait_a = true) {
   constexpr uint32_t idesc = make_idesc(128, 256, 0, 0);
   for (int kb = 0; kb < 4; ++kb) {
-    if (wait_a) mbar_wait(&b->a_blk[kb], s.g_cnt & 1);
+    if (wait_a) mbar_wait(&b->a_blk[kb], s.g_cnt & 1, 10000 + __LINE__);
     tc_fence_after();
     const uint64_t dah = make_desc(act_addr + kb * ACT_BLOCK, 16, 1024, LAYOUT_SW128);
     const uint64_t dal = make_desc(act_addr + ACT_SPLIT + kb * ACT_BLOCK, 16, 1024, LAYOUT_SW128);
 #pragma unroll
     for (int sp = 0; sp < 2; ++sp) {
       const uint32_t slot = s.stage & (NSLOT - 1), par = (s.stage / NSLOT) & 1;   // slot is 0 or 2
-      mbar_wait(&b->full[slot], par);
-      mbar_wait(&b->full[slot + 1], par);
+      mbar_wait(&b->full[slot], par, 10000 + __LINE__);
+      mbar_wait(&b->full[slot + 1], par, 10000 + __LINE__);
       tc_fence_after();
       const uint64_t db = make_desc(ring_addr + slot * STAGE_BYTES, 16, 1024, LAYOUT_SW128);
 #pragma unroll
@@ -150,9 +158,9 @@ __device__ __forceinline__ void mma_big(Bars* b, uint32_t act_addr, uint32_t rin
 // exactly chunks 0..3, so buffer j is used twice per GEMM and the mbarrier parities depend on c only.
 __device__ __forceinline__ void mma_l1_chunk(Bars* b, uint32_t p_addr, uint32_t bbase, int c, uint32_t tm_z1c) {
   constexpr uint32_t idesc = make_idesc(128, 64, 0, 0);
-  mbar_wait(&b->z_empty[c & 1], ((c >> 1) & 1) ^ 1);
+  mbar_wait(&b->z_empty[c & 1], ((c >> 1) & 1) ^ 1, 10000 + __LINE__);
   tc_fence_after();
-  const uint64_t dah = make_desc(p_addr, 128, 256, LAYOUT_NONE), dal = make_desc(p_addr + 4096, 128, 256, LAYOUT_NONE);
+  const uint64_t dah = make_desc(p_addr, 128, P_GROUP, LAYOUT_NONE), dal = make_desc(p_addr + P_LO, 128, P_GROUP, LAYOUT_NONE);
   const uint64_t dbh = make_desc(bbase + c * 2048, 128, 256, LAYOUT_NONE), dbl = make_desc(bbase + 8192 + c * 2048, 128, 256, LAYOUT_NONE);
   const uint32_t d = tm_z1c + (c & 1) * 64;
   umma_bf16(d, dah, dbh, idesc, 0u);
@@ -162,45 +170,46 @@ __device__ __forceinline__ void mma_l1_chunk(Bars* b, uint32_t p_addr, uint32_t 
 }
 // epilogue side of the chunk stream
 __device__ __forceinline__ void epi_wait_chunk(Bars* b, int c) {
-  mbar_wait(&b->z_full[c & 1], (c >> 1) & 1);
+  mbar_wait(&b->z_full[c & 1], (c >> 1) & 1, 10000 + __LINE__);
   tc_fence_after();
 }
 __device__ __forceinline__ void epi_release_chunk(Bars* b, int c) {
   tc_fence_before();
   mbar_arrive(&b->z_empty[c & 1]);
 }
-// Weight-gradient accumulation with the operands where they already are: D[half][128 features x 16] +=
-// IMG[:, half]^T . R16, IMG = activation image read MN-major (K = rows), R16 = [p|1] or [delta3|0] image read
-// MN-major.  24 UMMAs per half (8 row steps x 3 split products); a half needs only its two 64-feature blocks of the
-// image, so it can be issued as soon as those are written and lets the image be overwritten half by half.
+// Weight-gradient accumulation with the operands where they already are: D[half][128 features x N] +=
+// IMG[:, half]^T . R, IMG = activation image read MN-major (K = rows), R = an image with hi and lo side by side in N
+// read MN-major: the [p|a|1] image (N = 32, D1) or the delta3 image (N = 16, D3).  16 UMMAs per half (8 row steps x the
+// two splits of IMG); a half needs only its two 64-feature blocks of the image, so it can be issued as soon as those are
+// written and lets the image be overwritten half by half.
 // lin: the image is in the row-interleaved no-swizzle layout [chunk][row][16 B] (h2 images loaded from the h2 store):
 // MN-major INTERLEAVE, 8-row groups 128 B apart (LBO), 8-feature chunks 2048 B apart (SBO), 16 rows = 256 B per k-step.
-__device__ __forceinline__ void mma_acc16_half(uint32_t act_addr, uint32_t r16_addr, uint32_t d_tmem, int half, bool started,
-                                               bool lin = false) {
-  constexpr uint32_t idesc = make_idesc(128, 16, 1, 1);
-  const uint32_t d = d_tmem + half * 16;
+template <int N>
+__device__ __forceinline__ void mma_acc_half(uint32_t act_addr, uint32_t r_addr, uint32_t r_group, uint32_t d_tmem, int half,
+                                             bool started, bool lin = false) {
+  constexpr uint32_t idesc = make_idesc(128, N, 1, 1);
+  const uint32_t d = d_tmem + half * N;
 #pragma unroll
   for (int ks = 0; ks < ACT_ROWS / 16; ++ks) {
     const uint32_t a = act_addr + half * 2 * ACT_BLOCK + (lin ? ks * 256 : ks * 2048);
     const uint64_t dah = lin ? make_desc(a, 128, 2048, LAYOUT_NONE) : make_desc(a, ACT_BLOCK, 1024, LAYOUT_SW128);
     const uint64_t dal = lin ? make_desc(a + ACT_SPLIT, 128, 2048, LAYOUT_NONE) : make_desc(a + ACT_SPLIT, ACT_BLOCK, 1024, LAYOUT_SW128);
-    const uint64_t dbh = make_desc(r16_addr + ks * 512, 256, 128, LAYOUT_NONE), dbl = make_desc(r16_addr + 4096 + ks * 512, 256, 128, LAYOUT_NONE);
-    umma_bf16(d, dah, dbh, idesc, (started || ks) ? 1u : 0u);
-    umma_bf16(d, dal, dbh, idesc, 1u);
-    umma_bf16(d, dah, dbl, idesc, 1u);
+    const uint64_t db = make_desc(r_addr + ks * 2 * r_group, r_group, 128, LAYOUT_NONE);   // 8-row groups r_group apart (LBO)
+    umma_bf16(d, dah, db, idesc, (started || ks) ? 1u : 0u);
+    umma_bf16(d, dal, db, idesc, 1u);
   }
 }
 // first-layer GEMM: D[128 x 256] = P[128 x 16] . W1aug^T ; P is the INTERLEAVE image in shared memory,
 // W1aug image streamed as ONE stage = [hi: 256 rows x 32 B][lo: 256 rows x 32 B] = 16 KB
 __device__ __forceinline__ void mma_l1(Bars* b, uint32_t p_addr, uint32_t ring_addr, Sync& s, uint32_t d_tmem) {
   constexpr uint32_t idesc = make_idesc(128, 256, 0, 0);
-  mbar_wait(&b->a_full, s.a_cnt & 1);
+  mbar_wait(&b->a_full, s.a_cnt & 1, 10000 + __LINE__);
   ++s.a_cnt;
   const uint32_t slot = s.stage & (NSLOT - 1), par = (s.stage / NSLOT) & 1;
-  mbar_wait(&b->full[slot], par);
+  mbar_wait(&b->full[slot], par, 10000 + __LINE__);
   tc_fence_after();
   const uint32_t bbase = ring_addr + slot * STAGE_BYTES;
-  const uint64_t dah = make_desc(p_addr, 128, 256, LAYOUT_NONE), dal = make_desc(p_addr + 4096, 128, 256, LAYOUT_NONE);
+  const uint64_t dah = make_desc(p_addr, 128, P_GROUP, LAYOUT_NONE), dal = make_desc(p_addr + P_LO, 128, P_GROUP, LAYOUT_NONE);
   const uint64_t dbh = make_desc(bbase, 128, 256, LAYOUT_NONE), dbl = make_desc(bbase + 8192, 128, 256, LAYOUT_NONE);
   umma_bf16(d_tmem, dah, dbh, idesc, 0u);
   umma_bf16(d_tmem, dal, dbh, idesc, 1u);
@@ -209,26 +218,27 @@ __device__ __forceinline__ void mma_l1(Bars* b, uint32_t p_addr, uint32_t ring_a
   ++s.stage;
   consume_pad(b, s);
 }
-// input-gradient GEMM: D[128 x 16] = ACT[128 x 256] . W1nat^T (W1nat: 16 rows x 256), image streamed as ONE
-// stage = [hi: 4 k-blocks x (16 rows x 128 B)][lo: same] = 16 KB
+// input-gradient GEMM: D[128 x 32] = ACT[128 x 256] . [W1nat_hi ; W1nat_lo]^T (W1nat: 16 rows x 256); the image is
+// streamed as ONE stage = 4 k-blocks x (32 rows x 128 B) = 16 KB; g = D[:, 0:16] + D[:, 16:32]
+__device__ __forceinline__ void mma_in_block(uint32_t act_addr, uint32_t ibase, int kb, uint32_t d_tmem) {
+  constexpr uint32_t idesc = make_idesc(128, 32, 0, 0);
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) {
+    const uint32_t a_hi = act_addr + kb * ACT_BLOCK + ks * 32, a_lo = a_hi + ACT_SPLIT;
+    const uint64_t dah = make_desc(a_hi, 16, 1024, LAYOUT_SW128), dal = make_desc(a_lo, 16, 1024, LAYOUT_SW128);
+    const uint64_t db = make_desc(ibase + kb * 4096 + ks * 32, 16, 1024, LAYOUT_SW128);
+    umma_bf16(d_tmem, dah, db, idesc, (kb | ks) ? 1u : 0u);
+    umma_bf16(d_tmem, dal, db, idesc, 1u);
+  }
+}
 __device__ __forceinline__ void mma_in(Bars* b, uint32_t act_addr, uint32_t ring_addr, Sync& s, uint32_t d_tmem) {
-  constexpr uint32_t idesc = make_idesc(128, 16, 0, 0);
   const uint32_t slot = s.stage & (NSLOT - 1), par = (s.stage / NSLOT) & 1;
   const uint32_t bbase = ring_addr + slot * STAGE_BYTES;
   for (int kb = 0; kb < 4; ++kb) {
-    mbar_wait(&b->a_blk[kb], s.g_cnt & 1);
-    if (kb == 0) mbar_wait(&b->full[slot], par);
+    mbar_wait(&b->a_blk[kb], s.g_cnt & 1, 10000 + __LINE__);
+    if (kb == 0) mbar_wait(&b->full[slot], par, 10000 + __LINE__);
     tc_fence_after();
-#pragma unroll
-    for (int ks = 0; ks < 4; ++ks) {
-      const uint32_t a_hi = act_addr + kb * ACT_BLOCK + ks * 32, a_lo = a_hi + ACT_SPLIT;
-      const uint32_t b_hi = bbase + kb * 2048 + ks * 32, b_lo = b_hi + 8192;
-      const uint64_t dah = make_desc(a_hi, 16, 1024, LAYOUT_SW128), dal = make_desc(a_lo, 16, 1024, LAYOUT_SW128);
-      const uint64_t dbh = make_desc(b_hi, 16, 1024, LAYOUT_SW128), dbl = make_desc(b_lo, 16, 1024, LAYOUT_SW128);
-      umma_bf16(d_tmem, dah, dbh, idesc, (kb | ks) ? 1u : 0u);
-      umma_bf16(d_tmem, dal, dbh, idesc, 1u);
-      umma_bf16(d_tmem, dah, dbl, idesc, 1u);
-    }
+    mma_in_block(act_addr, bbase, kb, d_tmem);
   }
   umma_commit(&b->empty[slot]);
   ++s.stage;
@@ -251,7 +261,7 @@ __device__ __forceinline__ void epi_block_done(Bars* b, int kb) {
 }
 __device__ __forceinline__ void mma_publish_d(Bars* b) { umma_commit(&b->d_full); }
 __device__ __forceinline__ void epi_wait_d(Bars* b, Sync& s) {
-  mbar_wait(&b->d_full, s.d_cnt & 1);
+  mbar_wait(&b->d_full, s.d_cnt & 1, 10000 + __LINE__);
   ++s.d_cnt;
   tc_fence_after();
 }
@@ -288,10 +298,10 @@ __device__ __forceinline__ void fwd_pair_issue(Bars* b, uint8_t* smem, Sync& s, 
     produce(b, smem + SmemMap::RING, s, big_img, 16, STAGE_BYTES);
   } else if (ROLE == ROLE_MMA) {
     const uint32_t base = smem_u32(smem), p_addr = base + SmemMap::PIMG, ring = base + SmemMap::RING;
-    mbar_wait(&b->a_full, s.a_cnt & 1);
+    mbar_wait(&b->a_full, s.a_cnt & 1, 10000 + __LINE__);
     ++s.a_cnt;
     const uint32_t slot = s.stage & (NSLOT - 1), par = (s.stage / NSLOT) & 1;
-    mbar_wait(&b->full[slot], par);
+    mbar_wait(&b->full[slot], par, 10000 + __LINE__);
     tc_fence_after();
     const uint32_t bbase = ring + slot * STAGE_BYTES;
     mma_l1_chunk(b, p_addr, bbase, 0, tm_z1c);
@@ -324,11 +334,11 @@ __device__ __forceinline__ void bwd_tail_issue(Bars* b, uint8_t* smem, Sync& s, 
   } else if (ROLE == ROLE_MMA) {
     const uint32_t base = smem_u32(smem), p_addr = base + SmemMap::PIMG, ring = base + SmemMap::RING;
     if (wait_p) {                                 // the [p|1] image of this step was written at the start of the step
-      mbar_wait(&b->p_full, s.p_cnt & 1);
+      mbar_wait(&b->p_full, s.p_cnt & 1, 10000 + __LINE__);
       ++s.p_cnt;
     }
     const uint32_t slot = s.stage & (NSLOT - 1), par = (s.stage / NSLOT) & 1;
-    mbar_wait(&b->full[slot], par);
+    mbar_wait(&b->full[slot], par, 10000 + __LINE__);
     tc_fence_after();
     const uint32_t bbase = ring + slot * STAGE_BYTES;
     for (int c = 0; c < 4; ++c) mma_l1_chunk(b, p_addr, bbase, c, tm_z1c);
@@ -339,30 +349,20 @@ __device__ __forceinline__ void bwd_tail_issue(Bars* b, uint8_t* smem, Sync& s, 
     // delta1 blocks 0, 1 exist (it runs under the second half of the delta1 epilogue, when the tensor pipe has nothing
     // else to do), half 1 after g_p has been committed, so that it runs under the epilogue's lambda update and the start
     // of the next step (acc_done gates the next image writes)
-    constexpr uint32_t idesc_in = make_idesc(128, 16, 0, 0);
     const uint32_t act_addr = base + SmemMap::ACT;
     const uint32_t islot = s.stage & (NSLOT - 1), ipar = (s.stage / NSLOT) & 1;
     const uint32_t ibase = ring + islot * STAGE_BYTES;
     for (int kb = 0; kb < 4; ++kb) {
-      mbar_wait(&b->a_blk[kb], s.g_cnt & 1);
+      mbar_wait(&b->a_blk[kb], s.g_cnt & 1, 10000 + __LINE__);
       if (do_gp) {
-        if (kb == 0) mbar_wait(&b->full[islot], ipar);
+        if (kb == 0) mbar_wait(&b->full[islot], ipar, 10000 + __LINE__);
         tc_fence_after();
-#pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {
-          const uint32_t a_hi = act_addr + kb * ACT_BLOCK + ks * 32, a_lo = a_hi + ACT_SPLIT;
-          const uint32_t b_hi = ibase + kb * 2048 + ks * 32, b_lo = b_hi + 8192;
-          const uint64_t dah = make_desc(a_hi, 16, 1024, LAYOUT_SW128), dal = make_desc(a_lo, 16, 1024, LAYOUT_SW128);
-          const uint64_t dbh = make_desc(b_hi, 16, 1024, LAYOUT_SW128), dbl = make_desc(b_lo, 16, 1024, LAYOUT_SW128);
-          umma_bf16(tm_gp, dah, dbh, idesc_in, (kb | ks) ? 1u : 0u);
-          umma_bf16(tm_gp, dal, dbh, idesc_in, 1u);
-          umma_bf16(tm_gp, dah, dbl, idesc_in, 1u);
-        }
+        mma_in_block(act_addr, ibase, kb, tm_gp);
       } else {
         tc_fence_after();
       }
       if (kb == 1) {
-        if (do_d1) mma_acc16_half(act_addr, p_addr, tm_d1, 0, d1_started);
+        if (do_d1) mma_acc_half<32>(act_addr, p_addr, P_GROUP, tm_d1, 0, d1_started);
         if (release_img) umma_commit(&b->img_empty[0]);   // blocks 0, 1 of the image have been read for the last time
       }
     }
@@ -375,7 +375,7 @@ __device__ __forceinline__ void bwd_tail_issue(Bars* b, uint8_t* smem, Sync& s, 
       umma_commit(&b->gp_full);
     }
     if (do_d1) {
-      mma_acc16_half(act_addr, p_addr, tm_d1, 1, d1_started);
+      mma_acc_half<32>(act_addr, p_addr, P_GROUP, tm_d1, 1, d1_started);
       d1_started = true;
       umma_commit(&b->acc_done);
     }
@@ -389,16 +389,16 @@ __device__ __forceinline__ void d3_issue(Bars* b, uint8_t* smem, Sync& s, uint32
                                          bool lin = false) {
   if (ROLE == ROLE_MMA) {
     const uint32_t base = smem_u32(smem);
-    mbar_wait(&b->a_full, s.a_cnt & 1);
+    mbar_wait(&b->a_full, s.a_cnt & 1, 10000 + __LINE__);
     ++s.a_cnt;
     tc_fence_after();
-    mma_acc16_half(base + SmemMap::ACT, base + d3_off, tm_d3, 0, d3_started, lin);
+    mma_acc_half<16>(base + SmemMap::ACT, base + d3_off, 256, tm_d3, 0, d3_started, lin);
     mma_publish_d(b);                      // blocks 0, 1 of the h2 image may be overwritten
     if (lin) {                             // BPTT: the second half of the h2 image arrives separately
-      mbar_wait(&b->img_full[1], (s.i_cnt - 1) & 1);
+      mbar_wait(&b->img_full[1], (s.i_cnt - 1) & 1, 10000 + __LINE__);
       tc_fence_after();
     }
-    mma_acc16_half(base + SmemMap::ACT, base + d3_off, tm_d3, 1, d3_started, lin);
+    mma_acc_half<16>(base + SmemMap::ACT, base + d3_off, 256, tm_d3, 1, d3_started, lin);
     mma_publish_d(b);                      // blocks 2, 3
     d3_started = true;
   } else if (ROLE == ROLE_EPI || ROLE == ROLE_ROW) {
@@ -479,8 +479,8 @@ __global__ void pack_l1_image(const float* __restrict__ W1, const float* __restr
   *reinterpret_cast<uint4*>(img + off) = h;
   *reinterpret_cast<uint4*>(img + 8192 + off) = l;
 }
-// input-gradient image: value(i, n) = i < in_dim ? W1[i][n] : 0; 16 rows x 256 k, SW128 K-major per 64-k block:
-// [hi: 4 x 2 KB | lo: 4 x 2 KB]
+// input-gradient image: value(i, n) = i < in_dim ? W1[i][n] : 0; per 64-k block 32 rows (hi of rows 0..15, then lo of rows
+// 0..15) x 128 B, SW128 K-major: 4 x 4 KB
 __global__ void pack_in_image(const float* __restrict__ W1, int in_dim, uint8_t* __restrict__ img) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;   // (i, chunk): 16 x 32
   if (idx >= 512) return;
@@ -491,9 +491,9 @@ __global__ void pack_in_image(const float* __restrict__ W1, int in_dim, uint8_t*
   uint4 h, l;
   split2(x[0], x[1], h.x, l.x); split2(x[2], x[3], h.y, l.y); split2(x[4], x[5], h.z, l.z); split2(x[6], x[7], h.w, l.w);
   const int kb = cc >> 3, c = cc & 7;
-  const uint32_t off = kb * 2048 + (i >> 3) * 1024 + (i & 7) * 128 + ((c ^ (i & 7)) << 4);
-  *reinterpret_cast<uint4*>(img + off) = h;
-  *reinterpret_cast<uint4*>(img + 8192 + off) = l;
+  auto off = [&](int row) { return (uint32_t)(kb * 4096 + (row >> 3) * 1024 + (row & 7) * 128 + ((c ^ (row & 7)) << 4)); };
+  *reinterpret_cast<uint4*>(img + off(i)) = h;
+  *reinterpret_cast<uint4*>(img + off(16 + i)) = l;
 }
 
 // ---- self test: the three GEMM kinds against caller-provided fp32 data ---------------------------------------
@@ -524,8 +524,8 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) selftest_kernel(int kind, cons
             for (int e = 0; e < 8; ++e) x[e] = X[row * 16 + kh * 8 + e];
             uint4 h, l;
             split2(x[0], x[1], h.x, l.x); split2(x[2], x[3], h.y, l.y); split2(x[4], x[5], h.z, l.z); split2(x[6], x[7], h.w, l.w);
-            *reinterpret_cast<uint4*>(smem + SmemMap::PIMG + il_chunk_off(row, kh)) = h;
-            *reinterpret_cast<uint4*>(smem + SmemMap::PIMG + 4096 + il_chunk_off(row, kh)) = l;
+            *reinterpret_cast<uint4*>(smem + SmemMap::PIMG + p_chunk_off(row, kh)) = h;
+            *reinterpret_cast<uint4*>(smem + SmemMap::PIMG + p_chunk_off(row, 2 + kh)) = l;
           }
         }
       } else {
@@ -539,9 +539,10 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) selftest_kernel(int kind, cons
       const uint32_t lane_base = tmem + TM_WORK + ((uint32_t)((warp & 3) * 32) << 16);
       if (kind == 2) {
         if (hc == 0) {
-          float v[16];
+          float v[16], v2[16];
           tmem_ld16(lane_base, v);
-          for (int j = 0; j < 16; ++j) Z[row * 16 + j] = v[j];
+          tmem_ld16(lane_base + 16, v2);
+          for (int j = 0; j < 16; ++j) Z[row * 16 + j] = v[j] + v2[j];
         }
       } else {
         for (int c0 = hc * CW; c0 < (hc + 1) * CW; c0 += 32) {

@@ -112,7 +112,7 @@ __device__ __forceinline__ void store_image_follow(bool elected, Bars* b, const 
     const uint32_t par = (s.k_cnt - 1) & 1;                  // the big GEMM issued last
 #pragma unroll
     for (int kb = 0; kb < 4; ++kb) {
-      mbar_wait(&b->kb_done[kb], par);
+      mbar_wait(&b->kb_done[kb], par, 20000 + __LINE__);
       bulk_s2g(gdst + kb * ACT_BLOCK, ssrc + kb * ACT_BLOCK, ACT_BLOCK);
       bulk_s2g(gdst + ACT_SPLIT + kb * ACT_BLOCK, ssrc + ACT_SPLIT + kb * ACT_BLOCK, ACT_BLOCK);
       bulk_commit();
@@ -241,7 +241,7 @@ __device__ MPG_EPI_INLINE void epi_delta2_from_h2(Bars* b, const float* W3, floa
   for (int kb = 0; kb < 4; ++kb) {
     const int c0 = kb * 64 + hc * 16;
     if (kb == 2) {
-      mbar_wait(&b->img_full[1], img_parity);                 // second half of the h2 image has landed
+      mbar_wait(&b->img_full[1], img_parity, 20000 + __LINE__);                 // second half of the h2 image has landed
       if (wait_half1) epi_wait_d(b, *wait_half1);             // the D3 UMMAs have read blocks 2, 3 of the h2 image
     }
     float v[16];
@@ -290,32 +290,21 @@ __device__ MPG_EPI_INLINE void epi_delta1_blocks(Bars* b, uint32_t tm_work_lane,
     if (release_img && elected && (kb & 1)) mbar_arrive(&b->img_empty[kb >> 1]);
   }
 }
-// [x0..x15] -> INTERLEAVE image row (hi | lo 4 KB apart)
-__device__ __forceinline__ void write_row16(uint8_t* img, int row, const float* x, uint8_t* gimg = nullptr) {
-#pragma unroll
-  for (int kh = 0; kh < 2; ++kh) {
-    uint4 h, l;
-    split2(x[kh * 8 + 0], x[kh * 8 + 1], h.x, l.x);
-    split2(x[kh * 8 + 2], x[kh * 8 + 3], h.y, l.y);
-    split2(x[kh * 8 + 4], x[kh * 8 + 5], h.z, l.z);
-    split2(x[kh * 8 + 6], x[kh * 8 + 7], h.w, l.w);
-    if (img) {
-      *reinterpret_cast<uint4*>(img + il_chunk_off(row, kh)) = h;
-      *reinterpret_cast<uint4*>(img + 4096 + il_chunk_off(row, kh)) = l;
-    }
-    if (gimg) {
-      *reinterpret_cast<uint4*>(gimg + il_chunk_off(row, kh)) = h;
-      *reinterpret_cast<uint4*>(gimg + 4096 + il_chunk_off(row, kh)) = l;
-    }
-  }
+// delta3 image, one plane: the first 16-byte chunk of row `row` is [d0_hi, d1_hi, d0_lo, d1_lo, 0, 0, 0, 0] (hi and lo
+// side by side in N, see tc_gemm.cuh); the second chunk stays zero
+__device__ __forceinline__ void write_d3(uint8_t* img, int row, float d0, float d1) {
+  uint32_t h, l;
+  split2(d0, d1, h, l);
+  *reinterpret_cast<uint4*>(img + il_chunk_off(row, 0)) = make_uint4(h, l, 0u, 0u);
 }
 
-// [d0, d1, 0 ...] -> first 16-byte chunk of row `row` of the delta3 image (hi | lo); the second chunk stays zero
-__device__ __forceinline__ void write_d3(uint8_t* img, int row, float d0, float d1) {
-  uint4 h = make_uint4(0u, 0u, 0u, 0u), l = make_uint4(0u, 0u, 0u, 0u);
-  split2(d0, d1, h.x, l.x);
-  *reinterpret_cast<uint4*>(img + il_chunk_off(row, 0)) = h;
-  *reinterpret_cast<uint4*>(img + 4096 + il_chunk_off(row, 0)) = l;
+// g_p = delta1 . W1_hi^T + delta1 . W1_lo^T: columns [0,16) + [16,32) of the accumulator
+__device__ __forceinline__ void read_gp(uint32_t taddr, float (&g)[16]) {
+  float g2[16];
+  tmem_ld16(taddr, g);
+  tmem_ld16(taddr + 16, g2);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) g[i] += g2[i];
 }
 
 // named barriers between the epilogue warps (512 threads) and the row warps (128 threads)
@@ -361,7 +350,7 @@ __device__ __forceinline__ void run_rollout(const TcArgs& A, uint8_t* smem, Bars
   uint32_t acc_issued = 0;
   auto acc_wait = [&]() {
     if (ROLE == ROLE_ROW && d1_pending) {
-      mbar_wait(&b->acc_done, sy.acc_cnt & 1);
+      mbar_wait(&b->acc_done, sy.acc_cnt & 1, 20000 + __LINE__);
       ++sy.acc_cnt;
     }
     d1_pending = false;
@@ -420,12 +409,12 @@ __device__ __forceinline__ void run_rollout(const TcArgs& A, uint8_t* smem, Bars
         split2(x[2], x[3], h.y, l.y);
         split2(x[4], x[5], h.z, l.z);
         split2(x[6], x[7], h.w, l.w);
-        const uint32_t off = il_chunk_off(row, kh);
+        const uint32_t off = p_chunk_off(row, kh);
         *reinterpret_cast<uint4*>(p_img + off) = h;
-        *reinterpret_cast<uint4*>(p_img + 4096 + off) = l;
+        *reinterpret_cast<uint4*>(p_img + off + P_LO) = l;
         if (gimg) {
           *reinterpret_cast<uint4*>(gimg + off) = h;
-          *reinterpret_cast<uint4*>(gimg + 4096 + off) = l;
+          *reinterpret_cast<uint4*>(gimg + off + P_LO) = l;
         }
       }
     };
@@ -621,7 +610,7 @@ __device__ __forceinline__ void run_rollout(const TcArgs& A, uint8_t* smem, Bars
           const uint8_t* src = h2tile + (size_t)tt * (2 * ACT_SPLIT);
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
-            mbar_wait(&b->img_empty[h], sy.i_cnt & 1);
+            mbar_wait(&b->img_empty[h], sy.i_cnt & 1, 20000 + __LINE__);
             mbar_expect_tx(&b->img_full[h], ACT_SPLIT);
 #pragma unroll
             for (int sp = 0; sp < 2; ++sp)
@@ -672,11 +661,11 @@ __device__ __forceinline__ void run_rollout(const TcArgs& A, uint8_t* smem, Bars
           }
           if (reg) { d1_pending = true; ++acc_issued; }
           if (rowthread && !reg) {
-            mbar_wait(&b->gp_full, sy.gp_cnt & 1);
+            mbar_wait(&b->gp_full, sy.gp_cnt & 1, 20000 + __LINE__);
             ++sy.gp_cnt;
             tc_fence_after();
             float gin[16];
-            tmem_ld16(tm_gp + lane_off, gin);
+            read_gp(tm_gp + lane_off, gin);
             if (valid) {
               float go[MPG_MAX_OBS];
 #pragma unroll
@@ -732,7 +721,7 @@ __device__ __forceinline__ void run_rollout(const TcArgs& A, uint8_t* smem, Bars
         store_pending = false;
         stamp(1);
         if (ROLE == ROLE_EPI) {
-          mbar_wait(&b->img_full[0], sy.i_cnt & 1);         // first half of the h2 image landed
+          mbar_wait(&b->img_full[0], sy.i_cnt & 1, 20000 + __LINE__);         // first half of the h2 image landed
           stamp(3);
         }
         ++sy.i_cnt;
@@ -775,12 +764,12 @@ __device__ __forceinline__ void run_rollout(const TcArgs& A, uint8_t* smem, Bars
         }
         if (want_dw) { d1_pending = true; ++acc_issued; }
         if (t > 0 && rowthread) {
-          mbar_wait(&b->gp_full, sy.gp_cnt & 1);
+          mbar_wait(&b->gp_full, sy.gp_cnt & 1, 20000 + __LINE__);
           ++sy.gp_cnt;
           tc_fence_after();
           stamp(10);
           float gin[16];
-          tmem_ld16(tm_gp + lane_off, gin);
+          read_gp(tm_gp + lane_off, gin);
           if (valid) {
 #pragma unroll
             for (int j = 0; j < S; ++j) { lam[j] = g_s[j]; snext[j] = s[j]; }
@@ -808,7 +797,7 @@ __device__ __forceinline__ void run_rollout(const TcArgs& A, uint8_t* smem, Bars
       if (NA > 1) partial[L.ob3 + 1] = (mf->wsum[1] + mf->wsum[3]) + (mf->wsum[5] + mf->wsum[7]);
     }
   }
-  if (ROLE == ROLE_EPI && acc_issued > 0) mbar_wait(&b->acc_done, (acc_issued - 1) & 1);   // last D1 accumulation complete
+  if (ROLE == ROLE_EPI && acc_issued > 0) mbar_wait(&b->acc_done, (acc_issued - 1) & 1, 20000 + __LINE__);   // last D1 accumulation complete
   if (ROLE == ROLE_EPI) {
     tc_fence_before();
     if (elected) bulk_wait_all();
@@ -822,16 +811,17 @@ __device__ __forceinline__ void run_rollout(const TcArgs& A, uint8_t* smem, Bars
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
           const int f = half * 128 + row;
-          float v[16];
-          tmem_ld16(tm_d1 + half * 16 + lane_off, v);
+          float v[16], v2[16];
+          tmem_ld16(tm_d1 + half * 32 + lane_off, v);
+          tmem_ld16(tm_d1 + half * 32 + 16 + lane_off, v2);
 #pragma unroll
           for (int i = 0; i < 16; ++i)
-            if (i < A.pol.in_dim) partial[L.oW1 + (size_t)i * H + f] = v[i];
-          partial[L.ob1 + f] = v[BIAS_K];
+            if (i < A.pol.in_dim) partial[L.oW1 + (size_t)i * H + f] = v[i] + v2[i];
+          partial[L.ob1 + f] = v[BIAS_K] + v2[BIAS_K];
           tmem_ld16(tm_d3 + half * 16 + lane_off, v);
 #pragma unroll
           for (int j = 0; j < 2; ++j)
-            if (j < ncol3) partial[L.oW3 + (size_t)f * A.pol.out_dim + j] = v[j];
+            if (j < ncol3) partial[L.oW3 + (size_t)f * A.pol.out_dim + j] = v[j] + v[2 + j];
         }
       }
     }
@@ -954,21 +944,21 @@ __global__ void __launch_bounds__(192, 1) tc_dw_kernel(const __grid_constant__ D
     } else if (k < 6) {     // right operand delta2: all four blocks
       src = SLOT_D2 + (size_t)sp * ACT_SPLIT + (size_t)(k - 2) * ACT_BLOCK;
       dsto = DW_OFF_D2 + (sp * 4 + (k - 2)) * DW_BLK;
-    } else {                // [p|1] image
-      src = SLOT_P + (size_t)sp * 4096;
-      dsto = DW_OFF_P + sp * DW_R16;
-      bytes = DW_R16; qstep = DW_R16;
+    } else {                // [p|1] image: hi and lo chunks of an 8-row group are adjacent, one copy takes both
+      src = SLOT_P;
+      dsto = DW_OFF_P;
+      bytes = sp == 0 ? 2 * DW_R16 : 0; qstep = 2 * DW_R16;
     }
     uint32_t slot = 0, par = 0;
     for (int r = first; r < A.nrecords; r += stride) {
       const uint8_t* rec = A.store + (size_t)r * SLOT_BYTES;
       for (int q = 0; q < ACT_ROWS / DW_ROWS; ++q) {
         if (lane == 0) {
-          mbar_wait(&b->empty[slot], par ^ 1);
+          mbar_wait(&b->empty[slot], par ^ 1, 20000 + __LINE__);
           mbar_expect_tx(&b->full[slot], DW_STAGE);
         }
         __syncwarp();
-        if (lane < DW_COPIES) bulk_g2s(stage_buf + slot * DW_STAGE + dsto, rec + src + (size_t)q * qstep, bytes, &b->full[slot]);
+        if (lane < DW_COPIES && bytes) bulk_g2s(stage_buf + slot * DW_STAGE + dsto, rec + src + (size_t)q * qstep, bytes, &b->full[slot]);
         if (++slot == DW_NSTAGE) { slot = 0; par ^= 1; }
       }
     }
@@ -979,7 +969,7 @@ __global__ void __launch_bounds__(192, 1) tc_dw_kernel(const __grid_constant__ D
       const uint32_t sbase = smem_u32(stage_buf);
       uint32_t slot = 0, par = 0;
       for (int st = 0; st < nstages; ++st) {
-        mbar_wait(&b->full[slot], par);
+        mbar_wait(&b->full[slot], par, 20000 + __LINE__);
         tc_fence_after();
         const uint32_t base = sbase + slot * DW_STAGE;
 #pragma unroll
@@ -993,7 +983,7 @@ __global__ void __launch_bounds__(192, 1) tc_dw_kernel(const __grid_constant__ D
           auto LD2 = [&](int sp) { return make_desc(base + DW_OFF_D2 + sp * 4 * DW_BLK + mh * 2 * DW_BLK + ks * 2048, DW_BLK, 1024, LAYOUT_SW128); };
           // right operand [p|1] (MN-major INTERLEAVE, N = 16: halves 128 B apart (SBO), 8-row groups 256 B apart (LBO));
           // only its hi split is needed: the constant-1 column is exact in bf16
-          const uint64_t rp = make_desc(base + DW_OFF_P + ks * 512, 256, 128, LAYOUT_NONE);
+          const uint64_t rp = make_desc(base + DW_OFF_P + ks * 2 * P_GROUP, P_GROUP, 128, LAYOUT_NONE);
           umma_bf16(tmem + DW_TM_D2, L(0), R2(0), id256, acc);
           umma_bf16(tmem + DW_TM_D2, L(1), R2(0), id256, 1u);
           umma_bf16(tmem + DW_TM_D2, L(0), R2(1), id256, 1u);
@@ -1012,7 +1002,7 @@ __global__ void __launch_bounds__(192, 1) tc_dw_kernel(const __grid_constant__ D
     const int f = mh * 128 + warp * 32 + lane;                   // feature owned by this thread (TMEM lane)
     const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
     if (nstages > 0) {
-      mbar_wait(&b->d_full, 0);
+      mbar_wait(&b->d_full, 0, 20000 + __LINE__);
       tc_fence_after();
       for (int c0 = 0; c0 < 256; c0 += 32) {
         float v[32];

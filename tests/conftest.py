@@ -24,3 +24,18 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if 'gpu' in item.keywords:
             item.add_marker(skip)
+
+
+@pytest.fixture(autouse=True)
+def _report_wait_watchdog(request):
+    """If a kernel's mbarrier watchdog fired during a GPU test, say where (mpg_b200._lib.wait_debug)."""
+    yield
+    if 'gpu' not in request.keywords:
+        return
+    try:
+        from mpg_b200 import _lib
+        rec = _lib.wait_debug()
+    except Exception:
+        rec = None
+    if rec:
+        pytest.fail(f'mbarrier watchdog fired: {rec}', pytrace=False)
