@@ -1025,7 +1025,7 @@ int mpg_philox_noise(mpg_ctx* ctx, const mpg_rollout_params* p, float* out, void
 // prioritized replay
 // =====================================================================================================
 struct mpg_replay {
-  int capacity = 0, obs_dim = 0, act_dim = 0, size = 0, next_idx = 0;
+  int capacity = 0, maxsize = 0, obs_dim = 0, act_dim = 0, size = 0, next_idx = 0;   // capacity: power of two of the trees (it_capacity); maxsize: ring size
   double alpha = 0.6, beta = 0.4;
   float *obs = nullptr, *act = nullptr, *rew = nullptr, *obs1 = nullptr, *done = nullptr;
   double *sum_tree = nullptr, *min_tree = nullptr, *max_prio = nullptr;
@@ -1069,7 +1069,7 @@ int mpg_replay_create(int capacity, int obs_dim, int act_dim, double alpha, doub
   rb->err[0] = 0;
   int cap = 1;
   while (cap < capacity) cap *= 2;                       // it_capacity (buffer.py:119-121)
-  rb->capacity = cap; rb->obs_dim = obs_dim; rb->act_dim = act_dim; rb->alpha = alpha; rb->beta = beta;
+  rb->capacity = cap; rb->maxsize = capacity; rb->obs_dim = obs_dim; rb->act_dim = act_dim; rb->alpha = alpha; rb->beta = beta;
   bool ok = cudaMalloc(&rb->obs, (size_t)cap * obs_dim * 4) == cudaSuccess && cudaMalloc(&rb->obs1, (size_t)cap * obs_dim * 4) == cudaSuccess
             && cudaMalloc(&rb->act, (size_t)cap * act_dim * 4) == cudaSuccess && cudaMalloc(&rb->rew, (size_t)cap * 4) == cudaSuccess
             && cudaMalloc(&rb->done, (size_t)cap * 4) == cudaSuccess && cudaMalloc(&rb->sum_tree, (size_t)2 * cap * 8) == cudaSuccess
@@ -1096,13 +1096,13 @@ void mpg_replay_destroy(mpg_replay* rb) {
 int mpg_replay_add(mpg_replay* rb, int n, const float* obs, const float* act, const float* rew, const float* obs_tp1,
                    const float* done, const float* priorities, void* stream) {
   if (!rb || n <= 0 || !obs || !act || !rew || !obs_tp1) return rfail(rb, MPG_ERR_ARG, "bad argument to mpg_replay_add");
-  if (n > rb->capacity) return rfail(rb, MPG_ERR_ARG, "more transitions than the buffer capacity in one add");
+  if (n > rb->maxsize) return rfail(rb, MPG_ERR_ARG, "more transitions than the buffer capacity in one add");
   cudaStream_t st = (cudaStream_t)stream;
-  replay_write_kernel<<<(n + 127) / 128, 128, 0, st>>>(n, rb->capacity, rb->next_idx, rb->obs_dim, rb->act_dim, obs, act, rew,
+  replay_write_kernel<<<(n + 127) / 128, 128, 0, st>>>(n, rb->capacity, rb->maxsize, rb->next_idx, rb->obs_dim, rb->act_dim, obs, act, rew,
                                                         obs_tp1, done, priorities, rb->max_prio, rb->alpha, rb->obs, rb->act,
                                                         rb->rew, rb->obs1, rb->done, rb->sum_tree, rb->min_tree);
-  rb->next_idx = (rb->next_idx + n) % rb->capacity;
-  rb->size = rb->size + n < rb->capacity ? rb->size + n : rb->capacity;
+  rb->next_idx = (rb->next_idx + n) % rb->maxsize;                       // storage wraps at _maxsize (buffer.py:52-60)
+  rb->size = rb->size + n < rb->maxsize ? rb->size + n : rb->maxsize;
   return rebuild_tree(rb, st);
 }
 

@@ -10,7 +10,7 @@
 
 namespace mpg {
 
-__global__ void replay_write_kernel(int n, int capacity, int next_idx, int obs_dim, int act_dim,
+__global__ void replay_write_kernel(int n, int capacity, int maxsize, int next_idx, int obs_dim, int act_dim,
                                     const float* __restrict__ obs, const float* __restrict__ act,
                                     const float* __restrict__ rew, const float* __restrict__ obs_tp1,
                                     const float* __restrict__ done, const float* __restrict__ prio,
@@ -19,7 +19,7 @@ __global__ void replay_write_kernel(int n, int capacity, int next_idx, int obs_d
                                     double* sum_tree, double* min_tree) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const int slot = (next_idx + i) % capacity;
+  const int slot = (next_idx + i) % maxsize;   // ring of maxsize transitions; `capacity` only places the tree leaves
   for (int k = 0; k < obs_dim; ++k) {
     s_obs[(size_t)slot * obs_dim + k] = obs[(size_t)i * obs_dim + k];
     s_obs1[(size_t)slot * obs_dim + k] = obs_tp1[(size_t)i * obs_dim + k];

@@ -165,8 +165,17 @@ class PathTrackingEnv(object):
         z = torch.randn(4, n, device=dev, generator=g)
         vx = 15.0 + 10.0 * u[1]
         dy = z[0]
-        cols = [vx - 20.0, vx * torch.tan(0.15 * z[2]), 0.3 * z[3], dy, (math.pi / 9) * z[1], 600.0 * u[0]]
-        return torch.stack(cols + [dy] * self.num_future_data, 1).contiguous()
+        x = 600.0 * u[0]
+        cols = [vx - 20.0, vx * torch.tan(0.15 * z[2]), 0.3 * z[3], dy, (math.pi / 9) * z[1], x]
+        # future columns of _get_obs (path_tracking_env.py:384-402): delta_y of the pose against the reference path at
+        # x + k * v_x / 200 * 20 * 2; at reset y = delta_y + path_y(x)
+        path_y = lambda xs: (7.5 * torch.sin(xs * 2.0 * math.pi / 200.0) + 2.5 * torch.sin(xs * 2.0 * math.pi / 300.0)
+                             - 5.0 * torch.sin(xs * 2.0 * math.pi / 400.0))
+        y, xf = dy + path_y(x), x.clone()
+        for _ in range(self.num_future_data):
+            xf = xf + vx * 1.0 / 200.0 * 20.0 * 2.0
+            cols.append(y - path_y(xf))
+        return torch.stack(cols, 1).contiguous()
 
     def reset_done(self, fresh=None):
         """reset() of the reference without init_obs (path_tracking_env.py:422-454): agents whose `done` flag is set

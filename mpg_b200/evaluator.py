@@ -34,8 +34,13 @@ class Evaluator(object):
         self.preprocessor.set_params(params)
 
     def run_n_episodes(self, n=None, seed=777, fused=True):
-        """num_eval_agent parallel episodes of args.fixed_steps steps with the deterministic policy (compute_mode).
-        fused: the whole episode is one launch (mpg_env_sample without exploration noise and without restarts)."""
+        """n batches (default 1) of num_eval_agent parallel episodes of args.fixed_steps steps with the deterministic
+        policy (compute_mode), averaged (evaluator.py:115-145 runs n episodes one after the other).
+        fused: a whole batch of episodes is one launch (mpg_env_sample without exploration noise and without restarts)."""
+        n = max(1, int(n or 1))
+        if n > 1:
+            runs = [self.run_n_episodes(1, seed + k, fused) for k in range(n)]
+            return {k: (runs[0][k] if k == 'episode_len' else float(np.mean([r[k] for r in runs]))) for k in runs[0]}
         self.env._rng = np.random.default_rng(seed)      # same start states at every evaluation
         obs = self.env.reset()
         steps, agents = self.args.fixed_steps, obs.shape[0]

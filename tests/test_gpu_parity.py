@@ -105,7 +105,26 @@ def test_mpg_v2_compute_gradient_matches_reference_golden(backend):
 # ------------------------------------------------------------------------------------------------
 # CUDA vs oracle (fp64) on seeded inputs: variants and sizes
 # ------------------------------------------------------------------------------------------------
-def _nadp_vs_oracle(env_id, B, n, M, nfd, backend, seed=0, buffer_type='normal', tol_grad=TOL_GRAD, tol_scalar=2e-5):
+def _row_returns_vs_oracle(learner, args, w, batch, npol, n):
+    """Per-row n-step returns of the policy rollout (what the scalar losses are means of) against the fp64 oracle:
+    norm-relative error over the rows and the mean |R| that sets the scale of an absolute error of their mean."""
+    from oracle import mpg_oracle as O
+    from mpg_b200 import _lib
+    e = learner.engine
+    _, ret = e.policy_grad(e.dev(batch[0]), [0, n] if n else [0], [0.0, 1.0] if n else [1.0], M=args.M, full_bptt=True,
+                           q_net=_lib.NET_Q1, noise=e.dev(npol) if n else None)
+    nets = O.Nets(w, False, torch.float64)
+    with torch.no_grad():
+        ref = O.rollout(args, torch.float64, nets.policy, nets.policy, nets.Q1, O.to_t(batch[0], torch.float64),
+                        O.to_t(npol, torch.float64) if n else None, n)
+    rows = batch[0].shape[0]
+    got = ret.cpu().numpy().reshape(ret.shape[0], args.M, rows).mean(1)      # mean over the M tiles, like the reference
+    ref = ref.numpy()[[0, n] if n else [0]]
+    return max(rel_l2(got[i], ref[i]) for i in range(len(got))), float(np.abs(ref[-1]).mean())
+
+
+def _nadp_vs_oracle(env_id, B, n, M, nfd, backend, seed=0, buffer_type='normal', tol_grad=TOL_GRAD, tol_scalar=2e-5,
+                    per_row=False):
     from oracle import mpg_oracle as O
     args = default_args('NADP', env_id, replay_batch_size=B, M=M, num_future_data=nfd,
                         num_rollout_list_for_policy_update=[n], num_rollout_list_for_q_estimation=[n],
@@ -128,10 +147,21 @@ def _nadp_vs_oracle(env_id, B, n, M, nfd, backend, seed=0, buffer_type='normal',
                 value_mean=rel_l2(st['value_mean'], ref['value_mean']))
     if buffer_type != 'normal':
         errs['td'] = rel_l2(learner.get_info_for_buffer()['td_error'], ref['td_error'])
+    if per_row:
+        # the scalar statistics are means of per-row returns of both signs: hold the ROWS to the 1e-5 bar and the
+        # means to an absolute error of 2e-5 x mean |R| (a relative tolerance on a mean that nearly cancels is not a check)
+        row_err, scale = _row_returns_vs_oracle(learner, args, w, batch, npol, n)
+        errs['rows'] = row_err
+        assert row_err <= TOL_STATE, errs
+        for k in ('policy_loss', 'value_mean'):
+            assert abs(st[k] - ref[k]) <= 2e-5 * max(scale, abs(ref[k])), (k, st[k], ref[k], scale)
+        target_scale = float(np.abs(ref['q_targets']).mean())
+        assert abs(st['q_loss'] - ref['q_loss']) <= 2 * 2e-5 * max(target_scale ** 2, abs(ref['q_loss'])), (st['q_loss'], ref['q_loss'])
     print(env_id, B, n, M, nfd, backend, errs)
     assert errs['q'] <= tol_grad and errs['p'] <= tol_grad and errs['clipped'] <= tol_grad, errs
-    for k in ('q_loss', 'policy_loss', 'value_mean'):
-        assert errs[k] <= tol_scalar, errs
+    if not per_row:
+        for k in ('q_loss', 'policy_loss', 'value_mean'):
+            assert errs[k] <= tol_scalar, errs
     if 'td' in errs:
         assert errs['td'] <= tol_scalar, errs
     return learner
@@ -141,17 +171,16 @@ def _nadp_vs_oracle(env_id, B, n, M, nfd, backend, seed=0, buffer_type='normal',
 @pytest.mark.parametrize('B,n,M,nfd', [(256, 25, 1, 0), (100, 25, 1, 0), (1, 25, 1, 0), (48, 10, 2, 2), (64, 1, 1, 0), (300, 0, 1, 0),
                                        (2048, 25, 1, 0)])
 def test_nadp_pathtracking_vs_oracle(B, n, M, nfd, backend):
-    # split-bf16 contractions carry ~5e-6 relative error per GEMM; a batch of ONE row has no averaging and
-    # q_loss = 0.5 (Q - target)^2 doubles the relative error of the difference -> scalar tolerance 1e-4 there
-    tol_scalar = 1e-4 if (backend == 'tc' and B < 16) else 2e-5
-    _nadp_vs_oracle(PT, B, n, M, nfd, backend, buffer_type='priority' if B == 48 else 'normal', tol_scalar=tol_scalar)
+    # scalars to 2e-5 everywhere; a batch of ONE row has no mean to speak of (q_loss = 0.5 (Q - target)^2 is a difference of
+    # two nearly equal numbers): there the rows are held to 1e-5 and the scalars to the corresponding absolute error
+    _nadp_vs_oracle(PT, B, n, M, nfd, backend, buffer_type='priority' if B == 48 else 'normal', per_row=(B < 16))
 
 
 def test_tc_multi_tile_and_tail_split_vs_oracle():
     """More tiles than SMs (several tiles per CTA + the full-waves / tail-wave split with the side-stream weight
     gradient GEMMs) against the fp64 oracle, not only against itself: 20,011 rows = 157 tiles."""
-    # scalar tolerance 1e-4: the means over 20,011 returns are small numbers (n = 3) carrying the ~1e-5 per-row error
-    learner = _nadp_vs_oracle(PT, 20011, 3, 1, 0, 'tc', seed=9, tol_scalar=1e-4)
+    # the means over 20,011 short-horizon (n = 3) returns nearly cancel: rows to 1e-5, means to the matching absolute error
+    learner = _nadp_vs_oracle(PT, 20011, 3, 1, 0, 'tc', seed=9, per_row=True)
     assert learner.engine.num_sms < 157, 'the case is meant to exceed one wave'
 
 
@@ -166,8 +195,38 @@ def test_nadp_double_pendulum_vs_oracle(backend):
     # gradients, tests/test_oracle_golden.py): the north-star tolerance is checked on a short horizon,
     # the full horizon against the fp32-vs-fp64 spread of the oracle itself.
     _nadp_vs_oracle(IDP, 128, 3, 1, 0, backend)
-    loose = (0.5, 5e-3) if backend == 'tc' else (5e-2, 5e-3)   # chaotic beyond a few steps: sanity bound only
-    _nadp_vs_oracle(IDP, 128, 25, 1, 0, backend, tol_grad=loose[0], tol_scalar=loose[1])
+    _idp_full_horizon_vs_oracle_spread(backend)
+
+
+def _idp_full_horizon_vs_oracle_spread(backend):
+    """n = 25 on the falling double pendulum: rounding is amplified ~1e3-1e4 x over the 125 sub-steps, so the bar is the
+    sensitivity of the problem itself, measured as the distance between the oracle evaluated in fp32 and in fp64 on the
+    same inputs.  A correct fp32 implementation lands within a small multiple of that spread; K states the multiple:
+    the FFMA path rounds like the fp32 oracle (K = 4), the split-bf16 contractions carry ~2^-17 instead of 2^-24 per
+    product (x 128 per element, ~x 16 after the K = 256 averaging: K = 64)."""
+    from oracle import mpg_oracle as O
+    B, n = 128, 25
+    args = default_args('NADP', IDP, replay_batch_size=B, num_rollout_list_for_policy_update=[n],
+                        num_rollout_list_for_q_estimation=[n])
+    w = synthetic.make_policy_with_qs_weights(100, args.obs_dim, args.act_dim, 256, double_q=False)
+    batch = make_batch(200, IDP, B, 0)
+    rng = np.random.default_rng(300)
+    nq, npol = synthetic.make_noise(rng, n, B), synthetic.make_noise(rng, n, B)
+    learner = _learner('nadp', args, w, backend)
+    learner.set_rollout_noise(nq, npol)
+    flat = _flat(learner.compute_gradient(batch, None, None, 0))
+    st = learner.get_stats()
+    r64 = O.nadp_compute_gradient(args, w, batch, nq, npol, torch.float64)
+    r32 = O.nadp_compute_gradient(args, w, batch, nq, npol, torch.float32)
+    nQ = r64['q_grad'].size
+    got_p = _unclip(flat[nQ:], st['policy_gradient_norm'], args.gradient_clip_norm)
+    spread_p = rel_l2(r32['policy_grad'], r64['policy_grad'])
+    spread_l = rel_l2(r32['policy_loss'], r64['policy_loss'])
+    err_p, err_l = rel_l2(got_p, r64['policy_grad']), rel_l2(st['policy_loss'], r64['policy_loss'])
+    K = 4.0 if backend == 'ffma' else 64.0
+    print(IDP, 'n=25', backend, dict(err_grad=err_p, spread_grad=spread_p, err_loss=err_l, spread_loss=spread_l, K=K))
+    assert err_p <= K * max(spread_p, 1e-6), (err_p, spread_p)
+    assert err_l <= K * max(spread_l, 1e-7), (err_l, spread_l)
 
 
 @pytest.mark.parametrize('backend', BACKENDS)
@@ -376,6 +435,13 @@ def test_error_paths():
     bad.learner_version = 'MPG-v3'
     with pytest.raises(ValueError):
         MPGLearner(PolicyWithQs, bad)
+    # set_weights validates count and shapes like Keras' set_weights (weights built for another obs_dim / nfd)
+    pol = PolicyWithQs(**vars(args))
+    wrong = synthetic.make_policy_with_qs_weights(0, args.obs_dim + 2, args.act_dim, 256, double_q=False)
+    with pytest.raises(ValueError, match='shape'):
+        pol.set_weights(wrong)
+    with pytest.raises(ValueError, match='6 weight arrays'):
+        pol.engine.set_net_weights(0, wrong[0][:5])
 
 
 @pytest.mark.parametrize('version', ['MPG-v2', 'NADP'])
@@ -453,3 +519,112 @@ def test_tc_wave_tail_overlap_matches_single_launch(monkeypatch):
         res[mode] = [t.cpu().numpy() for t in e.policy_grad(obs, [0, n], [0.4, 0.6], full_bptt=True, use_philox=True, noise_seed=3)]
     assert np.array_equal(res['1'][1], res['0'][1])                      # returns: same kernels, same rows
     assert rel_l2(res['1'][0], res['0'][0]) <= 1e-5                      # gradient: same terms, different partial grouping
+
+
+# ------------------------------------------------------------------------------------------------
+# the benchmarked path itself against the oracle (B = 65,536, in-kernel Philox noise)
+# ------------------------------------------------------------------------------------------------
+_BENCH_ORACLE = {}
+
+
+def _bench_path_oracle(args, w, obs, n, seed, chunk=8192):
+    """fp64 oracle of the bench workload, evaluated in row chunks (the loss is a sum over rows): per-row returns R_n
+    and the policy gradient, with the noise from the numpy restatement of the kernel's Philox stream."""
+    from oracle import mpg_oracle as O
+    if 'ref' in _BENCH_ORACLE:
+        return _BENCH_ORACLE['ref']
+    B = obs.shape[0]
+    grad, rows = None, []
+    for lo in range(0, B, chunk):
+        hi = min(B, lo + chunk)
+        noise = synthetic.philox_normal(seed, hi - lo, n, global_rows=B, row_offset=lo)
+        nets = O.Nets(w, False, torch.float64)
+        ret = O.rollout(args, torch.float64, nets.policy, nets.policy, nets.Q1, O.to_t(obs[lo:hi], torch.float64),
+                        O.to_t(noise, torch.float64), n)
+        loss = -ret[n].sum() / B
+        g = np.concatenate([x.numpy().ravel() for x in torch.autograd.grad(loss, nets.policy)])
+        grad = g if grad is None else grad + g
+        rows.append(ret[n].detach().numpy())
+    _BENCH_ORACLE['ref'] = (np.concatenate(rows), grad)
+    return _BENCH_ORACLE['ref']
+
+
+@pytest.mark.parametrize('backend', BACKENDS)
+def test_bench_path_philox_65536_vs_oracle(backend):
+    """bench.py's device step (PathTracking NADP, B = 65,536, n = 25, full BPTT, use_philox) is compared with the fp64
+    oracle on the same noise stream: per-row returns <= 1e-5 (norm-relative over the rows), gradient <= 1e-4."""
+    from mpg_b200 import _lib
+    from mpg_b200.policy import PolicyWithQs
+    B, n, seed = 65536, 25, 7
+    args = default_args('NADP', PT, replay_batch_size=B)
+    w = synthetic.make_policy_with_qs_weights(0, args.obs_dim, args.act_dim, 256, double_q=False)
+    obs = synthetic.make_obs(np.random.default_rng(1234), PT, B)
+    pol = PolicyWithQs(**vars(args))
+    pol.set_weights(w)
+    e = pol.engine
+    if backend == 'tc' and not e.tc_available():
+        pytest.skip('tensor-core backend does not cover this configuration')
+    e.set_backend(1 if backend == 'tc' else 0)
+    g, ret = e.policy_grad(e.dev(obs), [n], [1.0], full_bptt=True, q_net=_lib.NET_Q1, use_philox=True, noise_seed=seed)
+    rows_ref, grad_ref = _bench_path_oracle(args, w, obs, n, seed)
+    err_rows = rel_l2(ret[0].cpu().numpy(), rows_ref)
+    err_grad = rel_l2(g.cpu().numpy(), grad_ref)
+    print('bench path', backend, dict(rows=err_rows, grad=err_grad))
+    assert err_rows <= TOL_STATE, err_rows
+    assert err_grad <= TOL_GRAD, err_grad
+
+
+def test_tc_closed_loop_margin_over_seeds():
+    """The tensor-core path's closed-loop error over 8 (weight, state, noise) seeds, worst per-step norm-relative error
+    of observations, rewards and actions separately: every seed must stay under 1e-5 (the margin is reported)."""
+    from oracle import mpg_oracle as O
+    from mpg_b200.policy import PolicyWithQs
+    B, n = 512, 25
+    args = default_args('NADP', PT, replay_batch_size=B)
+    pol = PolicyWithQs(**vars(args))
+    e = pol.engine
+    if not e.tc_available():
+        pytest.skip('tensor-core backend does not cover this configuration')
+    e.set_backend(1)
+    worst = dict(obs=0.0, rew=0.0, act=0.0)
+    for seed in range(8):
+        w = synthetic.make_policy_with_qs_weights(40 + seed, args.obs_dim, args.act_dim, 256, double_q=False)
+        rng = np.random.default_rng(60 + seed)
+        obs0 = synthetic.make_obs(rng, PT, B)
+        noise = synthetic.make_noise(rng, n, B)
+        pol.set_weights(w)
+        ret, t_obs, t_rew, t_act = e.rollout_forward(e.dev(obs0), [n], noise=e.dev(noise), want_traj=True)
+        ro, rr, ra = O.closed_loop(args, w[1], obs0, noise, n, torch.float64)
+        cur = dict(obs=max(rel_l2(t_obs[t].cpu().numpy(), ro[t]) for t in range(n)),
+                   rew=max(rel_l2(t_rew[t].cpu().numpy(), rr[t]) for t in range(n)),
+                   act=max(rel_l2(t_act[t].cpu().numpy(), ra[t]) for t in range(n + 1)))
+        print('seed', seed, cur)
+        for k in worst:
+            worst[k] = max(worst[k], cur[k])
+    print('worst over 8 seeds', worst)
+    assert max(worst.values()) <= TOL_STATE, worst
+
+
+def test_model_compute_rewards_matches_reference_golden():
+    """model.vehicle_dynamics.compute_rewards(states, scaled actions) (path_tracking_env.py:181-199) and
+    model.dynamics.compute_rewards(states) (inverted_pendulum_model.py:66-74, inverted_double_pendulum_model.py:89-100)
+    through mpg_compute_rewards, against the rewards of the reference's own open-loop trajectories."""
+    import math
+    from mpg_b200.envs_and_models import NAME2MODELCLS
+    from tests.util import model_case_inputs
+    for name in ('model_pt', 'model_pt_nfd2', 'model_ip', 'model_idp'):
+        case, gold = load_golden(name)
+        args, obs0, acts, noise, _ = model_case_inputs(case)
+        model = NAME2MODELCLS[case['env_id']](**vars(args))
+        model.set_noise(list(noise))
+        model.reset(obs0)
+        steps = case['n'] if 'idp' not in name else 4
+        for t in range(steps):
+            pre = model.states.clone()
+            model.rollout_out(acts[t])
+            if case['env_id'] == PT:      # reward of the PRE-step state and the scaled action (rollout_out :282-286)
+                scaled = torch.tensor(acts[t], device=pre.device) * torch.tensor([1.2 * math.pi / 9, 3.0], device=pre.device)
+                r = model.vehicle_dynamics.compute_rewards(pre, scaled)
+            else:                         # reward of the POST-step state
+                r = model.dynamics.compute_rewards(model.states)
+            assert rel_l2(r.cpu().numpy(), gold['open_rew__f64'][t]) <= TOL_STATE, (name, t)

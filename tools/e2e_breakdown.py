@@ -12,7 +12,7 @@ args = default_args('NADP', 'PathTracking-v0', replay_batch_size=B)
 L = NADPLearner(PolicyWithQs, args)
 L.set_weights(synthetic.make_policy_with_qs_weights(0, 6, 2, 256, double_q=False))
 L.engine.set_backend(1)   # (the default where the tensor-core path covers the configuration)
-batch = bench.make_inputs(B)
+batch = bench.make_inputs("PathTracking-v0", B)
 for _ in range(3): L.compute_gradient(batch, None, None, 0)
 def t(fn, n=10):
     torch.cuda.synchronize(); t0 = time.perf_counter()
