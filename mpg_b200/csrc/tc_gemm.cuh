@@ -119,10 +119,11 @@ __device__ __forceinline__ void consume_pad(Bars* b, Sync& s) {
 // N = 128 UMMAs).  K-block kb is issued as soon as the epilogue has published that 64-feature block of the
 // activation image, so the UMMAs overlap the epilogue that produces A.
 struct NoHook { __device__ __forceinline__ void operator()() const {} };
-template <typename Hook = NoHook>
+// FMT: element format of BOTH operands (forward GEMMs: fp16 pairs, dX GEMMs: bf16 pairs)
+template <int FMT = FMT_BF16, typename Hook = NoHook>
 __device__ __forceinline__ void mma_big(Bars* b, uint32_t act_addr, uint32_t ring_addr, Sync& s, uint32_t d_tmem,
                                         Hook hook = Hook(), bool wait_a = true) {
-  constexpr uint32_t idesc = make_idesc(128, 256, 0, 0);
+  constexpr uint32_t idesc = make_idesc(128, 256, 0, 0, FMT, FMT);
   for (int kb = 0; kb < 4; ++kb) {
     if (wait_a) mbar_wait(&b->a_blk[kb], s.g_cnt & 1, 10000 + __LINE__);
     tc_fence_after();
@@ -156,8 +157,9 @@ __device__ __forceinline__ void mma_big(Bars* b, uint32_t act_addr, uint32_t rin
 }
 // 64-column chunk c of the first-layer GEMM into chunk buffer c & 1.  Every streamed first-layer GEMM issues
 // exactly chunks 0..3, so buffer j is used twice per GEMM and the mbarrier parities depend on c only.
+template <int FMT>
 __device__ __forceinline__ void mma_l1_chunk(Bars* b, uint32_t p_addr, uint32_t bbase, int c, uint32_t tm_z1c) {
-  constexpr uint32_t idesc = make_idesc(128, 64, 0, 0);
+  constexpr uint32_t idesc = make_idesc(128, 64, 0, 0, FMT, FMT);
   mbar_wait(&b->z_empty[c & 1], ((c >> 1) & 1) ^ 1, 10000 + __LINE__);
   tc_fence_after();
   const uint64_t dah = make_desc(p_addr, 128, P_GROUP, LAYOUT_NONE), dal = make_desc(p_addr + P_LO, 128, P_GROUP, LAYOUT_NONE);
@@ -184,10 +186,10 @@ __device__ __forceinline__ void epi_release_chunk(Bars* b, int c) {
 // written and lets the image be overwritten half by half.
 // lin: the image is in the row-interleaved no-swizzle layout [chunk][row][16 B] (h2 images loaded from the h2 store):
 // MN-major INTERLEAVE, 8-row groups 128 B apart (LBO), 8-feature chunks 2048 B apart (SBO), 16 rows = 256 B per k-step.
-template <int N>
+template <int N, int B_FMT = FMT_BF16>
 __device__ __forceinline__ void mma_acc_half(uint32_t act_addr, uint32_t r_addr, uint32_t r_group, uint32_t d_tmem, int half,
                                              bool started, bool lin = false) {
-  constexpr uint32_t idesc = make_idesc(128, N, 1, 1);
+  constexpr uint32_t idesc = make_idesc(128, N, 1, 1, FMT_BF16, B_FMT);
   const uint32_t d = d_tmem + half * N;
 #pragma unroll
   for (int ks = 0; ks < ACT_ROWS / 16; ++ks) {
@@ -202,7 +204,7 @@ __device__ __forceinline__ void mma_acc_half(uint32_t act_addr, uint32_t r_addr,
 // first-layer GEMM: D[128 x 256] = P[128 x 16] . W1aug^T ; P is the INTERLEAVE image in shared memory,
 // W1aug image streamed as ONE stage = [hi: 256 rows x 32 B][lo: 256 rows x 32 B] = 16 KB
 __device__ __forceinline__ void mma_l1(Bars* b, uint32_t p_addr, uint32_t ring_addr, Sync& s, uint32_t d_tmem) {
-  constexpr uint32_t idesc = make_idesc(128, 256, 0, 0);
+  constexpr uint32_t idesc = make_idesc(128, 256, 0, 0, FMT_F16, FMT_F16);
   mbar_wait(&b->a_full, s.a_cnt & 1, 10000 + __LINE__);
   ++s.a_cnt;
   const uint32_t slot = s.stage & (NSLOT - 1), par = (s.stage / NSLOT) & 1;
@@ -304,16 +306,16 @@ __device__ __forceinline__ void fwd_pair_issue(Bars* b, uint8_t* smem, Sync& s, 
     mbar_wait(&b->full[slot], par, 10000 + __LINE__);
     tc_fence_after();
     const uint32_t bbase = ring + slot * STAGE_BYTES;
-    mma_l1_chunk(b, p_addr, bbase, 0, tm_z1c);
-    mma_l1_chunk(b, p_addr, bbase, 1, tm_z1c);
-    mma_l1_chunk(b, p_addr, bbase, 2, tm_z1c);
+    mma_l1_chunk<FMT_F16>(b, p_addr, bbase, 0, tm_z1c);
+    mma_l1_chunk<FMT_F16>(b, p_addr, bbase, 1, tm_z1c);
+    mma_l1_chunk<FMT_F16>(b, p_addr, bbase, 2, tm_z1c);
     ++s.stage;
     consume_pad(b, s);
     // the last chunk waits for the epilogue to have read chunk 1, which happens about when h1 block 0 is published:
     // issuing it BEFORE the first big UMMAs keeps it from queueing behind them in the tensor pipe
-    mma_l1_chunk(b, p_addr, bbase, 3, tm_z1c);
+    mma_l1_chunk<FMT_F16>(b, p_addr, bbase, 3, tm_z1c);
     umma_commit(&b->empty[slot]);
-    mma_big(b, base + SmemMap::ACT, ring, s, tm_work);
+    mma_big<FMT_F16>(b, base + SmemMap::ACT, ring, s, tm_work);
     mma_publish_d(b);
   } else {
     epi_publish_a(b);
@@ -341,7 +343,7 @@ __device__ __forceinline__ void bwd_tail_issue(Bars* b, uint8_t* smem, Sync& s, 
     mbar_wait(&b->full[slot], par, 10000 + __LINE__);
     tc_fence_after();
     const uint32_t bbase = ring + slot * STAGE_BYTES;
-    for (int c = 0; c < 4; ++c) mma_l1_chunk(b, p_addr, bbase, c, tm_z1c);
+    for (int c = 0; c < 4; ++c) mma_l1_chunk<FMT_BF16>(b, p_addr, bbase, c, tm_z1c);   // backward side: bf16 [p|1] image + bf16 W1aug
     umma_commit(&b->empty[slot]);
     ++s.stage;
     consume_pad(b, s);
@@ -445,6 +447,7 @@ __device__ __forceinline__ void cta_teardown(Bars* b, int mma_warp = EPI_WARPS +
 
 // ---- global weight-image packing (run once per set_weights) ------------------------------------------------
 // big image: value(row, k) = src[row * rs + k * cs], 256 rows x 256 k -> 8 stages (kb, h) of [hi 16 KB | lo 16 KB]
+template <bool F16>
 __global__ void pack_big_image(const float* __restrict__ src, int rs, int cs, uint8_t* __restrict__ img) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;   // one thread per (row, 8-element chunk): 256 x 32
   if (idx >= 256 * 32) return;
@@ -453,7 +456,7 @@ __global__ void pack_big_image(const float* __restrict__ src, int rs, int cs, ui
 #pragma unroll
   for (int e = 0; e < 8; ++e) x[e] = src[(size_t)row * rs + (size_t)(cc * 8 + e) * cs];
   uint4 h, l;
-  split2(x[0], x[1], h.x, l.x); split2(x[2], x[3], h.y, l.y); split2(x[4], x[5], h.z, l.z); split2(x[6], x[7], h.w, l.w);
+  split2x<F16>(x[0], x[1], h.x, l.x); split2x<F16>(x[2], x[3], h.y, l.y); split2x<F16>(x[4], x[5], h.z, l.z); split2x<F16>(x[6], x[7], h.w, l.w);
   const int hh = row >> 7, rr = row & 127, kb = cc >> 3, c = cc & 7;
   const size_t stage = (size_t)(kb * 4 + hh) * STAGE_BYTES;   // streamed in (k-block, split, n-half) order
   const uint32_t off = (rr >> 3) * 1024 + (rr & 7) * 128 + ((c ^ (rr & 7)) << 4);
@@ -462,6 +465,7 @@ __global__ void pack_big_image(const float* __restrict__ src, int rs, int cs, ui
 }
 // first-layer image: value(n, k) = k < in_dim ? W1[k][n] : (k == bias_k ? b1[n] : 0); 256 rows x 16 k,
 // INTERLEAVE K-major: [hi 8 KB | lo 8 KB]
+template <bool F16>
 __global__ void pack_l1_image(const float* __restrict__ W1, const float* __restrict__ b1, int in_dim, int bias_k,
                               uint8_t* __restrict__ img) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;   // (n, k-half): 256 x 2
@@ -474,7 +478,7 @@ __global__ void pack_l1_image(const float* __restrict__ W1, const float* __restr
     x[e] = k < in_dim ? W1[(size_t)k * H + n] : (k == bias_k ? b1[n] : 0.f);
   }
   uint4 h, l;
-  split2(x[0], x[1], h.x, l.x); split2(x[2], x[3], h.y, l.y); split2(x[4], x[5], h.z, l.z); split2(x[6], x[7], h.w, l.w);
+  split2x<F16>(x[0], x[1], h.x, l.x); split2x<F16>(x[2], x[3], h.y, l.y); split2x<F16>(x[4], x[5], h.z, l.z); split2x<F16>(x[6], x[7], h.w, l.w);
   const uint32_t off = il_chunk_off(n, kh);
   *reinterpret_cast<uint4*>(img + off) = h;
   *reinterpret_cast<uint4*>(img + 8192 + off) = l;
@@ -523,7 +527,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) selftest_kernel(int kind, cons
             float x[8];
             for (int e = 0; e < 8; ++e) x[e] = X[row * 16 + kh * 8 + e];
             uint4 h, l;
-            split2(x[0], x[1], h.x, l.x); split2(x[2], x[3], h.y, l.y); split2(x[4], x[5], h.z, l.z); split2(x[6], x[7], h.w, l.w);
+            split2h(x[0], x[1], h.x, l.x); split2h(x[2], x[3], h.y, l.y); split2h(x[4], x[5], h.z, l.z); split2h(x[6], x[7], h.w, l.w);
             *reinterpret_cast<uint4*>(smem + SmemMap::PIMG + p_chunk_off(row, kh)) = h;
             *reinterpret_cast<uint4*>(smem + SmemMap::PIMG + p_chunk_off(row, 2 + kh)) = l;
           }
@@ -561,7 +565,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) selftest_kernel(int kind, cons
     if (lane == 0)
       for (int rep = 0; rep < repeats; ++rep) {
         if (kind == 3) {          // weights streamed through the ring, no epilogue in the loop
-          mma_big(b, smem_u32(smem) + SmemMap::ACT, smem_u32(smem) + SmemMap::RING, s, tmem + TM_WORK, NoHook(), false);
+          mma_big<FMT_BF16>(b, smem_u32(smem) + SmemMap::ACT, smem_u32(smem) + SmemMap::RING, s, tmem + TM_WORK, NoHook(), false);
           if (rep == repeats - 1) mma_publish_d(b);
         } else if (kind == 4) {   // operands resident, no streaming: the tensor pipe's own rate for this shape
           constexpr uint32_t idesc = make_idesc(128, 256, 0, 0);

@@ -28,7 +28,8 @@ namespace tc {
 struct TcNet {
   const uint8_t* big_fwd;
   const uint8_t* big_dx;
-  const uint8_t* l1;
+  const uint8_t* l1;    // [W1; b1] as an fp16 pair: forward passes
+  const uint8_t* l1b;   // the same as a bf16 pair: first-layer recompute inside BPTT (meets the bf16 [p|1] image of D1)
   const uint8_t* in;
   const float* W3;   // [H][out_dim] natural
   const float* b2;
@@ -141,8 +142,8 @@ __device__ MPG_EPI_INLINE void epi_hidden1_blocks(Bars* b, uint32_t tm_zc_lane, 
     epi_release_chunk(b, kb);
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = elu_fast(v[i]);
-    act_store8(act, act + ACT_SPLIT, row, c0 >> 3, v);
-    act_store8(act, act + ACT_SPLIT, row, (c0 >> 3) + 1, v + 8);
+    act_store8<true>(act, act + ACT_SPLIT, row, c0 >> 3, v);
+    act_store8<true>(act, act + ACT_SPLIT, row, (c0 >> 3) + 1, v + 8);
     epi_block_done(b, kb);
   }
 }
@@ -383,7 +384,8 @@ __device__ __forceinline__ void run_rollout(const TcArgs& A, uint8_t* smem, Bars
     float rsum = 0.f, gpow = 1.f;
 
     // [sigma*obs(s) | act | 0.. | 1] -> p image (row warps)
-    auto write_pimg = [&](const float* st, const float* act_or_null, uint8_t* gimg = nullptr) {
+    // f16: forward computations read the image as an fp16 pair; BPTT (first-layer recompute, D1, the db2 record) as bf16
+    auto write_pimg = [&](const float* st, const float* act_or_null, bool f16, uint8_t* gimg = nullptr) {
       // every index below is a compile-time constant (fixed trip counts + predicates): o[] stays in registers, and the
       // image row is produced one 8-element chunk at a time
       float o[MPG_MAX_OBS];
@@ -405,10 +407,11 @@ __device__ __forceinline__ void run_rollout(const TcArgs& A, uint8_t* smem, Bars
           x[e] = i == BIAS_K ? 1.f : v;
         }
         uint4 h, l;
-        split2(x[0], x[1], h.x, l.x);
-        split2(x[2], x[3], h.y, l.y);
-        split2(x[4], x[5], h.z, l.z);
-        split2(x[6], x[7], h.w, l.w);
+        if (f16) {
+          split2h(x[0], x[1], h.x, l.x); split2h(x[2], x[3], h.y, l.y); split2h(x[4], x[5], h.z, l.z); split2h(x[6], x[7], h.w, l.w);
+        } else {
+          split2(x[0], x[1], h.x, l.x); split2(x[2], x[3], h.y, l.y); split2(x[4], x[5], h.z, l.z); split2(x[6], x[7], h.w, l.w);
+        }
         const uint32_t off = p_chunk_off(row, kh);
         *reinterpret_cast<uint4*>(p_img + off) = h;
         *reinterpret_cast<uint4*>(p_img + off + P_LO) = l;
@@ -495,7 +498,7 @@ __device__ __forceinline__ void run_rollout(const TcArgs& A, uint8_t* smem, Bars
 #pragma unroll
           for (int j = 0; j < S; ++j) c[j] = s[j];
         }
-        if (!given) write_pimg(s, nullptr, slot ? slot + SLOT_P : nullptr);
+        if (!given) write_pimg(s, nullptr, true);
       }
       if (!given) {
         float zpre[NA];
@@ -528,7 +531,7 @@ __device__ __forceinline__ void run_rollout(const TcArgs& A, uint8_t* smem, Bars
 #pragma unroll
           for (int j = 0; j < NA; ++j) A.act_ckpt[((size_t)kidx * MB + grow) * NA + j] = act[j];
         if (a.has_q) {
-          if (rowthread) write_pimg(s, act);
+          if (rowthread) write_pimg(s, act, true);
           qv = q_forward(false, nullptr);
         }
         if (valid && a.returns_out) a.returns_out[(size_t)kidx * MB + grow] = rsum + gpow * qv;
@@ -629,9 +632,19 @@ __device__ __forceinline__ void run_rollout(const TcArgs& A, uint8_t* smem, Bars
 #pragma unroll
             for (int j = 0; j < NA; ++j) ak[j] = valid ? A.act_ckpt[((size_t)kidx * MB + grow) * NA + j] : 0.f;
             acc_wait();
-            write_pimg(s, ak, qslot ? qslot + SLOT_P : nullptr);
+            write_pimg(s, ak, true);
           }
           const float qv = q_forward(true, qslot);         // h2q image in ACT
+          if (rowthread) {
+            // the forward part is done with the fp16 image (every z1 chunk has been consumed): the same row as a bf16 pair
+            // for the first-layer recompute / D1 of this part and the db2 record
+            float ak[NA];
+#pragma unroll
+            for (int j = 0; j < NA; ++j) ak[j] = valid ? A.act_ckpt[((size_t)kidx * MB + grow) * NA + j] : 0.f;
+            write_pimg(s, ak, false, qslot ? qslot + SLOT_P : nullptr);
+            fence_proxy_async();
+            mbar_arrive(&b->p_full);
+          }
           if (rowthread) {
             // upstream on Q: policy loss c w_k gamma^t, or the regression residual (Q - target) / B_global
             const float up = !valid ? 0.f : (reg ? (qv - A.q_target[i_idx]) * A.q_inv_rows : cscale * w_k * gp);
@@ -653,7 +666,7 @@ __device__ __forceinline__ void run_rollout(const TcArgs& A, uint8_t* smem, Bars
             if (qslot) store_image(elected, qslot + SLOT_D2, act_img, 2 * ACT_SPLIT);
             epi_wait_d(b, sy);
           }
-          bwd_tail_issue<ROLE>(b, smem, sy, A.q.l1, A.q.in, !reg, reg, d1_started, tm_z1c, tm_gp, tm_d1);
+          bwd_tail_issue<ROLE>(b, smem, sy, A.q.l1b, A.q.in, !reg, reg, d1_started, tm_z1c, tm_gp, tm_d1, true);
           if (ROLE == ROLE_EPI) {
             if (qslot) store_wait(elected);                // delta2 image read out before it is overwritten
             epi_delta1_blocks(b, tm_work + lane_off, tm_z1c + lane_off, act_img, row, hc);
@@ -731,7 +744,7 @@ __device__ __forceinline__ void run_rollout(const TcArgs& A, uint8_t* smem, Bars
         if (rowthread) {
           acc_wait();
           stamp(12);
-          write_pimg(s, nullptr, rec ? slot + SLOT_P : nullptr);
+          write_pimg(s, nullptr, false, rec ? slot + SLOT_P : nullptr);
           fence_proxy_async();
           mbar_arrive(&b->p_full);
           stamp(13);
@@ -754,7 +767,7 @@ __device__ __forceinline__ void run_rollout(const TcArgs& A, uint8_t* smem, Bars
           stamp(8);
         }
         // z1 recompute stream, g_p following the delta1 blocks, D1 += delta1^T [p|1]
-        bwd_tail_issue<ROLE>(b, smem, sy, A.pol.l1, A.pol.in, t > 0, want_dw, d1_started, tm_z1c, tm_gp, tm_d1, true, early_next);
+        bwd_tail_issue<ROLE>(b, smem, sy, A.pol.l1b, A.pol.in, t > 0, want_dw, d1_started, tm_z1c, tm_gp, tm_d1, true, early_next);
         if (ROLE == ROLE_PRODUCER && early_next) load_h2(t - 1);
         if (ROLE == ROLE_EPI) {
           epi_delta1_blocks(b, tm_work + lane_off, tm_z1c + lane_off, act_img, row, hc, rec, elected, early_next);
@@ -908,9 +921,10 @@ constexpr int DW_SMEM = DW_NSTAGE * DW_STAGE + 256 + 1024;      // dynamic share
 constexpr int DW_TM_D2 = 0, DW_TM_DB2 = 256;
 static_assert(DW_STAGE % 1024 == 0 && DW_ROWS % 16 == 0, "stages hold whole SW128 atoms and UMMA k-steps");
 static_assert(DW_SMEM <= 232448, "tc_dw_kernel shared memory");
+static_assert((2 * DW_BLK / 16) % 128 == 0, "h1 conversion: whole chunks per converter thread");
 
 struct DwBars {
-  uint64_t full[DW_NSTAGE], empty[DW_NSTAGE], d_full;
+  uint64_t full[DW_NSTAGE], empty[DW_NSTAGE], conv[DW_NSTAGE], d_full;
   uint32_t tmem_base;
 };
 
@@ -921,7 +935,7 @@ __global__ void __launch_bounds__(192, 1) tc_dw_kernel(const __grid_constant__ D
   DwBars* b = reinterpret_cast<DwBars*>(smem + DW_NSTAGE * DW_STAGE);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    for (int i = 0; i < DW_NSTAGE; ++i) { mbar_init(&b->full[i], 1); mbar_init(&b->empty[i], 1); }
+    for (int i = 0; i < DW_NSTAGE; ++i) { mbar_init(&b->full[i], 1); mbar_init(&b->empty[i], 1); mbar_init(&b->conv[i], 128); }
     mbar_init(&b->d_full, 1);
     fence_barrier_init();
   }
@@ -969,7 +983,7 @@ __global__ void __launch_bounds__(192, 1) tc_dw_kernel(const __grid_constant__ D
       const uint32_t sbase = smem_u32(stage_buf);
       uint32_t slot = 0, par = 0;
       for (int st = 0; st < nstages; ++st) {
-        mbar_wait(&b->full[slot], par, 20000 + __LINE__);
+        mbar_wait(&b->conv[slot], par, 20000 + __LINE__);      // stage landed and its h1 part converted to a bf16 pair
         tc_fence_after();
         const uint32_t base = sbase + slot * DW_STAGE;
 #pragma unroll
@@ -996,6 +1010,36 @@ __global__ void __launch_bounds__(192, 1) tc_dw_kernel(const __grid_constant__ D
       umma_commit(&b->d_full);
     }
   } else {
+    // ------------- converter + epilogue warps -------------
+    // The forward pass keeps h1 as an fp16 pair (the precision the layer-2 GEMM needs); delta2 is a bf16 pair (exponent
+    // range) and one UMMA cannot mix the two formats, so the h1 part of every stage is rewritten in place as a bf16 pair
+    // (16 significant bits: what the weight gradient had before) while the next stages are still in flight.
+    {
+      uint32_t slot = 0, par = 0;
+      for (int st = 0; st < nstages; ++st) {
+        mbar_wait(&b->full[slot], par, 20000 + __LINE__);
+        uint8_t* hi = stage_buf + slot * DW_STAGE + DW_OFF_H1;
+        uint8_t* lo = hi + 2 * DW_BLK;
+#pragma unroll
+        for (int i = 0; i < (2 * DW_BLK / 16) / 128; ++i) {
+          const int c = (int)threadIdx.x + i * 128;
+          const uint4 h = *reinterpret_cast<const uint4*>(hi + c * 16), l = *reinterpret_cast<const uint4*>(lo + c * 16);
+          const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+          uint32_t oh[4], ol[4];
+#pragma unroll
+          for (int w = 0; w < 4; ++w) {
+            const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&hw[w]));
+            const float2 d = __half22float2(*reinterpret_cast<const __half2*>(&lw[w]));
+            split2(a.x + d.x, a.y + d.y, oh[w], ol[w]);
+          }
+          *reinterpret_cast<uint4*>(hi + c * 16) = make_uint4(oh[0], oh[1], oh[2], oh[3]);
+          *reinterpret_cast<uint4*>(lo + c * 16) = make_uint4(ol[0], ol[1], ol[2], ol[3]);
+        }
+        fence_proxy_async();
+        mbar_arrive(&b->conv[slot]);
+        if (++slot == DW_NSTAGE) { slot = 0; par ^= 1; }
+      }
+    }
     // ------------------------------- epilogue: TMEM -> this CTA's partial gradient -------------------------------
     const GradLayout L(A.in_dim, A.out_dim);
     float* partial = A.partial + (size_t)blockIdx.x * A.partial_stride;

@@ -8,7 +8,8 @@ namespace mpg {
 struct TcNetImages {
   uint8_t* big_fwd = nullptr;   // Wt[n][k] = W2[k][n]   (z2 = h1 . W2)
   uint8_t* big_dx = nullptr;    // Wt[k][n] = W2[k][n]   (g_h1 = delta2 . W2^T)
-  uint8_t* l1 = nullptr;        // [W1; b1] as 256 x 16
+  uint8_t* l1 = nullptr;        // [W1; b1] as 256 x 16, fp16 pair (forward)
+  uint8_t* l1b = nullptr;       // the same as a bf16 pair (BPTT)
   uint8_t* in = nullptr;        // W1 as 16 x 256 (input gradient)
 };
 
@@ -45,7 +46,7 @@ inline bool tc_init(TcState& t, const mpg_config& cfg, int /*sms*/, size_t& ws_b
             && alloc((void**)&t.qtmp2, (size_t)cfg.max_rows * sizeof(float));
   for (int n = 0; n < MPG_NUM_NETS && ok; ++n)
     ok = alloc((void**)&t.nets[n].big_fwd, tc::BIG_IMAGE_BYTES) && alloc((void**)&t.nets[n].big_dx, tc::BIG_IMAGE_BYTES)
-         && alloc((void**)&t.nets[n].l1, 16384) && alloc((void**)&t.nets[n].in, 16384);
+         && alloc((void**)&t.nets[n].l1, 16384) && alloc((void**)&t.nets[n].l1b, 16384) && alloc((void**)&t.nets[n].in, 16384);
   if (!ok) return false;
   const int sm = tc::SM_TOTAL + 1024;
   ok = tc_set_smem(tc::selftest_kernel, tc::SmemMap::TOTAL + 1024)
@@ -65,7 +66,7 @@ inline bool tc_init(TcState& t, const mpg_config& cfg, int /*sms*/, size_t& ws_b
 inline void tc_destroy(TcState& t) {
   cudaFree(t.scratch_img); cudaFree(t.act_ckpt); cudaFree(t.z_ckpt); cudaFree(t.h2store); cudaFree(t.qtmp); cudaFree(t.qtmp2); cudaFree(t.store);
   for (int n = 0; n < MPG_NUM_NETS; ++n) {
-    cudaFree(t.nets[n].big_fwd); cudaFree(t.nets[n].big_dx); cudaFree(t.nets[n].l1); cudaFree(t.nets[n].in);
+    cudaFree(t.nets[n].big_fwd); cudaFree(t.nets[n].big_dx); cudaFree(t.nets[n].l1); cudaFree(t.nets[n].l1b); cudaFree(t.nets[n].in);
   }
 }
 
@@ -73,9 +74,10 @@ inline void tc_destroy(TcState& t) {
 inline bool tc_pack_weights(TcState& t, int net, const float* flat, int in_dim, int out_dim, cudaStream_t st) {
   if (!t.nets[net].big_fwd) return true;   // tensor-core path not configured for this handle
   const GradLayout L(in_dim, out_dim);
-  tc::pack_big_image<<<32, 256, 0, st>>>(flat + L.oW2, 1, H, t.nets[net].big_fwd);     // value(n,k) = W2[k][n]
-  tc::pack_big_image<<<32, 256, 0, st>>>(flat + L.oW2, H, 1, t.nets[net].big_dx);      // value(k,n) = W2[k][n]
-  tc::pack_l1_image<<<2, 256, 0, st>>>(flat + L.oW1, flat + L.ob1, in_dim, tc::BIAS_K, t.nets[net].l1);
+  tc::pack_big_image<true><<<32, 256, 0, st>>>(flat + L.oW2, 1, H, t.nets[net].big_fwd);     // value(n,k) = W2[k][n]
+  tc::pack_big_image<false><<<32, 256, 0, st>>>(flat + L.oW2, H, 1, t.nets[net].big_dx);      // value(k,n) = W2[k][n]
+  tc::pack_l1_image<true><<<2, 256, 0, st>>>(flat + L.oW1, flat + L.ob1, in_dim, tc::BIAS_K, t.nets[net].l1);
+  tc::pack_l1_image<false><<<2, 256, 0, st>>>(flat + L.oW1, flat + L.ob1, in_dim, tc::BIAS_K, t.nets[net].l1b);
   tc::pack_in_image<<<2, 256, 0, st>>>(flat + L.oW1, in_dim, t.nets[net].in);
   return cudaGetLastError() == cudaSuccess;
 }
@@ -83,7 +85,7 @@ inline bool tc_pack_weights(TcState& t, int net, const float* flat, int in_dim, 
 inline tc::TcNet tc_net(const TcState& t, int net, const float* flat, int in_dim, int out_dim) {
   const GradLayout L(in_dim, out_dim);
   tc::TcNet n;
-  n.big_fwd = t.nets[net].big_fwd; n.big_dx = t.nets[net].big_dx; n.l1 = t.nets[net].l1; n.in = t.nets[net].in;
+  n.big_fwd = t.nets[net].big_fwd; n.big_dx = t.nets[net].big_dx; n.l1 = t.nets[net].l1; n.l1b = t.nets[net].l1b; n.in = t.nets[net].in;
   n.W3 = flat + L.oW3; n.b2 = flat + L.ob2; n.b3 = flat + L.ob3;
   n.in_dim = in_dim; n.out_dim = out_dim;
   return n;
@@ -123,7 +125,7 @@ inline cudaError_t tc_selftest(TcState& t, int kind, const float* X, const float
     const char* g = getenv("MPG_SELFTEST_GRID");
     int grid = g ? atoi(g) & ~1 : 2;
     if (grid < 2) grid = 2;
-    tc::pack_big_image<<<32, 256, 0, st>>>(W, H, 1, t.scratch_img);
+    tc::pack_big_image<false><<<32, 256, 0, st>>>(W, H, 1, t.scratch_img);
     tc::pair_probe_kernel<<<grid, 192, tc::PAIR_SMEM, st>>>(X, t.scratch_img, Z, repeats);
     return cudaGetLastError();
   }
@@ -132,8 +134,8 @@ inline cudaError_t tc_selftest(TcState& t, int kind, const float* X, const float
     tc::selftest_kernel<<<g ? atoi(g) : 1, tc::CTA_THREADS, tc::SmemMap::TOTAL + 1024, st>>>(kind, X, t.scratch_img, Z, repeats);
     return cudaGetLastError();
   }
-  if (kind == 0) tc::pack_big_image<<<32, 256, 0, st>>>(W, H, 1, t.scratch_img);
-  else if (kind == 1) tc::pack_l1_image<<<2, 256, 0, st>>>(W, W, 16, -1, t.scratch_img);
+  if (kind == 0) tc::pack_big_image<false><<<32, 256, 0, st>>>(W, H, 1, t.scratch_img);
+  else if (kind == 1) tc::pack_l1_image<true><<<2, 256, 0, st>>>(W, W, 16, -1, t.scratch_img);
   else tc::pack_in_image<<<2, 256, 0, st>>>(W, 16, t.scratch_img);
   tc::selftest_kernel<<<1, tc::CTA_THREADS, tc::SmemMap::TOTAL + 1024, st>>>(kind, X, t.scratch_img, Z, repeats);
   return cudaGetLastError();
