@@ -422,6 +422,8 @@ def main():
         pass
     flop = flop_per_state_step(env_id, full_bptt)
     k_ms = float(np.mean(kernel_ms)) if kernel_ms else ms_per_step
+    if full_bptt and backend == 'tc' and rows > e.MAX_TC_FULL_BPTT_ROWS:
+        k_ms = ms_per_step      # the call is split into row chunks (several launches): the whole step is the denominator
     achieved_tf = rows * N_STEPS * flop / (k_ms * 1e-3) / 1e12
     # a kernel timed alone over a sub-100 ms region at full clocks: the burst figure is the honest denominator
     peak_tf = float(peaks.get('bf16_tflops', 1655.0))

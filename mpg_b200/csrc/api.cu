@@ -599,7 +599,11 @@ int mpg_policy_grad(mpg_ctx* ctx, const mpg_rollout_params* p, const float* obs,
     // the tail wave are two launches; the weight-gradient GEMMs of the full waves (HBM-bound) run on the side
     // stream on exactly the SMs the tail wave does not use.  Partial rows [0, sms): full waves, [sms, 2 sms): tail.
     const int tail = ntiles % ctx->sms, full = ntiles - tail;
-    const bool split = ctx->tail_overlap && ctx->aux && full > 0 && tail > 0 && ctx->sms - tail >= 16 && !ctx->prof;
+    // The side-stream GEMMs get only the SMs the tail wave leaves idle: worth it when that is a good part of the GPU (their
+    // work grows with the number of full waves); with a nearly full tail wave they would crawl on a handful of SMs, so
+    // the weight-gradient GEMMs then run on all SMs after the rollout.
+    const bool split = ctx->tail_overlap && ctx->aux && full > 0 && tail > 0 && !ctx->prof
+                       && (long long)(ctx->sms - tail) * 4 >= (long long)(full / ctx->sms) * ctx->sms / 2;
     CUDA_OK(ctx, cudaMemsetAsync(ctx->partial, 0, (size_t)(split ? 2 : 1) * ctx->sms * ctx->partial_stride * sizeof(float), st));
     if (ctx->timing) cudaEventRecord(ctx->ev0, st);
     if (!split) {
@@ -607,7 +611,7 @@ int mpg_policy_grad(mpg_ctx* ctx, const mpg_rollout_params* p, const float* obs,
       if (ctx->timing) { cudaEventRecord(ctx->ev1, st); ctx->timed = 1; }
       tc::DwArgs da = dw_args(0, ntiles, 0);
       int dgrid = 2 * da.nrecords < ctx->sms ? 2 * da.nrecords : (ctx->sms & ~1);
-      tc::tc_dw_kernel<<<dgrid, 192, dw_smem, st>>>(da);
+      tc::tc_dw_kernel<<<dgrid, tc::DW_THREADS, dw_smem, st>>>(da);
       reduce_partials_kernel<<<(L.total + 255) / 256, 256, 0, st>>>(ctx->partial, ctx->partial_stride, ctx->sms, L.total,
                                                                     grad_out, nullptr, nullptr);
       ctx->launches += 3;
@@ -621,11 +625,11 @@ int mpg_policy_grad(mpg_ctx* ctx, const mpg_rollout_params* p, const float* obs,
       CUDA_OK(ctx, tc_launch_rollout<true>(ctx->cfg.env, tb, tail, st));
       if (ctx->timing) { cudaEventRecord(ctx->ev1, st); ctx->timed = 1; }
       CUDA_OK(ctx, cudaStreamWaitEvent(ctx->aux, ctx->ev_wave, 0));
-      tc::tc_dw_kernel<<<(ctx->sms - tail) & ~1, 192, dw_smem, ctx->aux>>>(dw_args(0, full, 0));
+      tc::tc_dw_kernel<<<(ctx->sms - tail) & ~1, tc::DW_THREADS, dw_smem, ctx->aux>>>(dw_args(0, full, 0));
       CUDA_OK(ctx, cudaEventRecord(ctx->ev_aux, ctx->aux));
       tc::DwArgs db = dw_args(full, tail, ctx->sms);
       int dgrid = 2 * db.nrecords < ctx->sms ? 2 * db.nrecords : (ctx->sms & ~1);
-      tc::tc_dw_kernel<<<dgrid, 192, dw_smem, st>>>(db);
+      tc::tc_dw_kernel<<<dgrid, tc::DW_THREADS, dw_smem, st>>>(db);
       CUDA_OK(ctx, cudaStreamWaitEvent(st, ctx->ev_aux, 0));
       reduce_partials_kernel<<<(L.total + 255) / 256, 256, 0, st>>>(ctx->partial, ctx->partial_stride, 2 * ctx->sms, L.total,
                                                                     grad_out, nullptr, nullptr);
@@ -741,7 +745,7 @@ int mpg_q_grad(mpg_ctx* ctx, int net, int rows, int64_t global_rows, const float
     da.in_dim = qin; da.out_dim = 1;
     da.partial = ctx->partial; da.partial_stride = (long long)ctx->partial_stride;
     const int dgrid = 2 * da.nrecords < ctx->sms ? 2 * da.nrecords : (ctx->sms & ~1);
-    tc::tc_dw_kernel<<<dgrid, 192, tc::DW_SMEM, st>>>(da);
+    tc::tc_dw_kernel<<<dgrid, tc::DW_THREADS, tc::DW_SMEM, st>>>(da);
     const GradLayout L(qin, 1);
     reduce_partials_kernel<<<(L.total + 255) / 256, 256, 0, st>>>(ctx->partial, ctx->partial_stride, ctx->sms, L.total,
                                                                   grad_out, nullptr, nullptr);

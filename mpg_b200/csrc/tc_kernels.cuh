@@ -921,25 +921,27 @@ constexpr int DW_SMEM = DW_NSTAGE * DW_STAGE + 256 + 1024;      // dynamic share
 constexpr int DW_TM_D2 = 0, DW_TM_DB2 = 256;
 static_assert(DW_STAGE % 1024 == 0 && DW_ROWS % 16 == 0, "stages hold whole SW128 atoms and UMMA k-steps");
 static_assert(DW_SMEM <= 232448, "tc_dw_kernel shared memory");
-static_assert((2 * DW_BLK / 16) % 128 == 0, "h1 conversion: whole chunks per converter thread");
+
 
 struct DwBars {
   uint64_t full[DW_NSTAGE], empty[DW_NSTAGE], conv[DW_NSTAGE], d_full;
   uint32_t tmem_base;
 };
 
-__global__ void __launch_bounds__(192, 1) tc_dw_kernel(const __grid_constant__ DwArgs A) {
+constexpr int DW_CONV_WARPS = 8;                                // warps 0..7 convert h1 (0..3 also read the accumulators out)
+constexpr int DW_THREADS = (DW_CONV_WARPS + 2) * 32;           // + producer warp + mma warp
+__global__ void __launch_bounds__(DW_THREADS, 1) tc_dw_kernel(const __grid_constant__ DwArgs A) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* stage_buf = smem;                                    // DW_NSTAGE x DW_STAGE
   DwBars* b = reinterpret_cast<DwBars*>(smem + DW_NSTAGE * DW_STAGE);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    for (int i = 0; i < DW_NSTAGE; ++i) { mbar_init(&b->full[i], 1); mbar_init(&b->empty[i], 1); mbar_init(&b->conv[i], 128); }
+    for (int i = 0; i < DW_NSTAGE; ++i) { mbar_init(&b->full[i], 1); mbar_init(&b->empty[i], 1); mbar_init(&b->conv[i], DW_CONV_WARPS * 32); }
     mbar_init(&b->d_full, 1);
     fence_barrier_init();
   }
-  if (warp == 5) tmem_alloc(&b->tmem_base, TMEM_COLS);
+  if (warp == DW_CONV_WARPS + 1) tmem_alloc(&b->tmem_base, TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -948,7 +950,7 @@ __global__ void __launch_bounds__(192, 1) tc_dw_kernel(const __grid_constant__ D
   const int nmine = first < A.nrecords ? (A.nrecords - first + stride - 1) / stride : 0;
   const int nstages = nmine * (ACT_ROWS / DW_ROWS);
 
-  if (warp == 4) {
+  if (warp == DW_CONV_WARPS) {
     // ------------------------------- producer: one lane per bulk copy of a stage -------------------------------
     const int sp = lane / 7, k = lane % 7;
     size_t src = 0; uint32_t dsto = 0, bytes = DW_BLK, qstep = DW_BLK;
@@ -976,7 +978,7 @@ __global__ void __launch_bounds__(192, 1) tc_dw_kernel(const __grid_constant__ D
         if (++slot == DW_NSTAGE) { slot = 0; par ^= 1; }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == DW_CONV_WARPS + 1) {
     // ------------------------------- mma -------------------------------
     if (lane == 0) {
       constexpr uint32_t id256 = make_idesc(128, 256, 1, 1), id16 = make_idesc(128, 16, 1, 1);
@@ -1021,8 +1023,8 @@ __global__ void __launch_bounds__(192, 1) tc_dw_kernel(const __grid_constant__ D
         uint8_t* hi = stage_buf + slot * DW_STAGE + DW_OFF_H1;
         uint8_t* lo = hi + 2 * DW_BLK;
 #pragma unroll
-        for (int i = 0; i < (2 * DW_BLK / 16) / 128; ++i) {
-          const int c = (int)threadIdx.x + i * 128;
+        for (int i = 0; i < (2 * DW_BLK / 16) / (DW_CONV_WARPS * 32); ++i) {
+          const int c = (int)threadIdx.x + i * (DW_CONV_WARPS * 32);
           const uint4 h = *reinterpret_cast<const uint4*>(hi + c * 16), l = *reinterpret_cast<const uint4*>(lo + c * 16);
           const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
           uint32_t oh[4], ol[4];
@@ -1045,7 +1047,7 @@ __global__ void __launch_bounds__(192, 1) tc_dw_kernel(const __grid_constant__ D
     float* partial = A.partial + (size_t)blockIdx.x * A.partial_stride;
     const int f = mh * 128 + warp * 32 + lane;                   // feature owned by this thread (TMEM lane)
     const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
-    if (nstages > 0) {
+    if (nstages > 0 && warp < 4) {
       mbar_wait(&b->d_full, 0, 20000 + __LINE__);
       tc_fence_after();
       for (int c0 = 0; c0 < 256; c0 += 32) {
@@ -1063,7 +1065,7 @@ __global__ void __launch_bounds__(192, 1) tc_dw_kernel(const __grid_constant__ D
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) tmem_dealloc(tmem, TMEM_COLS);
+  if (warp == DW_CONV_WARPS + 1) tmem_dealloc(tmem, TMEM_COLS);
 }
 
 }  // namespace tc
