@@ -231,9 +231,9 @@ int mpg_tc_selftest(mpg_ctx* ctx, int kind, const float* X, const float* W, floa
  * mpg_policy_grad calls record clock64() stamps of one backward step of CTA 0. */
 int mpg_set_profile_buffer(mpg_ctx* ctx, long long* buf);
 /* Watchdog record of the kernels' mbarrier waits: a wait that does not complete within ~2 s traps (the launch fails
- * with a CUDA error instead of hanging the device) after storing {1, source line, block, thread, parity}. out[0] == 0:
- * no wait has timed out in this process. */
-int mpg_wait_debug(unsigned long long out[5]);
+ * with a CUDA error instead of hanging the device) after storing its place. out[0] = number of waits that timed out
+ * (0: none in this process); record k (k < 7) = out[4 + 4k ..] = {source line, block, thread, parity}. */
+int mpg_wait_debug(unsigned long long out[32]);
 
 /* counters for bench.py: kernels launched by this handle since creation */
 uint64_t mpg_launch_count(const mpg_ctx* ctx);

@@ -114,10 +114,12 @@ def load():
 
 
 def wait_debug():
-    """Watchdog record of the kernels' mbarrier waits: None, or dict(site=source line (+10000 tc_gemm.cuh, +20000
-    tc_kernels.cuh), block, thread, parity) of the wait that timed out and made the launch trap."""
-    out = (ctypes.c_uint64 * 5)()
+    """Watchdog records of the kernels' mbarrier waits: None, or a list of dict(role, site=source line (+10000
+    tc_gemm.cuh, +20000 tc_kernels.cuh), block, thread, parity), one per warpgroup that timed out before the launch trapped."""
+    out = (ctypes.c_uint64 * 32)()
     load().mpg_wait_debug(out)
     if not out[0]:
         return None
-    return dict(site=int(out[1]), block=int(out[2]), thread=int(out[3]), parity=int(out[4]))
+    roles = ['epi0', 'epi1', 'epi2', 'epi3', 'row', 'producer', 'mma']
+    return [dict(role=roles[k], site=int(out[4 + 4 * k]), block=int(out[5 + 4 * k]), thread=int(out[6 + 4 * k]),
+                 parity=int(out[7 + 4 * k]) - 1) for k in range(7) if out[7 + 4 * k]]

@@ -31,8 +31,8 @@ unsigned long long* g_wait_host = nullptr;
 bool wait_dbg_init() {
   if (g_wait_host) return true;
   unsigned long long* h = nullptr; unsigned long long* d = nullptr;
-  if (cudaHostAlloc((void**)&h, 64, cudaHostAllocMapped) != cudaSuccess) { cudaGetLastError(); return false; }
-  memset(h, 0, 64);
+  if (cudaHostAlloc((void**)&h, 256, cudaHostAllocMapped) != cudaSuccess) { cudaGetLastError(); return false; }
+  memset(h, 0, 256);
   if (cudaHostGetDevicePointer((void**)&d, h, 0) != cudaSuccess
       || cudaMemcpyToSymbol(mpg::tc::g_wait_dbg, &d, sizeof(d)) != cudaSuccess) {
     cudaGetLastError(); cudaFreeHost(h); return false;
@@ -304,9 +304,9 @@ int mpg_set_backend(mpg_ctx* ctx, int backend) {
 }
 
 // {flag, site, block, thread, parity} of the mbarrier wait that timed out (flag == 0: none); see tc_common.cuh
-int mpg_wait_debug(unsigned long long out[5]) {
+int mpg_wait_debug(unsigned long long out[32]) {
   if (!out) return MPG_ERR_ARG;
-  for (int i = 0; i < 5; ++i) out[i] = g_wait_host ? ((volatile unsigned long long*)g_wait_host)[i] : 0ull;
+  for (int i = 0; i < 32; ++i) out[i] = g_wait_host ? ((volatile unsigned long long*)g_wait_host)[i] : 0ull;
   return MPG_OK;
 }
 

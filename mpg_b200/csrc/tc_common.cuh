@@ -49,14 +49,19 @@ __device__ unsigned long long* g_wait_dbg = nullptr;
 #endif
 __device__ __noinline__ void mbar_timeout(int site, uint32_t parity) {
   if (g_wait_dbg) {
-    g_wait_dbg[1] = (unsigned long long)site;
-    g_wait_dbg[2] = (unsigned long long)blockIdx.x;
-    g_wait_dbg[3] = (unsigned long long)threadIdx.x;
-    g_wait_dbg[4] = (unsigned long long)parity;
+    // records {site, block, thread, parity} at g_wait_dbg[4 + 4 k], k = warpgroup of the thread (0..3 epilogue, 4 row warps,
+    // 5/6 producer / mma warp), g_wait_dbg[0] = flag.  The first thread to give up lingers a little before it traps, so that
+    // the other stuck roles of the CTA get to record as well.
+    const int w = (int)(threadIdx.x >> 5);
+    const int k = w >= 20 ? 5 + (w & 1) : w / 4;
+    volatile unsigned long long* r = g_wait_dbg + 4 + 4 * k;
+    r[0] = (unsigned long long)site;
+    r[1] = (unsigned long long)blockIdx.x;
+    r[2] = (unsigned long long)threadIdx.x;
+    r[3] = (unsigned long long)parity + 1ull;
     g_wait_dbg[0] = 1ull;
     __threadfence_system();
   }
-  __trap();
 }
 // try_wait suspends the thread in hardware (up to the time hint) and wakes it on phase completion, so
 // waiting warps do not burn issue slots of the warps doing the per-row math on the same sub-partition
@@ -64,7 +69,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int si
   if (mbar_try(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try(bar, parity)) {
-    if (clock64() - t0 > MPG_WAIT_LIMIT_CYCLES) mbar_timeout(site, parity);
+    if (clock64() - t0 > MPG_WAIT_LIMIT_CYCLES) {
+      mbar_timeout(site, parity);
+      const long long t1 = clock64();
+      while (clock64() - t1 < 400000000ll) {}     // a little later, so that the other stuck roles record too
+      __trap();
+    }
   }
 }
 #define MBAR_WAIT(bar, parity) mbar_wait((bar), (parity), __LINE__)

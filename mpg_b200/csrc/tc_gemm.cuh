@@ -58,6 +58,8 @@ struct Bars {
   uint64_t a_full;       // [p|a|1] image written (first-layer GEMMs)
   uint64_t a_blk[4];     // 64-feature block kb of the activation image written (K-block pipelining)
   uint64_t d_full;
+  uint64_t d_half;       // second publish of an accumulator that is handed over in two parts (forward GEMM halves, D3 halves): a
+                         // waiter that lags TWO phases behind a parity barrier never wakes up, so each part has its own barrier
   uint64_t z_full[2];    // first-layer chunk buffer j holds a fresh 64-column chunk (mma -> epilogue)
   uint64_t z_empty[2];   // chunk buffer j has been read out (epilogue -> mma)
   uint64_t acc_done;     // the D1 accumulation UMMAs have read the delta1 / [p|1] images
@@ -77,6 +79,7 @@ struct Sync {
   uint32_t a_cnt = 0;    // a_full phases seen
   uint32_t g_cnt = 0;    // a_blk[] phases seen (GEMMs whose A operand is the activation image)
   uint32_t d_cnt = 0;    // d_full phases seen
+  uint32_t h_cnt = 0;    // d_half phases seen
   uint32_t acc_cnt = 0;  // acc_done phases seen (epilogue side)
   uint32_t k_cnt = 0;    // big GEMMs issued so far (kb_done[] phases, epilogue side)
   uint32_t p_cnt = 0;    // p_full phases seen
@@ -262,6 +265,11 @@ __device__ __forceinline__ void epi_block_done(Bars* b, int kb) {
   mbar_arrive(&b->a_blk[kb]);
 }
 __device__ __forceinline__ void mma_publish_d(Bars* b) { umma_commit(&b->d_full); }
+__device__ __forceinline__ void epi_wait_half(Bars* b, Sync& s) {
+  mbar_wait(&b->d_half, s.h_cnt & 1, 10000 + __LINE__);
+  ++s.h_cnt;
+  tc_fence_after();
+}
 __device__ __forceinline__ void epi_wait_d(Bars* b, Sync& s) {
   mbar_wait(&b->d_full, s.d_cnt & 1, 10000 + __LINE__);
   ++s.d_cnt;
@@ -401,7 +409,7 @@ __device__ __forceinline__ void d3_issue(Bars* b, uint8_t* smem, Sync& s, uint32
       tc_fence_after();
     }
     mma_acc_half<16>(base + SmemMap::ACT, base + d3_off, 256, tm_d3, 1, d3_started, lin);
-    mma_publish_d(b);                      // blocks 2, 3
+    umma_commit(&b->d_half);               // blocks 2, 3
     d3_started = true;
   } else if (ROLE == ROLE_EPI || ROLE == ROLE_ROW) {
     epi_publish_a(b);                      // epilogue warps: h2 image in place; row warps: delta3 image written
@@ -425,6 +433,7 @@ __device__ __forceinline__ Bars* cta_setup(uint8_t* smem, int a_full_count = EPI
     mbar_init(&b->a_full, a_full_count);
     for (int i = 0; i < 4; ++i) mbar_init(&b->a_blk[i], EPI_THREADS);
     mbar_init(&b->d_full, 1);
+    mbar_init(&b->d_half, 1);
     for (int i = 0; i < 2; ++i) { mbar_init(&b->z_full[i], 1); mbar_init(&b->z_empty[i], EPI_THREADS); }
     mbar_init(&b->acc_done, 1);
     for (int i = 0; i < 4; ++i) mbar_init(&b->kb_done[i], 1);

@@ -218,7 +218,7 @@ __device__ MPG_EPI_INLINE void epi_delta2_blocks(Bars* b, const float* W3, float
                                                  Sync* wait_half1 = nullptr) {
   for (int kb = 0; kb < 4; ++kb) {
     const int c0 = kb * 64 + hc * 16;
-    if (kb == 2 && wait_half1) epi_wait_d(b, *wait_half1);   // the D3 UMMAs have read blocks 2, 3 of the h2 image
+    if (kb == 2 && wait_half1) epi_wait_half(b, *wait_half1);   // the D3 UMMAs have read blocks 2, 3 of the h2 image
     float v[16];
     act_load8(act, act + ACT_SPLIT, row, c0 >> 3, v);
     act_load8(act, act + ACT_SPLIT, row, (c0 >> 3) + 1, v + 8);
@@ -243,7 +243,7 @@ __device__ MPG_EPI_INLINE void epi_delta2_from_h2(Bars* b, const float* W3, floa
     const int c0 = kb * 64 + hc * 16;
     if (kb == 2) {
       mbar_wait(&b->img_full[1], img_parity, 20000 + __LINE__);                 // second half of the h2 image has landed
-      if (wait_half1) epi_wait_d(b, *wait_half1);             // the D3 UMMAs have read blocks 2, 3 of the h2 image
+      if (wait_half1) epi_wait_half(b, *wait_half1);          // the D3 UMMAs have read blocks 2, 3 of the h2 image
     }
     float v[16];
 #pragma unroll
