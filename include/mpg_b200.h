@@ -221,18 +221,21 @@ int mpg_get_backend(const mpg_ctx* ctx);
 int mpg_set_timing(mpg_ctx* ctx, int enabled);
 float mpg_kernel_ms(mpg_ctx* ctx);
 
+#ifdef MPG_DEBUG_PROBES   /* development probes: exported by libmpg_b200_dbg.so only, never by the product library */
 /* Self test of the tcgen05 GEMM building blocks (tests only). kind 0: Z[128x256] = X[128x256].W[256x256]^T;
  * kind 1: Z[128x256] = X[128x16].W[16x256]; kind 2: Z[128x16] = X[128x256].W[16x256]^T. fp32 device pointers.
  * kinds 3 / 4 are timing probes (tools/gemm_probe.py): the big GEMM `repeats` times back to back with streamed /
  * resident weights on MPG_SELFTEST_GRID CTAs; Z is not written. */
 int mpg_tc_selftest(mpg_ctx* ctx, int kind, const float* X, const float* W, float* Z, int repeats, void* stream);
 
-/* Debug timeline of the tensor-core rollout kernel: when `buf` (64 int64, device) is non-NULL the next
+/* Debug timeline of the tensor-core rollout kernel: when `buf` (128 int64, device) is non-NULL the next
  * mpg_policy_grad calls record clock64() stamps of one backward step of CTA 0. */
 int mpg_set_profile_buffer(mpg_ctx* ctx, long long* buf);
+#endif
 /* Watchdog record of the kernels' mbarrier waits: a wait that does not complete within ~2 s traps (the launch fails
- * with a CUDA error instead of hanging the device) after storing its place. out[0] = number of waits that timed out
- * (0: none in this process); record k (k < 7) = out[4 + 4k ..] = {source line, block, thread, parity}. */
+ * with a CUDA error instead of hanging the device) after storing its place. out[0] != 0: some wait has timed out in
+ * this process; record k (k < 7: epilogue warpgroups 0..3, row warps, producer, mma) = out[4 + 4k ..] =
+ * {source line, block, thread, parity + 1} (all zero: that role was not stuck). */
 int mpg_wait_debug(unsigned long long out[32]);
 
 /* counters for bench.py: kernels launched by this handle since creation */

@@ -5,6 +5,8 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get('MPG_B200_LIB', os.path.join(_HERE, 'libmpg_b200.so'))  # override: kernel-variant A/B runs
+# the same library built with -DMPG_DEBUG_PROBES (GEMM self tests, cta_group::2 probe, clock64 timeline): tests / tools only
+DEBUG_LIB_PATH = os.path.join(_HERE, 'libmpg_b200_dbg.so')
 
 MAX_OBS, MAX_LIST = 16, 8
 ENV_IDS = {'PathTracking-v0': 0, 'InvertedPendulumConti-v0': 1, 'InvertedDoublePendulum-v2': 2,
@@ -18,11 +20,13 @@ SYMBOLS = [
     'mpg_returns_tile_mean', 'mpg_q_grad', 'mpg_policy_forward', 'mpg_q_forward', 'mpg_q_target', 'mpg_td_error',
     'mpg_model_reset', 'mpg_model_step', 'mpg_model_step_bwd', 'mpg_compute_rewards', 'mpg_state_dim',
     'mpg_clip_global_norm', 'mpg_philox_noise', 'mpg_launch_count', 'mpg_set_backend', 'mpg_get_backend',
-    'mpg_set_timing', 'mpg_kernel_ms', 'mpg_tc_selftest', 'mpg_set_profile_buffer', 'mpg_wait_debug', 'mpg_adam_step', 'mpg_polyak_update', 'mpg_get_adam_state',
+    'mpg_set_timing', 'mpg_kernel_ms', 'mpg_wait_debug', 'mpg_adam_step', 'mpg_polyak_update', 'mpg_get_adam_state',
     'mpg_set_adam_state', 'mpg_env_sample',
     'mpg_replay_create', 'mpg_replay_destroy', 'mpg_replay_last_error', 'mpg_replay_size', 'mpg_replay_add',
     'mpg_replay_sample', 'mpg_replay_update_priorities', 'mpg_replay_tree_stats', 'mpg_q_bootstrap', 'mpg_env_step',
 ]
+# exported by libmpg_b200_dbg.so only (include/mpg_b200.h, #ifdef MPG_DEBUG_PROBES)
+DEBUG_SYMBOLS = ['mpg_tc_selftest', 'mpg_set_profile_buffer']
 
 
 class MpgConfig(ctypes.Structure):
@@ -42,19 +46,22 @@ class RolloutParams(ctypes.Structure):
 
 
 _lib = None
+_lib_dbg = None
 
 
-def load():
+def load(debug=False):
     """Load the shared library (once). Raises RuntimeError when it is absent: the product path
-    must fail loudly rather than fall back to anything else."""
-    global _lib
-    if _lib is not None:
-        return _lib
-    if not os.path.exists(LIB_PATH):
+    must fail loudly rather than fall back to anything else.  debug=True loads libmpg_b200_dbg.so (the same code
+    + the development probes) -- tests/test_gpu_tc.py and tools/ only."""
+    global _lib, _lib_dbg
+    if (debug and _lib_dbg is not None) or (not debug and _lib is not None):
+        return _lib_dbg if debug else _lib
+    path = DEBUG_LIB_PATH if debug else LIB_PATH
+    if not os.path.exists(path):
         raise RuntimeError(
-            f'{LIB_PATH} not found: build it first (python -c "import __graft_entry__ as g; g.build()" '
-            f'or make -C mpg_b200/csrc). mpg_b200 has no CPU fallback.')
-    lib = ctypes.CDLL(LIB_PATH)
+            f'{path} not found: build it first (python -c "import __graft_entry__ as g; g.build()" '
+            f'or make -C mpg_b200/csrc all). mpg_b200 has no CPU fallback.')
+    lib = ctypes.CDLL(path)
     vp, i32, i64, u64, f32 = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_uint64, ctypes.c_float
     P = ctypes.POINTER
     sig = {
@@ -107,9 +114,14 @@ def load():
         'mpg_replay_tree_stats': (i32, [vp, P(ctypes.c_double), P(ctypes.c_double), P(ctypes.c_double), vp]),
     }
     for name, (res, args) in sig.items():
+        if name in DEBUG_SYMBOLS and not debug:
+            continue
         fn = getattr(lib, name)  # AttributeError if the header and the library ever diverge
         fn.restype, fn.argtypes = res, args
-    _lib = lib
+    if debug:
+        _lib_dbg = lib
+    else:
+        _lib = lib
     return lib
 
 

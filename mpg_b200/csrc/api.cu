@@ -310,11 +310,13 @@ int mpg_wait_debug(unsigned long long out[32]) {
   return MPG_OK;
 }
 
+#ifdef MPG_DEBUG_PROBES
 int mpg_set_profile_buffer(mpg_ctx* ctx, long long* buf) {
   if (!ctx) return MPG_ERR_ARG;
   ctx->prof = buf;
   return MPG_OK;
 }
+#endif
 int mpg_set_timing(mpg_ctx* ctx, int enabled) {
   if (!ctx) return MPG_ERR_ARG;
   if (enabled && !ctx->ev0) {
@@ -332,12 +334,14 @@ float mpg_kernel_ms(mpg_ctx* ctx) {
   return ms;
 }
 
+#ifdef MPG_DEBUG_PROBES
 int mpg_tc_selftest(mpg_ctx* ctx, int kind, const float* X, const float* W, float* Z, int repeats, void* stream) {
   if (!ctx || !X || !W || !Z || kind < 0 || kind > 5 || repeats < 1) return fail(ctx, MPG_ERR_ARG, "bad argument to mpg_tc_selftest%s");
   CUDA_OK(ctx, tc_selftest(ctx->tc, kind, X, W, Z, repeats, (cudaStream_t)stream));
   ctx->launches += 2;
   return MPG_OK;
 }
+#endif
 
 int mpg_param_count(const mpg_ctx* ctx, int net) {
   if (net < 0 || net >= MPG_NUM_NETS) return -1;

@@ -509,6 +509,7 @@ __global__ void pack_in_image(const float* __restrict__ W1, int in_dim, uint8_t*
   *reinterpret_cast<uint4*>(img + off(16 + i)) = l;
 }
 
+#ifdef MPG_DEBUG_PROBES
 // ---- self test: the three GEMM kinds against caller-provided fp32 data ---------------------------------------
 //   kind 0: Z[128 x 256] = X[128 x 256] . (image of Wt[256 x 256])^T
 //   kind 1: Z[128 x 256] = X16[128 x 16] . (first-layer image)^T
@@ -597,6 +598,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) selftest_kernel(int kind, cons
   }
   cta_teardown(b);
 }
+#endif
 
 }  // namespace tc
 }  // namespace mpg

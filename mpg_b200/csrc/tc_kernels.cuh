@@ -358,10 +358,14 @@ __device__ __forceinline__ void run_rollout(const TcArgs& A, uint8_t* smem, Bars
   };
   float db3acc[2] = {0.f, 0.f};                  // row warps: sum of this row's delta3 over steps and tiles
   int prof_t = -1;   // step being traced
-  auto stamp = [&](int id) {
+  auto stamp = [&](int id) {      // clock64 timeline of one step of CTA 0 (tools/tc_timeline.py): debug library only
+#ifdef MPG_DEBUG_PROBES
     if (A.prof && blockIdx.x == 0 && prof_t >= 0
         && ((ROLE == ROLE_EPI && tid == 0) || ROLE == ROLE_MMA || (ROLE == ROLE_ROW && tid == EPI_THREADS)))
       A.prof[(ROLE == ROLE_MMA ? 32 : (ROLE == ROLE_ROW ? 64 : 0)) + id] = clock64();
+#else
+    (void)id; (void)prof_t;
+#endif
   };
 
   const int tile_end = A.tile1 > 0 && A.tile1 < ntiles ? A.tile1 : ntiles;

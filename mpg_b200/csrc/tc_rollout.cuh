@@ -1,7 +1,9 @@
 // Tensor-core (tcgen05) path: state owned by the handle, weight-image packing, launchers.
 #pragma once
 #include "tc_kernels.cuh"
+#ifdef MPG_DEBUG_PROBES
 #include "tc_pair_probe.cuh"
+#endif
 
 namespace mpg {
 
@@ -49,16 +51,17 @@ inline bool tc_init(TcState& t, const mpg_config& cfg, int /*sms*/, size_t& ws_b
          && alloc((void**)&t.nets[n].l1, 16384) && alloc((void**)&t.nets[n].l1b, 16384) && alloc((void**)&t.nets[n].in, 16384);
   if (!ok) return false;
   const int sm = tc::SM_TOTAL + 1024;
-  ok = tc_set_smem(tc::selftest_kernel, tc::SmemMap::TOTAL + 1024)
-       && tc_set_smem(tc::tc_rollout_kernel<MPG_ENV_PATH_TRACKING, true>, sm)
+  ok = tc_set_smem(tc::tc_rollout_kernel<MPG_ENV_PATH_TRACKING, true>, sm)
        && tc_set_smem(tc::tc_rollout_kernel<MPG_ENV_PATH_TRACKING, false>, sm)
        && tc_set_smem(tc::tc_rollout_kernel<MPG_ENV_INVERTED_PENDULUM, true>, sm)
        && tc_set_smem(tc::tc_rollout_kernel<MPG_ENV_INVERTED_PENDULUM, false>, sm)
        && tc_set_smem(tc::tc_rollout_kernel<MPG_ENV_INVERTED_DOUBLE_PENDULUM, true>, sm)
        && tc_set_smem(tc::tc_rollout_kernel<MPG_ENV_INVERTED_DOUBLE_PENDULUM, false>, sm)
        && tc_set_smem(tc::tc_rollout_kernel<MPG_ENV_PATH_TRACKING_REAL, false>, sm)
-       && tc_set_smem(tc::tc_dw_kernel, tc::DW_SMEM)
-       && tc_set_smem(tc::pair_probe_kernel, tc::PAIR_SMEM);
+       && tc_set_smem(tc::tc_dw_kernel, tc::DW_SMEM);
+#ifdef MPG_DEBUG_PROBES
+  ok = ok && tc_set_smem(tc::selftest_kernel, tc::SmemMap::TOTAL + 1024) && tc_set_smem(tc::pair_probe_kernel, tc::PAIR_SMEM);
+#endif
   t.ready = ok;
   return ok;
 }
@@ -118,6 +121,7 @@ inline cudaError_t tc_launch_rollout(int env, const tc::TcArgs& a, int grid, cud
   return cudaGetLastError();
 }
 
+#ifdef MPG_DEBUG_PROBES
 // self test of one GEMM kind (see tc_gemm.cuh): W is fp32 [256 x 256] (kind 0), [16 x 256] (kinds 1, 2)
 inline cudaError_t tc_selftest(TcState& t, int kind, const float* X, const float* W, float* Z, int repeats, cudaStream_t st) {
   if (!t.scratch_img) return cudaErrorNotSupported;
@@ -140,5 +144,6 @@ inline cudaError_t tc_selftest(TcState& t, int kind, const float* X, const float
   tc::selftest_kernel<<<1, tc::CTA_THREADS, tc::SmemMap::TOTAL + 1024, st>>>(kind, X, t.scratch_img, Z, repeats);
   return cudaGetLastError();
 }
+#endif
 
 }  // namespace mpg

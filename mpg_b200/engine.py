@@ -26,8 +26,8 @@ class Engine:
 
     def __init__(self, env_id, obs_dim, act_dim, obs_scale, rew_scale, rew_shift, gamma,
                  policy_out_activation='tanh', action_range=None, num_future_data=0, hidden=256,
-                 max_rows=4096, max_horizon=25, device=None, **_unused):
-        self.lib = _lib.load()
+                 max_rows=4096, max_horizon=25, device=None, debug_lib=False, **_unused):
+        self.lib = _lib.load(debug=bool(debug_lib))   # debug_lib: the library with the development probes (tests / tools)
         if not torch.cuda.is_available():
             raise RuntimeError('mpg_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback')
         self.device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
@@ -114,6 +114,7 @@ class Engine:
         return ok
 
     def tc_selftest(self, kind, X, W, repeats=1):
+        """GEMM building-block self test: needs Engine(..., debug_lib=True)."""
         Z = self.empty(256 if kind == 5 else 128, 16 if kind == 2 else 256)
         self._check(self.lib.mpg_tc_selftest(self.h, kind, _ptr(X), _ptr(W), _ptr(Z), repeats, self.stream))
         return Z

@@ -46,7 +46,7 @@ class PolicyWithQs(object):
                              rew_shift=kwargs.get('rew_shift', 0.0), gamma=kwargs.get('gamma', 0.99),
                              policy_out_activation=policy_out_activation, action_range=action_range,
                              num_future_data=kwargs.get('num_future_data', 0), max_rows=max(rows, 64),
-                             max_horizon=max(lists + [1]), device=kwargs.get('device'))
+                             max_horizon=max(lists + [1]), device=kwargs.get('device'), debug_lib=kwargs.get('debug_lib', False))
         # slot order == get_weights() order (policy.py:72-89)
         if policy_only:
             self.model_slots, self.target_slots = [_lib.NET_POLICY], []

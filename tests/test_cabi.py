@@ -3,6 +3,7 @@ path fails loudly without a GPU (no CPU fallback)."""
 import ctypes
 import os
 import re
+import subprocess
 
 import pytest
 import torch
@@ -10,9 +11,15 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _declared_symbols():
+def _declared_symbols(debug=False):
+    """Entry points include/mpg_b200.h declares: the product ABI, or (debug=True) the ones inside #ifdef MPG_DEBUG_PROBES."""
     src = open(os.path.join(ROOT, 'include', 'mpg_b200.h')).read()
     src = re.sub(r'/\*.*?\*/', '', src, flags=re.S)
+    dbg = ''.join(re.findall(r'#ifdef MPG_DEBUG_PROBES(.*?)#endif', src, flags=re.S))
+    if debug:
+        src = dbg
+    else:
+        src = re.sub(r'#ifdef MPG_DEBUG_PROBES.*?#endif', '', src, flags=re.S)
     return sorted(set(re.findall(r'\b(mpg_[a-z_0-9]+)\s*\(', src)))
 
 
@@ -27,6 +34,17 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, name), f'{name} declared in include/mpg_b200.h but not exported'
     assert sorted(_lib.SYMBOLS) == declared, 'python binding table out of sync with the header'
     _lib.load()  # sets argtypes for every symbol
+    # the development probes live in the debug build only: the product library exports the boundary and nothing else
+    probes = _declared_symbols(debug=True)
+    assert sorted(_lib.DEBUG_SYMBOLS) == probes and probes
+    for name in probes:
+        assert not hasattr(lib, name), f'{name} is a development probe and must not be exported by the product library'
+    dbg = ctypes.CDLL(_lib.DEBUG_LIB_PATH)
+    for name in declared + probes:
+        assert hasattr(dbg, name), f'{name} missing from the debug build'
+    exported = subprocess.run(['nm', '-D', '--defined-only', _lib.LIB_PATH], capture_output=True, text=True).stdout
+    extra = sorted(set(re.findall(r' T (mpg_[a-z_0-9]+)', exported)) - set(declared))
+    assert not extra, f'exported but not declared in include/mpg_b200.h: {extra}'
 
 
 def test_struct_layouts_match_header():

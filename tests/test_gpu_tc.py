@@ -11,7 +11,7 @@ pytestmark = pytest.mark.gpu
 
 def _engine():
     from mpg_b200.engine import Engine
-    return Engine(**vars(default_args('NADP', 'PathTracking-v0')))
+    return Engine(debug_lib=True, **vars(default_args('NADP', 'PathTracking-v0')))   # libmpg_b200_dbg.so: the probes are not in the product library
 
 
 @pytest.mark.parametrize('kind,repeats', [(0, 1), (0, 3), (1, 1), (1, 2), (2, 1), (2, 2)])

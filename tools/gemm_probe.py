@@ -5,7 +5,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 if len(sys.argv) > 1:
     import numpy as np, torch
     from mpg_b200.engine import Engine
-    e = Engine(env_id='PathTracking-v0', obs_dim=6, act_dim=2, obs_scale=None, rew_scale=1.0, rew_shift=0.0, gamma=1.0, max_rows=128, max_horizon=1)
+    e = Engine(env_id='PathTracking-v0', obs_dim=6, act_dim=2, obs_scale=None, rew_scale=1.0, rew_shift=0.0, gamma=1.0, max_rows=128, max_horizon=1, debug_lib=True)
     X = e.dev(np.zeros((128, 256), np.float32)); W = e.dev(np.zeros((256, 256), np.float32))
     e.tc_selftest(0, X, W)            # packs an image into the scratch buffer
     reps = 4000

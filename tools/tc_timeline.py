@@ -7,7 +7,7 @@ from mpg_b200.config import default_args
 from mpg_b200.policy import PolicyWithQs
 B = 65536
 args = default_args('NADP', 'PathTracking-v0', replay_batch_size=B)
-pol = PolicyWithQs(**vars(args)); pol.set_weights(synthetic.make_policy_with_qs_weights(1, 6, 2, 256, double_q=False))
+pol = PolicyWithQs(debug_lib=True, **vars(args)); pol.set_weights(synthetic.make_policy_with_qs_weights(1, 6, 2, 256, double_q=False))
 e = pol.engine; e.set_backend(1)
 obs = e.dev(synthetic.make_obs(np.random.default_rng(2), 'PathTracking-v0', B))
 buf = torch.zeros(128, dtype=torch.int64, device='cuda')
