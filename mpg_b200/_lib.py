@@ -6,7 +6,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get('MPG_B200_LIB', os.path.join(_HERE, 'libmpg_b200.so'))  # override: kernel-variant A/B runs
 # the same library built with -DMPG_DEBUG_PROBES (GEMM self tests, cta_group::2 probe, clock64 timeline): tests / tools only
-DEBUG_LIB_PATH = os.path.join(_HERE, 'libmpg_b200_dbg.so')
+DEBUG_LIB_PATH = os.environ.get('MPG_B200_DBG_LIB', os.path.join(_HERE, 'libmpg_b200_dbg.so'))
 
 MAX_OBS, MAX_LIST = 16, 8
 ENV_IDS = {'PathTracking-v0': 0, 'InvertedPendulumConti-v0': 1, 'InvertedDoublePendulum-v2': 2,
