@@ -51,6 +51,7 @@ struct mpg_ctx {
   float* partial = nullptr;
   float* loss_partial = nullptr;
   float* stats_part = nullptr;   // [MPG_MAX_LIST][RS_BLOCKS][2]
+  float* red_part = nullptr;     // [2][64] partial sums of the two-stage reductions (squared error, gradient norm)
   size_t partial_stride = 0;
   size_t ws_bytes = 0;
   uint64_t launches = 0;
@@ -111,19 +112,24 @@ __global__ void adam_kernel(float* __restrict__ w, float* __restrict__ m, float*
   w[i] -= lr_t * mi / (sqrtf(vi) + eps);
 }
 
-// loss_sum = sum_i 0.5 (q_i - target_i)^2, fixed-order single-block reduction
-__global__ void sq_err_kernel(const float* __restrict__ q, const float* __restrict__ target, int n, float* __restrict__ out) {
-  __shared__ float red[1024];
+// loss_sum = sum_i 0.5 (q_i - target_i)^2: CLIP_BLOCKS fixed slices, then their partial sums in index order
+__global__ void sq_err_partial_kernel(const float* __restrict__ q, const float* __restrict__ target, int n, float* __restrict__ part) {
+  __shared__ float red[256];
+  const int per = (n + 63) / 64, lo = blockIdx.x * per, hi = min(n, lo + per);
   float s = 0.f;
-#pragma unroll 8
-  for (int i = threadIdx.x; i < n; i += blockDim.x) { const float d = q[i] - target[i]; s = fmaf(0.5f * d, d, s); }
+  for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) { const float d = q[i] - target[i]; s = fmaf(0.5f * d, d, s); }
   red[threadIdx.x] = s;
   __syncthreads();
   for (int o = blockDim.x / 2; o > 0; o >>= 1) {
     if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
     __syncthreads();
   }
-  if (threadIdx.x == 0) out[0] = red[0];
+  if (threadIdx.x == 0) part[blockIdx.x] = red[0];
+}
+__global__ void sum_partials64_kernel(const float* __restrict__ part, float* __restrict__ out) {
+  float s = 0.f;
+  for (int b = 0; b < 64; ++b) s += part[b];
+  out[0] = s;
 }
 
 __global__ void polyak_kernel(float* __restrict__ dst, const float* __restrict__ src, int n, float tau) {
@@ -147,33 +153,33 @@ __global__ void reduce_partials_kernel(const float* __restrict__ partial, size_t
   }
 }
 
-__global__ void clip_kernel(float* __restrict__ g, int n, float clip, float* __restrict__ norm_out) {
-  // one block (fixed summation order => bit-reproducible); 8 independent loads in flight per thread hide the
-  // global-memory latency that otherwise serialises the 67 iterations of a 68K-float net
-  __shared__ float red[1024];
+// tf.clip_by_global_norm in two stages (a single block needed 45 us for a 68K-float net: latency bound): CLIP_BLOCKS blocks
+// sum the squares of fixed slices, then every block adds the partial sums in index order (bit-reproducible) and scales
+// its slice.
+constexpr int CLIP_BLOCKS = 64;
+__global__ void sumsq_partial_kernel(const float* __restrict__ g, int n, float* __restrict__ part) {
+  __shared__ float red[256];
+  const int per = (n + CLIP_BLOCKS - 1) / CLIP_BLOCKS, lo = blockIdx.x * per, hi = min(n, lo + per);
   float s = 0.f;
-  int i = threadIdx.x;
-  for (; i + 7 * (int)blockDim.x < n; i += 8 * blockDim.x) {
-    float v[8];
-#pragma unroll
-    for (int u = 0; u < 8; ++u) v[u] = g[i + u * blockDim.x];
-#pragma unroll
-    for (int u = 0; u < 8; ++u) s = fmaf(v[u], v[u], s);
-  }
-  for (; i < n; i += blockDim.x) s = fmaf(g[i], g[i], s);
+  for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) s = fmaf(g[i], g[i], s);
   red[threadIdx.x] = s;
   __syncthreads();
   for (int o = blockDim.x / 2; o > 0; o >>= 1) {
     if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
     __syncthreads();
   }
-  const float norm = sqrtf(red[0]);
+  if (threadIdx.x == 0) part[blockIdx.x] = red[0];
+}
+__global__ void clip_apply_kernel(float* __restrict__ g, int n, float clip, const float* __restrict__ part,
+                                  float* __restrict__ norm_out) {
+  float tot = 0.f;
+  for (int b = 0; b < CLIP_BLOCKS; ++b) tot += part[b];
+  const float norm = sqrtf(tot);
   const float scale = clip * fminf(1.f / norm, 1.f / clip);   // tf.clip_by_global_norm
-  if (scale != 1.f) {
-#pragma unroll 8
-    for (int j = threadIdx.x; j < n; j += blockDim.x) g[j] *= scale;
-  }
-  if (threadIdx.x == 0 && norm_out) norm_out[0] = norm;
+  const int per = (n + CLIP_BLOCKS - 1) / CLIP_BLOCKS, lo = blockIdx.x * per, hi = min(n, lo + per);
+  if (scale != 1.f)
+    for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) g[i] *= scale;
+  if (blockIdx.x == 0 && threadIdx.x == 0 && norm_out) norm_out[0] = norm;
 }
 
 // returns (n_list, M*rows) -> tile mean (n_list, rows) and/or sums over rows of mean, mean^2.
@@ -396,7 +402,7 @@ int mpg_create(const mpg_config* cfg, mpg_ctx** out) {
   c->partial_stride = (maxP + 3) & ~size_t(3);
   ok = ok && alloc(&c->ckpt, (size_t)(cfg->max_horizon + 1) * cfg->max_rows * c->S)
        && alloc(&c->partial, (size_t)2 * c->sms * c->partial_stride) && alloc(&c->loss_partial, c->sms)
-       && alloc(&c->stats_part, (size_t)MPG_MAX_LIST * 64 * 2);
+       && alloc(&c->stats_part, (size_t)MPG_MAX_LIST * 64 * 2) && alloc(&c->red_part, 128);
   if (ok) ok = tc_init(c->tc, c->cfg, c->sms, c->ws_bytes);
   wait_dbg_init();   // best effort: without it a timed-out wait still traps, only the record is missing
   if (!ok) {
@@ -443,7 +449,7 @@ void mpg_destroy(mpg_ctx* c) {
     cudaFree(c->nets[n].flat); cudaFree(c->nets[n].W1p); cudaFree(c->nets[n].W2p); cudaFree(c->nets[n].W2Tp);
     cudaFree(c->nets[n].adam_m); cudaFree(c->nets[n].adam_v);
   }
-  cudaFree(c->ckpt); cudaFree(c->partial); cudaFree(c->loss_partial); cudaFree(c->stats_part);
+  cudaFree(c->ckpt); cudaFree(c->partial); cudaFree(c->loss_partial); cudaFree(c->stats_part); cudaFree(c->red_part);
   if (c->ev0) { cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); }
   if (c->aux) { cudaStreamSynchronize(c->aux); cudaStreamDestroy(c->aux); }
   if (c->ev_wave) cudaEventDestroy(c->ev_wave);
@@ -753,8 +759,11 @@ int mpg_q_grad(mpg_ctx* ctx, int net, int rows, int64_t global_rows, const float
     const GradLayout L(qin, 1);
     reduce_partials_kernel<<<(L.total + 255) / 256, 256, 0, st>>>(ctx->partial, ctx->partial_stride, ctx->sms, L.total,
                                                                   grad_out, nullptr, nullptr);
-    if (loss_sum_out) sq_err_kernel<<<1, 1024, 0, st>>>(ctx->tc.qtmp, target, rows, loss_sum_out);
-    ctx->launches += 4;
+    if (loss_sum_out) {
+      sq_err_partial_kernel<<<64, 256, 0, st>>>(ctx->tc.qtmp, target, rows, ctx->red_part);
+      sum_partials64_kernel<<<1, 1, 0, st>>>(ctx->red_part, loss_sum_out);
+    }
+    ctx->launches += 5;
     CUDA_OK(ctx, cudaGetLastError());
     return MPG_OK;
   }
@@ -1009,8 +1018,9 @@ int mpg_compute_rewards(mpg_ctx* ctx, int rows, const float* state, const float*
 
 int mpg_clip_global_norm(mpg_ctx* ctx, float* grad, int n, float clip, float* norm_out, void* stream) {
   if (!ctx || !grad || n <= 0 || !(clip > 0.f)) return fail(ctx, MPG_ERR_ARG, "bad argument to mpg_clip_global_norm%s");
-  clip_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(grad, n, clip, norm_out);
-  ctx->launches++;
+  sumsq_partial_kernel<<<CLIP_BLOCKS, 256, 0, (cudaStream_t)stream>>>(grad, n, ctx->red_part + 64);
+  clip_apply_kernel<<<CLIP_BLOCKS, 256, 0, (cudaStream_t)stream>>>(grad, n, clip, ctx->red_part + 64, norm_out);
+  ctx->launches += 2;
   CUDA_OK(ctx, cudaGetLastError());
   return MPG_OK;
 }
