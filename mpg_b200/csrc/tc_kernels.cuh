@@ -52,6 +52,7 @@ struct TcArgs {
                             //    recomputing layer 2)
   uint8_t* store;           // dW operand store: [tile][step][SLOT_BYTES]
   int store_steps;          // steps recorded per tile: horizon+1 (full BPTT) or 1 (first action only)
+  int rec_hi_only;          // 1: the dW2 records keep only the hi plane of h1 / delta2 (large batches, see mpg_policy_grad)
   int tile0, tile1;         // tile range of this launch (tile1 == 0: all tiles); CTA c owns tile0 + c, tile0 + c + grid, ...
   int q_regress;            // 1: Q regression gradient (q_forward_and_backward): horizon 0, given actions,
                             //    upstream (Q - target) / B_global, dW operands of the Q net recorded, no policy part
@@ -108,14 +109,15 @@ __device__ __forceinline__ void store_image(bool elected, uint8_t* gdst, const u
 // (hi and lo 16 KB pieces of block kb) behind the GEMM; the next epilogue overwrites the image block by block and
 // waits for group kb only (store_wait_block), so the 128 KB store (~4.8 K cycles at the per-SM store rate) drains
 // under the GEMM tail and that epilogue instead of in front of it.
-__device__ __forceinline__ void store_image_follow(bool elected, Bars* b, const Sync& s, uint8_t* gdst, const uint8_t* ssrc) {
+__device__ __forceinline__ void store_image_follow(bool elected, Bars* b, const Sync& s, uint8_t* gdst, const uint8_t* ssrc,
+                                                   bool hi_only = false) {
   if (elected) {
     const uint32_t par = (s.k_cnt - 1) & 1;                  // the big GEMM issued last
 #pragma unroll
     for (int kb = 0; kb < 4; ++kb) {
       mbar_wait(&b->kb_done[kb], par, 20000 + __LINE__);
       bulk_s2g(gdst + kb * ACT_BLOCK, ssrc + kb * ACT_BLOCK, ACT_BLOCK);
-      bulk_s2g(gdst + ACT_SPLIT + kb * ACT_BLOCK, ssrc + ACT_SPLIT + kb * ACT_BLOCK, ACT_BLOCK);
+      if (!hi_only) bulk_s2g(gdst + ACT_SPLIT + kb * ACT_BLOCK, ssrc + ACT_SPLIT + kb * ACT_BLOCK, ACT_BLOCK);
       bulk_commit();
     }
   }
@@ -436,7 +438,7 @@ __device__ __forceinline__ void run_rollout(const TcArgs& A, uint8_t* smem, Bars
         if (store_pending) { store_wait(elected); store_pending = false; }   // the previous step's h1 record has left long ago
         epi_hidden1_blocks(b, tm_z1c + lane_off, act_img, row, hc);          // follows the z1 chunk stream
         stamp(18);
-        if (slot) { store_image_follow(elected, b, sy, slot + SLOT_H1, act_img); store_pending = true; }
+        if (slot) { store_image_follow(elected, b, sy, slot + SLOT_H1, act_img, A.rec_hi_only != 0); store_pending = true; }
         epi_wait_d(b, sy);                                   // z2 (all layer-2 UMMAs done)
         stamp(19);
         float p0, p1;
@@ -462,7 +464,7 @@ __device__ __forceinline__ void run_rollout(const TcArgs& A, uint8_t* smem, Bars
       if (ROLE == ROLE_EPI) {
         if (store_pending) { store_wait(elected); store_pending = false; }
         epi_hidden1_blocks(b, tm_z1c + lane_off, act_img, row, hc);
-        if (qslot) store_image(elected, qslot + SLOT_H1, act_img, 2 * ACT_SPLIT);
+        if (qslot) store_image(elected, qslot + SLOT_H1, act_img, A.rec_hi_only ? ACT_SPLIT : 2 * ACT_SPLIT);
         epi_wait_d(b, sy);
         float p0, p1;
         if (with_img) {
@@ -667,7 +669,7 @@ __device__ __forceinline__ void run_rollout(const TcArgs& A, uint8_t* smem, Bars
           gemm_issue<ROLE>(0, b, smem, sy, A.q.big_dx, tm_work);  // g_h1q, K-blocks issued as delta2 blocks appear
           if (ROLE == ROLE_EPI) {
             epi_delta2_blocks(b, mf->W3q, mf->d3s[row], 0.f, act_img, row, hc, reg ? &sy : nullptr);
-            if (qslot) store_image(elected, qslot + SLOT_D2, act_img, 2 * ACT_SPLIT);
+            if (qslot) store_image(elected, qslot + SLOT_D2, act_img, A.rec_hi_only ? ACT_SPLIT : 2 * ACT_SPLIT);
             epi_wait_d(b, sy);
           }
           bwd_tail_issue<ROLE>(b, smem, sy, A.q.l1b, A.q.in, !reg, reg, d1_started, tm_z1c, tm_gp, tm_d1, true);
@@ -766,7 +768,7 @@ __device__ __forceinline__ void run_rollout(const TcArgs& A, uint8_t* smem, Bars
           epi_delta2_from_h2(b, mf->W3p, mf->d3s[row], mf->d3s[ACT_ROWS + row], act_img, row, hc, (sy.i_cnt - 1) & 1,
                              want_dw ? &sy : nullptr);
           stamp(7);
-          if (rec) store_image_follow(elected, b, sy, slot + SLOT_D2, act_img);   // delta2 blocks leave behind their K-blocks
+          if (rec) store_image_follow(elected, b, sy, slot + SLOT_D2, act_img, A.rec_hi_only != 0);   // delta2 blocks leave behind their K-blocks
           epi_wait_d(b, sy);                                       // g_h1 complete, delta2 image consumed
           stamp(8);
         }
@@ -906,6 +908,7 @@ struct DwArgs {
   int in_dim, out_dim;     // gradient layout of the net
   float* partial;
   long long partial_stride;
+  int hi_only;             // records hold only the hi planes: one product per contraction instead of three
 };
 
 #ifndef MPG_DW_ROWS
@@ -975,10 +978,10 @@ __global__ void __launch_bounds__(DW_THREADS, 1) tc_dw_kernel(const __grid_const
       for (int q = 0; q < ACT_ROWS / DW_ROWS; ++q) {
         if (lane == 0) {
           mbar_wait(&b->empty[slot], par ^ 1, 20000 + __LINE__);
-          mbar_expect_tx(&b->full[slot], DW_STAGE);
+          mbar_expect_tx(&b->full[slot], A.hi_only ? 6 * DW_BLK + 2 * DW_R16 : DW_STAGE);
         }
         __syncwarp();
-        if (lane < DW_COPIES && bytes) bulk_g2s(stage_buf + slot * DW_STAGE + dsto, rec + src + (size_t)q * qstep, bytes, &b->full[slot]);
+        if (lane < DW_COPIES && bytes && !(A.hi_only && sp == 1 && k < 6)) bulk_g2s(stage_buf + slot * DW_STAGE + dsto, rec + src + (size_t)q * qstep, bytes, &b->full[slot]);
         if (++slot == DW_NSTAGE) { slot = 0; par ^= 1; }
       }
     }
@@ -1005,10 +1008,12 @@ __global__ void __launch_bounds__(DW_THREADS, 1) tc_dw_kernel(const __grid_const
           // only its hi split is needed: the constant-1 column is exact in bf16
           const uint64_t rp = make_desc(base + DW_OFF_P + ks * 2 * P_GROUP, P_GROUP, 128, LAYOUT_NONE);
           umma_bf16(tmem + DW_TM_D2, L(0), R2(0), id256, acc);
-          umma_bf16(tmem + DW_TM_D2, L(1), R2(0), id256, 1u);
-          umma_bf16(tmem + DW_TM_D2, L(0), R2(1), id256, 1u);
+          if (!A.hi_only) {
+            umma_bf16(tmem + DW_TM_D2, L(1), R2(0), id256, 1u);
+            umma_bf16(tmem + DW_TM_D2, L(0), R2(1), id256, 1u);
+          }
           umma_bf16(tmem + DW_TM_DB2, LD2(0), rp, id16, acc);
-          umma_bf16(tmem + DW_TM_DB2, LD2(1), rp, id16, 1u);
+          if (!A.hi_only) umma_bf16(tmem + DW_TM_DB2, LD2(1), rp, id16, 1u);
         }
         umma_commit(&b->empty[slot]);
         if (++slot == DW_NSTAGE) { slot = 0; par ^= 1; }
@@ -1029,7 +1034,8 @@ __global__ void __launch_bounds__(DW_THREADS, 1) tc_dw_kernel(const __grid_const
 #pragma unroll
         for (int i = 0; i < (2 * DW_BLK / 16) / (DW_CONV_WARPS * 32); ++i) {
           const int c = (int)threadIdx.x + i * (DW_CONV_WARPS * 32);
-          const uint4 h = *reinterpret_cast<const uint4*>(hi + c * 16), l = *reinterpret_cast<const uint4*>(lo + c * 16);
+          const uint4 h = *reinterpret_cast<const uint4*>(hi + c * 16);
+          const uint4 l = A.hi_only ? make_uint4(0u, 0u, 0u, 0u) : *reinterpret_cast<const uint4*>(lo + c * 16);
           const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
           uint32_t oh[4], ol[4];
 #pragma unroll
@@ -1039,7 +1045,7 @@ __global__ void __launch_bounds__(DW_THREADS, 1) tc_dw_kernel(const __grid_const
             split2(a.x + d.x, a.y + d.y, oh[w], ol[w]);
           }
           *reinterpret_cast<uint4*>(hi + c * 16) = make_uint4(oh[0], oh[1], oh[2], oh[3]);
-          *reinterpret_cast<uint4*>(lo + c * 16) = make_uint4(ol[0], ol[1], ol[2], ol[3]);
+          if (!A.hi_only) *reinterpret_cast<uint4*>(lo + c * 16) = make_uint4(ol[0], ol[1], ol[2], ol[3]);
         }
         fence_proxy_async();
         mbar_arrive(&b->conv[slot]);

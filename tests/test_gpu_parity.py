@@ -629,3 +629,40 @@ def test_model_compute_rewards_matches_reference_golden():
             else:                         # reward of the POST-step state
                 r = model.dynamics.compute_rewards(model.states)
             assert rel_l2(r.cpu().numpy(), gold['open_rew__f64'][t]) <= TOL_STATE, (name, t)
+
+
+def test_tc_hi_only_records_vs_full_records(monkeypatch):
+    """Large contractions (rows x recorded steps >= 262,144) keep only the hi plane of the dW2 operand records
+    (api.cu: rec_hi_only).  At the smallest batch where that applies the gradient must stay within the 1e-4 bar of the
+    fp64 oracle and close to the full-record result; MPG_REC_HI_ONLY forces either mode."""
+    from oracle import mpg_oracle as O
+    from mpg_b200 import _lib
+    from mpg_b200.policy import PolicyWithQs
+    B, n = 10112, 25                      # 10112 x 26 = 262,912 (row, step) pairs: just over the threshold
+    args = default_args('NADP', PT, replay_batch_size=B)
+    w = synthetic.make_policy_with_qs_weights(5, args.obs_dim, args.act_dim, 256, double_q=False)
+    obs = synthetic.make_obs(np.random.default_rng(6), PT, B)
+    noise = synthetic.make_noise(np.random.default_rng(7), n, B)
+    res = {}
+    for mode in ('1', '0', 'auto'):
+        if mode == 'auto':
+            monkeypatch.delenv('MPG_REC_HI_ONLY', raising=False)
+        else:
+            monkeypatch.setenv('MPG_REC_HI_ONLY', mode)
+        pol = PolicyWithQs(**vars(args))
+        pol.set_weights(w)
+        e = pol.engine
+        if not e.tc_available():
+            pytest.skip('tensor-core backend does not cover this configuration')
+        e.set_backend(1)
+        g, _ = e.policy_grad(e.dev(obs), [n], [1.0], full_bptt=True, q_net=_lib.NET_Q1, noise=e.dev(noise))
+        res[mode] = g.cpu().numpy()
+    nets = O.Nets(w, False, torch.float64)
+    ret = O.rollout(args, torch.float64, nets.policy, nets.policy, nets.Q1, O.to_t(obs, torch.float64),
+                    O.to_t(noise, torch.float64), n)
+    ref = np.concatenate([x.numpy().ravel() for x in torch.autograd.grad(-ret[n].mean(), nets.policy)])
+    errs = {m: rel_l2(g, ref) for m, g in res.items()}
+    print('hi-only records', errs, 'hi vs full', rel_l2(res['1'], res['0']))
+    assert np.array_equal(res['auto'], res['1']), 'the automatic mode must pick hi-only records at this size'
+    assert errs['1'] <= TOL_GRAD and errs['0'] <= TOL_GRAD, errs
+    assert rel_l2(res['1'], res['0']) <= 5e-5
