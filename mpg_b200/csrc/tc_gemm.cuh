@@ -24,9 +24,10 @@ constexpr int EPI_WARPS = MPG_EPI_WARPS;                 // 4 per TMEM lane quad
 constexpr int EPI_THREADS = EPI_WARPS * 32;
 constexpr int CTA_THREADS = EPI_THREADS + 64;  // + producer warp + mma warp
 constexpr int COLS_PER_WARP = 256 / (EPI_WARPS / 4);
-constexpr int STAGE_BYTES = 16384;            // ring slot: one split (hi or lo) of a 128-row x 64-k weight block
+constexpr int STAGE_BYTES = 16384;            // ring slot: one split (hi or lo) of all 256 output features x 32 contraction elements
 constexpr int NSLOT = 4;                      // 3 loads in flight while one slot is consumed
-constexpr int BIG_IMAGE_BYTES = 16 * STAGE_BYTES;
+constexpr int BIG_STAGES = 16;                // (k-block, split, k-half)
+constexpr int BIG_IMAGE_BYTES = BIG_STAGES * STAGE_BYTES;
 constexpr int TMEM_COLS = 512;
 // TMEM column regions: two 64-column first-layer chunk buffers (z1 is streamed, never resident), the 256-column
 // working accumulator (z2 / g_h1), the 16-column input gradient, and the persistent weight-gradient accumulators
@@ -49,7 +50,7 @@ struct SmemMap {
   static constexpr int MISC = PIMG + 8192;                    // fp32 scratch, see MiscF
   static constexpr int MISC_BYTES = 12288;
   static constexpr int BARS = MISC + MISC_BYTES;              // mbarriers + tmem pointer
-  static constexpr int TOTAL = BARS + 256;
+  static constexpr int TOTAL = BARS + 512;
 };
 
 struct Bars {
@@ -71,7 +72,7 @@ struct Bars {
   uint64_t gp_full;      // the input gradient g_p is complete (mma -> row warps; the epilogue warps use d_full)
   uint32_t tmem_base;
 };
-static_assert(sizeof(Bars) <= 256, "BARS region too small");
+static_assert(sizeof(Bars) <= 512, "BARS region too small");
 
 // per-role running counters (phase tracking)
 struct Sync {
@@ -99,33 +100,50 @@ __device__ __forceinline__ void produce(Bars* b, uint8_t* ring, Sync& s, const u
   }
 }
 
-// The ring is consumed in slot PAIRS (0,1) / (2,3) by the big GEMMs; single-stage GEMMs (first layer, input
-// gradient) pad their second slot with an empty stage so that every GEMM starts on an even slot and the
-// mbarrier phases of all four slots advance in lock step.
-__device__ __forceinline__ void produce_pad(Bars* b, Sync& s) {
+// The 16 KB images of the small GEMMs (first layer, input gradient) are ONE stage, followed by an empty one, so that every
+// GEMM consumes an even number of stages (the big GEMM's k-halves start on an even slot).
+__device__ __forceinline__ uint32_t wait_single(Bars* b, const Sync& s) {
+  const uint32_t slot = s.stage & (NSLOT - 1), par = (s.stage / NSLOT) & 1;
+  mbar_wait(&b->full[slot], par, 10000 + __LINE__);
+  tc_fence_after();
+  return slot;
+}
+__device__ __forceinline__ void consume_pad(Bars* b, Sync& s) {   // the empty stage behind a single-stage image
+  const uint32_t pad = s.stage & (NSLOT - 1), par = (s.stage / NSLOT) & 1;
+  mbar_wait(&b->full[pad], par, 10000 + __LINE__);
+  umma_commit(&b->empty[pad]);
+  ++s.stage;
+}
+__device__ __forceinline__ void release_single(Bars* b, Sync& s, uint32_t slot) {
+  umma_commit(&b->empty[slot]);
+  ++s.stage;
+  consume_pad(b, s);
+}
+// producer side of a 16 KB single-stage image + its empty stage
+__device__ __forceinline__ void produce_single(Bars* b, uint8_t* ring, Sync& s, const uint8_t* gsrc) {
+  produce(b, ring, s, gsrc, 1, STAGE_BYTES);
   const uint32_t slot = s.stage & (NSLOT - 1), par = (s.stage / NSLOT) & 1;
   mbar_wait(&b->empty[slot], par ^ 1, 10000 + __LINE__);
   mbar_arrive(&b->full[slot]);
   ++s.stage;
 }
-__device__ __forceinline__ void consume_pad(Bars* b, Sync& s) {
-  const uint32_t slot = s.stage & (NSLOT - 1), par = (s.stage / NSLOT) & 1;
-  mbar_wait(&b->full[slot], par, 10000 + __LINE__);
-  umma_commit(&b->empty[slot]);
-  ++s.stage;
-}
 
 // ---- mma role ----------------------------------------------------------------------------------------
 // big GEMM: D[128 x 256] = ACT[128 x 256] . Wt^T.  The Wt image is streamed as 16 stages of 16 KB ordered
-// (k-block kb, split, n-half h); the two n-halves of a split land in ADJACENT ring slots (0,1 or 2,3), so one
-// N = 256 UMMA reads both (half the instruction count and 25 % less shared-memory operand traffic than two
-// N = 128 UMMAs).  K-block kb is issued as soon as the epilogue has published that 64-feature block of the
-// activation image, so the UMMAs overlap the epilogue that produces A.
-struct NoHook { __device__ __forceinline__ void operator()() const {} };
+// (k-block kb, split, k-half kh); a stage holds ALL 256 output features of 32 contraction elements (64-byte rows,
+// SW64 K-major), so every ring slot is an independent B operand: it feeds two K = 16 steps of N = 256 UMMAs and goes
+// back to the producer as soon as those have completed -- three 16 KB loads stay in flight.
+//   Measured (tools/gemm_probe.py, one CTA per SM): 6.7 K cycles per GEMM = the rate with resident operands (6.6 K);
+//   832 KB of shared-memory traffic per GEMM (576 KB operand reads + 256 KB ring writes) = 125 of the 128 B/clk.
+//   (kb, split, n-half) stages of 128 features x 64 elements consumed and released in PAIRS (round 2's first layout):
+//   8.8 K -- only two 32 KB granules in flight, every refill exposed the L2 latency.  32 stages of 8 KB (one K = 16 step
+//   each, 8 slots; SW32 or no-swizzle): 9.8 K -- ~190 cycles of fixed cost per stage (wait + commit + bulk copy) x 32.
+// K-block kb is issued as soon as the epilogue has published that 64-feature block of the activation image, so the
+// UMMAs overlap the epilogue that produces A.
 // FMT: element format of BOTH operands (forward GEMMs: fp16 pairs, dX GEMMs: bf16 pairs)
-template <int FMT = FMT_BF16, typename Hook = NoHook>
+template <int FMT = FMT_BF16>
 __device__ __forceinline__ void mma_big(Bars* b, uint32_t act_addr, uint32_t ring_addr, Sync& s, uint32_t d_tmem,
-                                        Hook hook = Hook(), bool wait_a = true) {
+                                        bool wait_a = true) {
   constexpr uint32_t idesc = make_idesc(128, 256, 0, 0, FMT, FMT);
   for (int kb = 0; kb < 4; ++kb) {
     if (wait_a) mbar_wait(&b->a_blk[kb], s.g_cnt & 1, 10000 + __LINE__);
@@ -134,25 +152,26 @@ __device__ __forceinline__ void mma_big(Bars* b, uint32_t act_addr, uint32_t rin
     const uint64_t dal = make_desc(act_addr + ACT_SPLIT + kb * ACT_BLOCK, 16, 1024, LAYOUT_SW128);
 #pragma unroll
     for (int sp = 0; sp < 2; ++sp) {
-      const uint32_t slot = s.stage & (NSLOT - 1), par = (s.stage / NSLOT) & 1;   // slot is 0 or 2
-      mbar_wait(&b->full[slot], par, 10000 + __LINE__);
-      mbar_wait(&b->full[slot + 1], par, 10000 + __LINE__);
-      tc_fence_after();
-      const uint64_t db = make_desc(ring_addr + slot * STAGE_BYTES, 16, 1024, LAYOUT_SW128);
 #pragma unroll
-      for (int ks = 0; ks < 4; ++ks) {
-        const uint64_t ko = (uint64_t)(ks * 2);          // +32 bytes along K inside the 128-byte swizzle atom
-        if (sp == 0) {
-          umma_bf16(d_tmem, dah + ko, db + ko, idesc, (kb | ks) ? 1u : 0u);   // a_hi . b_hi
-          umma_bf16(d_tmem, dal + ko, db + ko, idesc, 1u);                    // a_lo . b_hi
-        } else {
-          umma_bf16(d_tmem, dah + ko, db + ko, idesc, 1u);                    // a_hi . b_lo
+      for (int kh = 0; kh < 2; ++kh) {
+        const uint32_t slot = s.stage & (NSLOT - 1), par = (s.stage / NSLOT) & 1;
+        mbar_wait(&b->full[slot], par, 10000 + __LINE__);
+        tc_fence_after();
+        const uint64_t db = make_desc(ring_addr + slot * STAGE_BYTES, 16, 512, LAYOUT_SW64);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const uint64_t ka = (uint64_t)((kh * 2 + j) * 2);   // +32 bytes along K inside the 128-byte swizzle atom of A
+          const uint64_t kw = (uint64_t)(j * 2);              // +32 bytes inside the 64-byte swizzle atom of the weights
+          if (sp == 0) {
+            umma_bf16(d_tmem, dah + ka, db + kw, idesc, (kb | kh | j) ? 1u : 0u);   // a_hi . b_hi
+            umma_bf16(d_tmem, dal + ka, db + kw, idesc, 1u);                        // a_lo . b_hi
+          } else {
+            umma_bf16(d_tmem, dah + ka, db + kw, idesc, 1u);                        // a_hi . b_lo
+          }
         }
+        umma_commit(&b->empty[slot]);
+        ++s.stage;
       }
-      umma_commit(&b->empty[slot]);
-      umma_commit(&b->empty[slot + 1]);
-      s.stage += 2;
-      if (kb == 0 && sp == 0) hook();
     }
     umma_commit(&b->kb_done[kb]);
   }
@@ -210,18 +229,14 @@ __device__ __forceinline__ void mma_l1(Bars* b, uint32_t p_addr, uint32_t ring_a
   constexpr uint32_t idesc = make_idesc(128, 256, 0, 0, FMT_F16, FMT_F16);
   mbar_wait(&b->a_full, s.a_cnt & 1, 10000 + __LINE__);
   ++s.a_cnt;
-  const uint32_t slot = s.stage & (NSLOT - 1), par = (s.stage / NSLOT) & 1;
-  mbar_wait(&b->full[slot], par, 10000 + __LINE__);
-  tc_fence_after();
+  const uint32_t slot = wait_single(b, s);
   const uint32_t bbase = ring_addr + slot * STAGE_BYTES;
   const uint64_t dah = make_desc(p_addr, 128, P_GROUP, LAYOUT_NONE), dal = make_desc(p_addr + P_LO, 128, P_GROUP, LAYOUT_NONE);
   const uint64_t dbh = make_desc(bbase, 128, 256, LAYOUT_NONE), dbl = make_desc(bbase + 8192, 128, 256, LAYOUT_NONE);
   umma_bf16(d_tmem, dah, dbh, idesc, 0u);
   umma_bf16(d_tmem, dal, dbh, idesc, 1u);
   umma_bf16(d_tmem, dah, dbl, idesc, 1u);
-  umma_commit(&b->empty[slot]);
-  ++s.stage;
-  consume_pad(b, s);
+  release_single(b, s, slot);
 }
 // input-gradient GEMM: D[128 x 32] = ACT[128 x 256] . [W1nat_hi ; W1nat_lo]^T (W1nat: 16 rows x 256); the image is
 // streamed as ONE stage = 4 k-blocks x (32 rows x 128 B) = 16 KB; g = D[:, 0:16] + D[:, 16:32]
@@ -237,17 +252,14 @@ __device__ __forceinline__ void mma_in_block(uint32_t act_addr, uint32_t ibase, 
   }
 }
 __device__ __forceinline__ void mma_in(Bars* b, uint32_t act_addr, uint32_t ring_addr, Sync& s, uint32_t d_tmem) {
-  const uint32_t slot = s.stage & (NSLOT - 1), par = (s.stage / NSLOT) & 1;
-  const uint32_t bbase = ring_addr + slot * STAGE_BYTES;
+  uint32_t slot = 0;
   for (int kb = 0; kb < 4; ++kb) {
     mbar_wait(&b->a_blk[kb], s.g_cnt & 1, 10000 + __LINE__);
-    if (kb == 0) mbar_wait(&b->full[slot], par, 10000 + __LINE__);
+    if (kb == 0) slot = wait_single(b, s);
     tc_fence_after();
-    mma_in_block(act_addr, bbase, kb, d_tmem);
+    mma_in_block(act_addr, ring_addr + slot * STAGE_BYTES, kb, d_tmem);
   }
-  umma_commit(&b->empty[slot]);
-  ++s.stage;
-  consume_pad(b, s);
+  release_single(b, s, slot);
   ++s.g_cnt;
 }
 
@@ -283,8 +295,8 @@ __device__ __forceinline__ void epi_wait_d(Bars* b, Sync& s) {
 template <int ROLE>
 __device__ __forceinline__ void gemm_issue(int kind, Bars* b, uint8_t* smem, Sync& s, const uint8_t* gimg, uint32_t d_tmem) {
   if (ROLE == ROLE_PRODUCER) {
-    if (kind == 0) produce(b, smem + SmemMap::RING, s, gimg, 16, STAGE_BYTES);
-    else { produce(b, smem + SmemMap::RING, s, gimg, 1, 16384); produce_pad(b, s); }
+    if (kind == 0) produce(b, smem + SmemMap::RING, s, gimg, BIG_STAGES, STAGE_BYTES);
+    else produce_single(b, smem + SmemMap::RING, s, gimg);
   } else if (ROLE == ROLE_MMA) {
     const uint32_t base = smem_u32(smem);
     if (kind == 0) mma_big(b, base + SmemMap::ACT, base + SmemMap::RING, s, d_tmem);
@@ -303,22 +315,19 @@ template <int ROLE>
 __device__ __forceinline__ void fwd_pair_issue(Bars* b, uint8_t* smem, Sync& s, const uint8_t* l1_img, const uint8_t* big_img,
                                                uint32_t tm_z1c, uint32_t tm_work) {
   if (ROLE == ROLE_PRODUCER) {
-    produce(b, smem + SmemMap::RING, s, l1_img, 1, 16384);
-    produce_pad(b, s);
-    produce(b, smem + SmemMap::RING, s, big_img, 16, STAGE_BYTES);
+    produce_single(b, smem + SmemMap::RING, s, l1_img);
+    produce(b, smem + SmemMap::RING, s, big_img, BIG_STAGES, STAGE_BYTES);
   } else if (ROLE == ROLE_MMA) {
     const uint32_t base = smem_u32(smem), p_addr = base + SmemMap::PIMG, ring = base + SmemMap::RING;
     mbar_wait(&b->a_full, s.a_cnt & 1, 10000 + __LINE__);
     ++s.a_cnt;
-    const uint32_t slot = s.stage & (NSLOT - 1), par = (s.stage / NSLOT) & 1;
-    mbar_wait(&b->full[slot], par, 10000 + __LINE__);
-    tc_fence_after();
+    const uint32_t slot = wait_single(b, s);
     const uint32_t bbase = ring + slot * STAGE_BYTES;
     mma_l1_chunk<FMT_F16>(b, p_addr, bbase, 0, tm_z1c);
     mma_l1_chunk<FMT_F16>(b, p_addr, bbase, 1, tm_z1c);
     mma_l1_chunk<FMT_F16>(b, p_addr, bbase, 2, tm_z1c);
     ++s.stage;
-    consume_pad(b, s);
+    consume_pad(b, s);                        // hands the empty slot to the big GEMM's first stages right away
     // the last chunk waits for the epilogue to have read chunk 1, which happens about when h1 block 0 is published:
     // issuing it BEFORE the first big UMMAs keeps it from queueing behind them in the tensor pipe
     mma_l1_chunk<FMT_F16>(b, p_addr, bbase, 3, tm_z1c);
@@ -338,23 +347,18 @@ __device__ __forceinline__ void bwd_tail_issue(Bars* b, uint8_t* smem, Sync& s, 
                                                bool do_gp, bool do_d1, bool& d1_started, uint32_t tm_z1c, uint32_t tm_gp,
                                                uint32_t tm_d1, bool wait_p = false, bool release_img = false) {
   if (ROLE == ROLE_PRODUCER) {
-    produce(b, smem + SmemMap::RING, s, l1_img, 1, 16384);
-    produce_pad(b, s);
-    if (do_gp) { produce(b, smem + SmemMap::RING, s, in_img, 1, 16384); produce_pad(b, s); }
+    produce_single(b, smem + SmemMap::RING, s, l1_img);
+    if (do_gp) produce_single(b, smem + SmemMap::RING, s, in_img);
   } else if (ROLE == ROLE_MMA) {
     const uint32_t base = smem_u32(smem), p_addr = base + SmemMap::PIMG, ring = base + SmemMap::RING;
     if (wait_p) {                                 // the [p|1] image of this step was written at the start of the step
       mbar_wait(&b->p_full, s.p_cnt & 1, 10000 + __LINE__);
       ++s.p_cnt;
     }
-    const uint32_t slot = s.stage & (NSLOT - 1), par = (s.stage / NSLOT) & 1;
-    mbar_wait(&b->full[slot], par, 10000 + __LINE__);
-    tc_fence_after();
+    const uint32_t slot = wait_single(b, s);
     const uint32_t bbase = ring + slot * STAGE_BYTES;
     for (int c = 0; c < 4; ++c) mma_l1_chunk<FMT_BF16>(b, p_addr, bbase, c, tm_z1c);   // backward side: bf16 [p|1] image + bf16 W1aug
-    umma_commit(&b->empty[slot]);
-    ++s.stage;
-    consume_pad(b, s);
+    release_single(b, s, slot);
     // g_p K-block kb follows delta1 block kb.  D1 += delta1^T [p|1] is issued per 128-feature half: half 0 as soon as
     // delta1 blocks 0, 1 exist (it runs under the second half of the delta1 epilogue, when the tensor pipe has nothing
     // else to do), half 1 after g_p has been committed, so that it runs under the epilogue's lambda update and the start
@@ -378,9 +382,7 @@ __device__ __forceinline__ void bwd_tail_issue(Bars* b, uint8_t* smem, Sync& s, 
     }
     ++s.g_cnt;
     if (do_gp) {
-      umma_commit(&b->empty[islot]);
-      ++s.stage;
-      consume_pad(b, s);
+      release_single(b, s, islot);
       mma_publish_d(b);
       umma_commit(&b->gp_full);
     }
@@ -455,7 +457,8 @@ __device__ __forceinline__ void cta_teardown(Bars* b, int mma_warp = EPI_WARPS +
 }
 
 // ---- global weight-image packing (run once per set_weights) ------------------------------------------------
-// big image: value(row, k) = src[row * rs + k * cs], 256 rows x 256 k -> 8 stages (kb, h) of [hi 16 KB | lo 16 KB]
+// big image: value(row, k) = src[row * rs + k * cs], 256 rows x 256 k -> 16 stages (kb, split, kh) of 256 rows x 64 B,
+// SW64 K-major (8-row groups of 512 B, 16-byte chunk index ^ ((row >> 1) & 3))
 template <bool F16>
 __global__ void pack_big_image(const float* __restrict__ src, int rs, int cs, uint8_t* __restrict__ img) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;   // one thread per (row, 8-element chunk): 256 x 32
@@ -466,9 +469,9 @@ __global__ void pack_big_image(const float* __restrict__ src, int rs, int cs, ui
   for (int e = 0; e < 8; ++e) x[e] = src[(size_t)row * rs + (size_t)(cc * 8 + e) * cs];
   uint4 h, l;
   split2x<F16>(x[0], x[1], h.x, l.x); split2x<F16>(x[2], x[3], h.y, l.y); split2x<F16>(x[4], x[5], h.z, l.z); split2x<F16>(x[6], x[7], h.w, l.w);
-  const int hh = row >> 7, rr = row & 127, kb = cc >> 3, c = cc & 7;
-  const size_t stage = (size_t)(kb * 4 + hh) * STAGE_BYTES;   // streamed in (k-block, split, n-half) order
-  const uint32_t off = (rr >> 3) * 1024 + (rr & 7) * 128 + ((c ^ (rr & 7)) << 4);
+  const int kb = cc >> 3, kh = (cc >> 2) & 1, c = cc & 3;
+  const size_t stage = (size_t)(kb * 4 + kh) * STAGE_BYTES;   // streamed in (k-block, split, k-half) order
+  const uint32_t off = (row >> 3) * 512 + (row & 7) * 64 + ((c ^ ((row >> 1) & 3)) << 4);
   *reinterpret_cast<uint4*>(img + stage + off) = h;
   *reinterpret_cast<uint4*>(img + stage + 2 * STAGE_BYTES + off) = l;
 }
@@ -575,7 +578,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) selftest_kernel(int kind, cons
     if (lane == 0)
       for (int rep = 0; rep < repeats; ++rep) {
         if (kind == 3) {          // weights streamed through the ring, no epilogue in the loop
-          mma_big<FMT_BF16>(b, smem_u32(smem) + SmemMap::ACT, smem_u32(smem) + SmemMap::RING, s, tmem + TM_WORK, NoHook(), false);
+          mma_big<FMT_BF16>(b, smem_u32(smem) + SmemMap::ACT, smem_u32(smem) + SmemMap::RING, s, tmem + TM_WORK, false);
           if (rep == repeats - 1) mma_publish_d(b);
         } else if (kind == 4) {   // operands resident, no streaming: the tensor pipe's own rate for this shape
           constexpr uint32_t idesc = make_idesc(128, 256, 0, 0);
@@ -585,7 +588,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) selftest_kernel(int kind, cons
             const uint64_t dah = make_desc(act + (k >> 2) * ACT_BLOCK, 16, 1024, LAYOUT_SW128) + ko;
             const uint64_t dal = make_desc(act + ACT_SPLIT + (k >> 2) * ACT_BLOCK, 16, 1024, LAYOUT_SW128) + ko;
             const uint64_t dbh = make_desc(ring, 16, 1024, LAYOUT_SW128) + ko;
-            const uint64_t dbl = make_desc(ring + 2 * STAGE_BYTES, 16, 1024, LAYOUT_SW128) + ko;
+            const uint64_t dbl = make_desc(ring + 32768, 16, 1024, LAYOUT_SW128) + ko;
             umma_bf16(tmem + TM_WORK, dah, dbh, idesc, 1u);
             umma_bf16(tmem + TM_WORK, dal, dbh, idesc, 1u);
             umma_bf16(tmem + TM_WORK, dah, dbl, idesc, 1u);

@@ -59,6 +59,7 @@ __device__ __forceinline__ void umma2_commit_both(uint64_t* bar) {
 #ifndef MPG_PAIR_NSLOT
 #define MPG_PAIR_NSLOT 6
 #endif
+constexpr int PSTAGE_BYTES = 16384;      // the probe's own stage: one split of a 128-feature x 64-element weight block
 constexpr int PNSLOT = MPG_PAIR_NSLOT;   // ring depth of the probe (the pair kernel has no MISC / p-image regions to fit)
 struct PairBars {
   uint64_t full[PNSLOT], empty[PNSLOT];
@@ -67,10 +68,27 @@ struct PairBars {
   uint64_t d_full;
   uint32_t tmem_base;
 };
-constexpr int PAIR_SMEM = 2 * ACT_SPLIT + PNSLOT * STAGE_BYTES + 256 + 1024;
+// weight image of the probe: 16 stages (k-block, split, n-half) of 128 features x 64 elements, SW128 K-major -- each CTA of
+// the pair streams ONE n-half of every (k-block, split)
+__global__ void pack_pair_image(const float* __restrict__ src, int rs, int cs, uint8_t* __restrict__ img) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;   // one thread per (row, 8-element chunk): 256 x 32
+  if (idx >= 256 * 32) return;
+  const int row = idx >> 5, cc = idx & 31;
+  float x[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) x[e] = src[(size_t)row * rs + (size_t)(cc * 8 + e) * cs];
+  uint4 h, l;
+  split2x<false>(x[0], x[1], h.x, l.x); split2x<false>(x[2], x[3], h.y, l.y); split2x<false>(x[4], x[5], h.z, l.z); split2x<false>(x[6], x[7], h.w, l.w);
+  const int hh = row >> 7, rr = row & 127, kb = cc >> 3, c = cc & 7;
+  const size_t stage = (size_t)(kb * 4 + hh) * PSTAGE_BYTES;
+  const uint32_t off = (rr >> 3) * 1024 + (rr & 7) * 128 + ((c ^ (rr & 7)) << 4);
+  *reinterpret_cast<uint4*>(img + stage + off) = h;
+  *reinterpret_cast<uint4*>(img + stage + 2 * PSTAGE_BYTES + off) = l;
+}
+constexpr int PAIR_SMEM = 2 * ACT_SPLIT + PNSLOT * PSTAGE_BYTES + 256 + 1024;
 static_assert(PAIR_SMEM <= 232448, "pair probe shared memory");
 
-// X: fp32 [256 x 256] (rows 0..127 -> CTA 0, 128..255 -> CTA 1), img: packed big image (pack_big_image),
+// X: fp32 [256 x 256] (rows 0..127 -> CTA 0, 128..255 -> CTA 1), img: packed weight image (pack_pair_image),
 // Z: fp32 [256 x 256] = X . Wt^T accumulated `repeats` times when write_z (rep > 1 re-accumulates: timing only)
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
 pair_probe_kernel(const float* __restrict__ X, const uint8_t* __restrict__ img, float* __restrict__ Z, int repeats) {
@@ -78,7 +96,7 @@ pair_probe_kernel(const float* __restrict__ X, const uint8_t* __restrict__ img, 
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* act = smem;
   uint8_t* ring = smem + 2 * ACT_SPLIT;
-  PairBars* b = reinterpret_cast<PairBars*>(ring + PNSLOT * STAGE_BYTES);
+  PairBars* b = reinterpret_cast<PairBars*>(ring + PNSLOT * PSTAGE_BYTES);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
@@ -132,8 +150,8 @@ pair_probe_kernel(const float* __restrict__ X, const uint8_t* __restrict__ img, 
         for (int i = 0; i < 8; ++i, ++st) {              // i = kb * 2 + sp
           const uint32_t slot = st % PNSLOT, par = (st / PNSLOT) & 1;
           mbar_wait_cluster(&b->empty[slot], par ^ 1);
-          mbar_expect_tx(&b->full[slot], STAGE_BYTES);
-          bulk_g2s(ring + slot * STAGE_BYTES, img + (size_t)((i >> 1) * 4 + (i & 1) * 2 + rank) * STAGE_BYTES, STAGE_BYTES,
+          mbar_expect_tx(&b->full[slot], PSTAGE_BYTES);
+          bulk_g2s(ring + slot * PSTAGE_BYTES, img + (size_t)((i >> 1) * 4 + (i & 1) * 2 + rank) * PSTAGE_BYTES, PSTAGE_BYTES,
                    &b->full[slot]);
         }
     } else if (lane == 1 && !leader) {
@@ -163,7 +181,7 @@ pair_probe_kernel(const float* __restrict__ X, const uint8_t* __restrict__ img, 
             mbar_wait(&b->full[slot], par);
             mbar_wait_cluster(&b->peer_full[slot], par);
             tc_fence_after();
-            const uint64_t db = make_desc(ring_addr + slot * STAGE_BYTES, 16, 1024, LAYOUT_SW128);
+            const uint64_t db = make_desc(ring_addr + slot * PSTAGE_BYTES, 16, 1024, LAYOUT_SW128);
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) {
               const uint64_t ko = (uint64_t)(ks * 2);

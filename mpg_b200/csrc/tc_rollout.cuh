@@ -129,7 +129,7 @@ inline cudaError_t tc_selftest(TcState& t, int kind, const float* X, const float
     const char* g = getenv("MPG_SELFTEST_GRID");
     int grid = g ? atoi(g) & ~1 : 2;
     if (grid < 2) grid = 2;
-    tc::pack_big_image<false><<<32, 256, 0, st>>>(W, H, 1, t.scratch_img);
+    tc::pack_pair_image<<<32, 256, 0, st>>>(W, H, 1, t.scratch_img);
     tc::pair_probe_kernel<<<grid, 192, tc::PAIR_SMEM, st>>>(X, t.scratch_img, Z, repeats);
     return cudaGetLastError();
   }
