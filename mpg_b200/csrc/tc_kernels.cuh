@@ -370,6 +370,24 @@ __device__ __forceinline__ void run_rollout(const TcArgs& A, uint8_t* smem, Bars
 #endif
   };
 
+  // which steps are in the rollout list (bit t), and which of those carry a non-zero weight: looked up once per kernel
+  // instead of scanning the list several times in every step of every tile (steps >= 64 scan)
+  unsigned long long list_bits = 0ull, q_bits = 0ull;
+#pragma unroll
+  for (int k = 0; k < MPG_MAX_LIST; ++k)
+    if (k < a.n_list && a.list[k] < 64) {
+      list_bits |= 1ull << a.list[k];
+      if (a.list_w[k] != 0.f) q_bits |= 1ull << a.list[k];
+    }
+  auto list_index = [&](int tt) {       // position of step tt in the list, or -1
+    int kidx = -1;
+    if (tt >= 64 || ((list_bits >> tt) & 1ull)) {
+#pragma unroll
+      for (int k = 0; k < MPG_MAX_LIST; ++k) if (k < a.n_list && a.list[k] == tt) kidx = k;
+    }
+    return kidx;
+  };
+
   const int tile_end = A.tile1 > 0 && A.tile1 < ntiles ? A.tile1 : ntiles;
   for (int tile = A.tile0 + blockIdx.x; tile < tile_end; tile += gridDim.x) {
     const int grow = tile * ACT_ROWS + row;
@@ -432,7 +450,9 @@ __device__ __forceinline__ void run_rollout(const TcArgs& A, uint8_t* smem, Bars
     // kernel h2 goes to the h2 store of this (tile, step) and, for the steps whose weight gradient is wanted (slot),
     // the h1 image leaves for the dW operand store behind the K-blocks of the GEMM.
     auto policy_forward = [&](float* zpre, uint8_t* h2slot, uint8_t* slot) {
+      if (ROLE == ROLE_MMA) stamp(16);
       fwd_pair_issue<ROLE>(b, smem, sy, A.pol.l1, A.pol.big_fwd, tm_z1c, tm_work);
+      if (ROLE == ROLE_MMA) stamp(17);
       if (ROLE == ROLE_EPI) {
         stamp(17);
         if (store_pending) { store_wait(elected); store_pending = false; }   // the previous step's h1 record has left long ago
@@ -494,9 +514,12 @@ __device__ __forceinline__ void run_rollout(const TcArgs& A, uint8_t* smem, Bars
       // steps whose weight gradient is wanted leave their dW2 operands (h1 now, delta2 during BPTT) in the operand store
       const bool rec_f = store_dw && !A.q_regress && (a.full_bptt || t == 0);
       uint8_t* slot = rec_f ? A.store + ((size_t)tile * A.store_steps + (a.full_bptt ? t : 0)) * SLOT_BYTES : nullptr;
-      if (ROLE == ROLE_EPI || ROLE == ROLE_ROW) {
-        if (tile == A.tile0 + (int)blockIdx.x && t == 2) { prof_t = t; stamp(16); }
-        else if (prof_t >= 0) { stamp(22); prof_t = -1; }
+      if (tile == A.tile0 + (int)blockIdx.x && t == 2) {
+        prof_t = t;
+        if (ROLE != ROLE_MMA) stamp(16);
+      } else if (prof_t >= 0) {
+        if (ROLE != ROLE_MMA) stamp(22);
+        prof_t = -1;
       }
       if (rowthread) {
         if (BWD && valid) {
@@ -528,9 +551,7 @@ __device__ __forceinline__ void run_rollout(const TcArgs& A, uint8_t* smem, Bars
       if (valid && a.traj_act)
 #pragma unroll
         for (int j = 0; j < NA; ++j) a.traj_act[((size_t)t * MB + grow) * NA + j] = act[j];
-      int kidx = -1;   // fixed trip count: the list is read with immediate constant-bank offsets (an indexed LDC is slow)
-#pragma unroll
-      for (int k = 0; k < MPG_MAX_LIST; ++k) if (k < a.n_list && a.list[k] == t) kidx = k;
+      const int kidx = list_index(t);   // fixed trip count inside: immediate constant-bank offsets (an indexed LDC is slow)
       if (kidx >= 0) {
         float qv = 0.f;
         if (BWD && valid)
@@ -570,12 +591,17 @@ __device__ __forceinline__ void run_rollout(const TcArgs& A, uint8_t* smem, Bars
 #pragma unroll
       for (int j = 0; j < 2 * NA; ++j)
         zpre_n[j] = (valid && !A.q_regress) ? A.z_ckpt[((size_t)a.horizon * MB + grow) * (2 * NA) + j] : 0.f;
+      float w_later = 0.f;     // sum of the list weights of the steps behind t (the reward of step t counts for those returns)
       for (int t = a.horizon; t >= 0; --t) {
+        if (t < a.horizon && list_index(t + 1) >= 0) {
+#pragma unroll
+          for (int k = 0; k < MPG_MAX_LIST; ++k) if (k < a.n_list && a.list[k] == t + 1) w_later += a.list_w[k];
+        }
         float gp = 1.f;
         for (int i = 0; i < t; ++i) gp *= a.gamma;
         const bool want_dw = a.full_bptt || t == 0;
         const bool rec = store_dw && want_dw;
-        prof_t = (tile == A.tile0 + (int)blockIdx.x && t == a.horizon - 1) ? t : -1;
+        prof_t = (tile == A.tile0 + (int)blockIdx.x && t == a.horizon - 2) ? t : -1;
         stamp(0);
         uint8_t* slot = rec ? A.store + ((size_t)tile * A.store_steps + (a.full_bptt ? t : 0)) * SLOT_BYTES : nullptr;
         float g_a[NA], g_s[S], act[NA], hgrad[NA];
@@ -597,19 +623,24 @@ __device__ __forceinline__ void run_rollout(const TcArgs& A, uint8_t* smem, Bars
               for (int j = 0; j < 2 * NA; ++j) zpre_n[j] = A.z_ckpt[((size_t)(t - 1) * MB + grow) * (2 * NA) + j];
           }
         }
-        int kidx = -1;
-#pragma unroll
-        for (int k = 0; k < MPG_MAX_LIST; ++k) if (k < a.n_list && a.list[k] == t) kidx = k;
+        if (ROLE == ROLE_ROW) stamp(4);
+        const int kidx = list_index(t);
         if (want_dw) any_dw = true;
         // ---- Q input gradient at the list steps: upstream c w_k gamma^t on Q1(p_t, a_t) ----
         float w_k = 0.f;
+        if (kidx >= 0) {
 #pragma unroll
-        for (int k = 0; k < MPG_MAX_LIST; ++k) if (k == kidx) w_k = a.list_w[k];
+          for (int k = 0; k < MPG_MAX_LIST; ++k) if (k == kidx) w_k = a.list_w[k];
+        }
         // does step tt start with a Q part (which uses the activation image before the policy part does)?
         auto q_part_at = [&](int tt) {
           bool q = false;
+          if (tt < 64) {
+            q = (q_bits >> tt) & 1ull;
+          } else {
 #pragma unroll
-          for (int k = 0; k < MPG_MAX_LIST; ++k) if (k < a.n_list && a.list[k] == tt && a.list_w[k] != 0.f) q = true;
+            for (int k = 0; k < MPG_MAX_LIST; ++k) if (k < a.n_list && a.list[k] == tt && a.list_w[k] != 0.f) q = true;
+          }
           return q && a.has_q;
         };
         // early: the h2 image of this step was requested during the previous one; early_next: request the next one
@@ -703,11 +734,9 @@ __device__ __forceinline__ void run_rollout(const TcArgs& A, uint8_t* smem, Bars
         // run them first; the dX chain of the epilogue warps hangs on delta3 ----
         if (rowthread) {
           tc_fence_before();         // the g_p read of the previous step precedes the next g_p UMMAs (ordered through p_full)
+          stamp(5);
           if (t < a.horizon && valid) {
-            float Wt = 0.f;
-#pragma unroll
-            for (int k = 0; k < MPG_MAX_LIST; ++k) if (k < a.n_list && a.list[k] > t) Wt += a.list_w[k];
-            env_step_bwd<ENV, true>(s, act, lam, cscale * Wt * gp * a.rew_scale, g_s, g_a, snext);
+            env_step_bwd<ENV, true>(s, act, lam, cscale * w_later * gp * a.rew_scale, g_s, g_a, snext);
           }
           stamp(14);
           float d3[2] = {0.f, 0.f};
@@ -744,7 +773,9 @@ __device__ __forceinline__ void run_rollout(const TcArgs& A, uint8_t* smem, Bars
           stamp(3);
         }
         ++sy.i_cnt;
+        if (ROLE == ROLE_MMA) stamp(5);
         if (want_dw) d3_issue<ROLE>(b, smem, sy, SM_D3IMG, d3_started, tm_d3, true);   // dW3 += h2^T delta3
+        if (ROLE == ROLE_MMA) stamp(6);
         // ---- [p|1] image of step t (first-layer recompute for elu'(z1), D1 operand, db2 record); the D1 UMMAs of the
         // previous step still read the old one ----
         if (rowthread) {

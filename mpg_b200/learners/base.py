@@ -147,5 +147,17 @@ class LearnerBase(object):
     def _allreduce(self, flat):
         return parallel.allreduce_flat(flat, self.world_size)
 
+    def _to_host(self, dev):
+        """The update's single device -> host copy: into a pinned staging buffer (a pageable destination makes the
+        driver bounce the copy through its own staging area), then one stream synchronise.  Returns a fresh numpy
+        array -- the caller hands views of it out as the gradient list."""
+        n = dev.numel()
+        pin = self._pinned.get('_d2h')
+        if pin is None or pin.numel() < n:
+            pin = self._pinned['_d2h'] = torch.empty(n, dtype=torch.float32, pin_memory=True)
+        pin[:n].copy_(dev, non_blocking=True)
+        torch.cuda.current_stream(self.engine.device).synchronize()
+        return pin[:n].numpy().copy()
+
     def _split_to_numpy(self, flat_host, nets):
         return parallel.split_flat(flat_host, self.args.obs_dim, self.args.act_dim, nets)

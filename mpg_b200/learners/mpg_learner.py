@@ -103,7 +103,7 @@ class MPGLearner(LearnerBase):
             pos += n
         ng = pos
         self._finish_upload()
-        host = torch.cat([flat] + norms).cpu().numpy()
+        host = self._to_host(torch.cat([flat] + norms))
         B = float(self.global_rows)
         nql = len(q_res)
         n_list = len(klist)

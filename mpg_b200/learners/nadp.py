@@ -77,7 +77,7 @@ class NADPLearner(LearnerBase):
         q_norm = e.clip_global_norm(flat[:nq], clip)
         p_norm = e.clip_global_norm(flat[nq:nq + p_grad.numel()], clip)
         self._finish_upload()                                     # deferred H2D (rewards / obs_tp1) has overlapped the kernels
-        host = torch.cat([flat, q_norm, p_norm]).cpu().numpy()   # the only device->host copy of the update
+        host = self._to_host(torch.cat([flat, q_norm, p_norm]))   # the only device->host copy of the update
         ng = nq + p_grad.numel()
         B = float(self.global_rows)
         n_list = (host.size - ng - 3) // 2

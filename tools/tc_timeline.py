@@ -22,9 +22,10 @@ for full in (1, 0):
     for i, n in {0: 'start', 12: 'acc_wait done', 1: 'load issued', 2: 'waiting for h2', 3: 'h2 image landed', 6: 'Ed2 start (D3 half, d3s)',
                  7: 'Ed2 done', 8: 'g_h1 ready', 9: 'Ed1 done', 10: 'g_p ready', 11: 'step end'}.items():
         print(f'  epi {n:26s} {ep[i]:8d}')
-    for i, n in {0: 'start', 12: 'acc_wait done', 13: 'p image written', 14: 'env adjoint done', 2: 'd3 published', 10: 'g_p ready', 11: 'lambda done'}.items():
+    for i, n in {0: 'start', 4: 'checkpoint loads issued', 5: 'env adjoint start', 12: 'acc_wait done', 13: 'p image written', 14: 'env adjoint done', 2: 'd3 published', 10: 'g_p ready', 11: 'lambda done'}.items():
         print(f'  row {n:26s} {rw[i]:8d}')
-    print('  mma: dx-start', mm[3], 'dx-issued', mm[4])
+    print('  mma: d3-start', mm[5], 'd3-issued', mm[6], 'dx-start', mm[3], 'dx-issued', mm[4])
     fw = t[16:23] - t[16]; fr = t[80:87] - t[16]
     print('  forward step t=2 (epi): start 0, E1 start', fw[1], 'E1 done', fw[2], 'z2 ready', fw[3], 'E2 done', fw[4], 'next step', fw[6])
+    print('  forward step t=2 (mma): enter', t[32 + 16] - t[16], 'all UMMAs issued', t[32 + 17] - t[16])
     print('  forward step t=2 (row): start', fr[0], 'zpre', fr[5], 'next step', fr[6])
