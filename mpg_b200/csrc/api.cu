@@ -272,11 +272,14 @@ int fill_rollout_args(mpg_ctx* ctx, const mpg_rollout_params* p, RolloutArgs& a)
 }
 
 // dW2 = sum over (row, step) of h1^T delta2 is the only contraction of the path whose K is the batch.  With K in the
-// millions the rounding of the operands averages out, so the records of LARGE contractions keep only the hi plane of h1
-// (11 bits) and delta2 (8 bits) and the dW kernel issues one product instead of three: half the record traffic, and the
-// side-stream GEMMs fit under the tail wave.  Emulated on the CPU oracle and measured: the added gradient error
-// is ~3e-5 x sqrt(53,248 / K) (K = rows x recorded steps); below K = 262,144 the full hi + lo records are kept (at
-// K = 16..256 x 26 hi-only records miss the 1e-4 bar).  MPG_REC_HI_ONLY=0/1 forces the mode.
+// millions the rounding of the operands averages out, so the records of LARGE policy-gradient contractions keep only the hi
+// plane of h1 (11 bits) and delta2 (8 bits) and the dW kernel issues one product instead of three: half the record
+// traffic, and the side-stream GEMMs fit under the tail wave (+14 % state-steps/s at 65,536 rows).  Emulated on the CPU
+// oracle and measured: the added gradient error is ~1e-5 at K = 262,144 (rows x recorded steps) and falls
+// with 1/sqrt(K); below that the full hi + lo records are kept (at K = 16..256 x 26 hi-only records miss the 1e-4 bar).
+// The rounding error is ~1.1e-3 of the root-sum-square of the terms, so relative to the gradient it grows with the
+// cancellation in the sum (worst case, a gradient that is pure sampling noise: 1.1e-3 of that noise): the Q regression
+// never uses it, and MPG_REC_HI_ONLY=0 keeps full records everywhere (=1 forces hi-only, for tests).
 int rec_hi_only(const mpg_ctx* ctx, long long contraction_rows) {
   (void)ctx;
   const char* e = getenv("MPG_REC_HI_ONLY");
@@ -763,7 +766,10 @@ int mpg_q_grad(mpg_ctx* ctx, int net, int rows, int64_t global_rows, const float
     ta.store_steps = 1;
     if (!tc_ensure_store(ctx->tc, (size_t)ntiles * tc::SLOT_BYTES)) return fail(ctx, MPG_ERR_CUDA, "cudaMalloc of the dW operand store failed%s");
     ta.store = ctx->tc.store;
-    ta.rec_hi_only = rec_hi_only(ctx, rows);
+    // full hi + lo records always: a regression residual can be pure zero-mean noise (converged critic), the sum over the rows
+    // then cancels to ~1/sqrt(rows) of its terms and the 2^-9 rounding of hi-only records would not average out relative
+    // to it (measured 1.4e-3 at 262,144 rows); this GEMM is 0.04 ms, there is nothing to gain
+    ta.rec_hi_only = 0;
     CUDA_OK(ctx, cudaMemsetAsync(ctx->partial, 0, (size_t)ctx->sms * ctx->partial_stride * sizeof(float), st));
     CUDA_OK(ctx, tc_launch_rollout<true>(c.env, ta, grid, st));
     tc::DwArgs da;

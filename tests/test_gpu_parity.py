@@ -666,3 +666,47 @@ def test_tc_hi_only_records_vs_full_records(monkeypatch):
     assert np.array_equal(res['auto'], res['1']), 'the automatic mode must pick hi-only records at this size'
     assert errs['1'] <= TOL_GRAD and errs['0'] <= TOL_GRAD, errs
     assert rel_l2(res['1'], res['0']) <= 5e-5
+
+
+@pytest.mark.parametrize('residual', ['systematic', 'noise'])
+def test_tc_q_grad_262144_rows_vs_oracle(monkeypatch, residual):
+    """Q regression gradient (0.5 mean (Q1(s, a) - target)^2, nadp.py:173-184) at 262,144 rows against the fp64 oracle.
+    'systematic': targets that differ from Q like n-step returns of an untrained critic do -> the 1e-4 bar.
+    'noise': target = Q + N(0, 1), the converged-critic limit: the sum over the rows cancels to ~1/512 of its terms, so
+    every rounding error is amplified by that factor relative to the gradient (the forward pass alone, 2e-6 |Q| against
+    residuals of order 1, gives 2e-4) -> asserted at 5e-4, and it is why the Q regression never takes the hi-only
+    dW2 records of the large policy-gradient contractions (1.4e-3 here; api.cu: rec_hi_only)."""
+    from oracle import mpg_oracle as O
+    from mpg_b200 import _lib
+    from mpg_b200.policy import PolicyWithQs
+    rows = 262144
+    args = default_args('NADP', PT, replay_batch_size=rows)
+    w = synthetic.make_policy_with_qs_weights(11, args.obs_dim, args.act_dim, 256, double_q=False)
+    rng = np.random.default_rng(12)
+    obs = synthetic.make_obs(rng, PT, rows)
+    act = rng.uniform(-1, 1, (rows, args.act_dim)).astype(np.float32)
+    nets = O.Nets(w, False, torch.float64)
+    q_pred = O.q_value(nets.Q1, O.to_t(obs, torch.float64) * O.to_t(args.obs_scale, torch.float64), O.to_t(act, torch.float64))
+    q0 = q_pred.detach().numpy()
+    target = ((0.5 * q0 if residual == 'systematic' else q0) + rng.standard_normal(rows)).astype(np.float32)
+    loss = 0.5 * torch.mean((q_pred - O.to_t(target, torch.float64)) ** 2)
+    ref = np.concatenate([x.numpy().ravel() for x in torch.autograd.grad(loss, nets.Q1)])
+    errs, grads = {}, {}
+    for mode in ('0', 'auto'):
+        if mode == 'auto':
+            monkeypatch.delenv('MPG_REC_HI_ONLY', raising=False)
+        else:
+            monkeypatch.setenv('MPG_REC_HI_ONLY', mode)
+        pol = PolicyWithQs(**vars(args))
+        pol.set_weights(w)
+        e = pol.engine
+        if not e.tc_available():
+            pytest.skip('tensor-core backend does not cover this configuration')
+        e.set_backend(1)
+        g, loss_sum = e.q_grad(_lib.NET_Q1, e.dev(obs), e.dev(act), e.dev(target))
+        grads[mode] = g.cpu().numpy()
+        errs[mode] = rel_l2(grads[mode], ref)
+        assert abs(float(loss_sum.item()) / rows - float(loss.item())) <= 2e-5 * abs(float(loss.item()))
+    print('q_grad 262144 rows,', residual, 'residual:', errs, 'cancellation |grad| =', float(np.linalg.norm(ref)))
+    assert np.array_equal(grads['auto'], grads['0']), 'the Q regression keeps full hi + lo records at every size'
+    assert errs['auto'] <= (TOL_GRAD if residual == 'systematic' else 5e-4), errs

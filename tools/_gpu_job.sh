@@ -1,3 +1,2 @@
 cd $GRAFT_REPO_ROOT
-mkdir -p gpurun_out
-timeout 200 python tools/tc_timeline.py > gpurun_out/r2w_timeline.txt 2>&1; echo "timeline rc=$?"
+timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -s -k "hi_only or 262144" 2>&1 | grep -E "q_grad|hi-only|passed|failed|Error|assert" | tail -12
