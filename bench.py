@@ -449,7 +449,7 @@ def main():
         'traffic': traffic,
         'traffic_note': ('bytes per launch from profiles/%s (ncu --set full of the same kernel at B=65536, scaled by rows); '
                          'algorithmic bytes are 56 B/state-step; the tc path adds the h2 image store (1 KB/state-step written '
-                         'by the forward pass, read back by BPTT) and the dW2 operand records (h1, delta2: 2 KB/state-step)'
+                         'by the forward pass, read back by BPTT) and the dW2 operand records (h1, delta2: 1 KB/state-step hi-only at this size, 2 KB below 262,144 row-steps)'
                          % traffic_src) if traffic_src else 'no ncu capture of this configuration',
         'kernel': 'rollout_kernel<%s,BWD> (fused forward rollout + BPTT, %s backend)' % (env_id, backend),
         'kernel_ms': k_ms, 'algorithmic_flop_per_state_step': flop,

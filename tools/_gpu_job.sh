@@ -1,2 +1,4 @@
 cd $GRAFT_REPO_ROOT
-timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -s -k "hi_only or 262144" 2>&1 | grep -E "q_grad|hi-only|passed|failed|Error|assert" | tail -12
+mkdir -p gpurun_out
+bash tools/verify_round.sh 2>&1 | tail -12
+bash tools/run_configs.sh 2>&1 | tail -16
