@@ -1,20 +1,21 @@
 #!/bin/bash
 # bench.py at N GPUs of one box the way the driver launches it (one rank per GPU over NCCL):
 #   weak scaling of the headline workload (config 2), strong scaling of config 4 (1,048,576-row MPG) and of one 65,536-row
-#   NADP batch.  Lines are appended to gpurun_out/r2_scaling.jsonl.
+#   NADP batch.  Lines are appended to gpurun_out/r2_scaling_<N>gpu.jsonl.
 N=${1:-2}
 cd ${GRAFT_REPO_ROOT:-.}
 mkdir -p gpurun_out
-OUT=gpurun_out/r2_scaling.jsonl
+OUT=gpurun_out/r2_scaling_${N}gpu.jsonl
 run() {
   if [ "$N" = 1 ]; then timeout 600 python bench.py --gpus 1 --no-cpu-baseline "$@" >> $OUT 2>> gpurun_out/r2_scaling.err
   else timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533 \
          bench.py --gpus $N "$@" >> $OUT 2>> gpurun_out/r2_scaling.err; fi
   echo "N=$N bench $* rc=$?"
 }
+WHICH=${2:-all}      # all | weak | weak+c4
 run --steps 10 --warmup 3
-run --config 4 --steps 5 --warmup 3
-run --global-rows 65536 --steps 10 --warmup 3
+if [ "$WHICH" != weak ]; then run --config 4 --steps 5 --warmup 3; fi
+if [ "$WHICH" = all ]; then run --global-rows 65536 --steps 10 --warmup 3; fi
 tail -3 $OUT | python -c "
 import sys, json
 for l in sys.stdin:
