@@ -95,7 +95,8 @@ __global__ void pack_kernel(const float* __restrict__ flat, int in_dim, int out_
   const GradLayout L(in_dim, out_dim);
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= H * H) return;
-  const int k = idx / H, pc = idx % H, l = pc >> 3, j = pc & 7, c = l + 32 * j;
+  // packed column pc = 128 (j >> 2) + 4 l + (j & 3)  <->  natural column c = l + 32 j (mlp_tile.cuh: rowgemm)
+  const int k = idx / H, pc = idx % H, l = (pc & 127) >> 2, j = (pc >> 7) * 4 + (pc & 3), c = l + 32 * j;
   W2p[idx] = flat[L.oW2 + k * H + c];
   W2Tp[idx] = flat[L.oW2 + c * H + k];   // W2T[n=k][col c] = W2[c][k]
   if (k < in_dim) W1p[idx] = flat[L.oW1 + k * H + c];

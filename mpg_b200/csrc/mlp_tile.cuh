@@ -6,8 +6,9 @@
 //     float4s and its B operand (a weight slab staged by cp.async) as conflict-free float4s;
 //   * the "dW GEMM" (dW[k][n] += sum_r X[k][r] Y[n][r]) reads both operands as float4s along rows.
 // Thread mapping of the row GEMM: warp w owns rows 8w..8w+7, lane l owns columns l + 32 j (j<8).
-// Weights are re-packed once per set_weights so that those 8 columns are contiguous:
-//   Wp[k][8 l + j] = W[k][l + 32 j].
+// Weights are re-packed once per set_weights so that those 8 columns are two float4s, each at a 16-byte lane stride
+// (a 32-byte lane stride made every weight read a 2-way bank conflict and the loop shared-memory bound in round 1):
+//   Wp[k][4 l + j] = W[k][l + 32 j] (j < 4),  Wp[k][128 + 4 l + j - 4] = W[k][l + 32 j] (j >= 4).
 #pragma once
 #include "common.cuh"
 
@@ -73,7 +74,7 @@ __device__ __forceinline__ void rowgemm(const float* __restrict__ in_s, int K, c
   for (int s = 0; s < nslab; ++s) {
     if (s + 1 < nslab) { issue(s + 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
     __syncthreads();
-    const float* sb = slab + (s & 1) * KS * H + l * 8;
+    const float* sb = slab + (s & 1) * KS * H + l * 4;
     const int k0 = s * KS, kn = min(KS, K - k0);
     const float* ap = in_s + (size_t)k0 * RP + w * 8;
 #pragma unroll 4
@@ -81,7 +82,7 @@ __device__ __forceinline__ void rowgemm(const float* __restrict__ in_s, int K, c
       const float4 a0 = *reinterpret_cast<const float4*>(ap + kk * RP);
       const float4 a1 = *reinterpret_cast<const float4*>(ap + kk * RP + 4);
       const float4 b0 = *reinterpret_cast<const float4*>(sb + kk * H);
-      const float4 b1 = *reinterpret_cast<const float4*>(sb + kk * H + 4);
+      const float4 b1 = *reinterpret_cast<const float4*>(sb + kk * H + 128);
       const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
       const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll

@@ -116,7 +116,7 @@ class LearnerBase(object):
         pin = self._pinned.get(k)
         if pin is None or pin.shape != v.shape:
             pin = self._pinned[k] = torch.empty(v.shape, dtype=torch.float32, pin_memory=True)
-        pin.numpy()[...] = v
+        pin.copy_(torch.from_numpy(v))      # multi-threaded for MB-sized batches (a numpy slice assignment is one thread)
         return pin
 
     def _finish_upload(self, consumer_waits=True):

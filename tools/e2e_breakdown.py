@@ -25,7 +25,7 @@ print('  q_forward_and_backward %.3f ms' % t(lambda: L.q_forward_and_backward(o,
 print('    rollout for q target %.3f ms' % t(lambda: L.model_rollout_for_q_estimation(o, a)))
 print('  policy_fwd_and_bwd     %.3f ms' % t(lambda: L.policy_forward_and_backward(o)))
 g = torch.zeros(136965 + 10, device='cuda')
-print('  clip x2 + D2H          %.3f ms' % t(lambda: (L.engine.clip_global_norm(g[:68353], 3.0), L.engine.clip_global_norm(g[68353:136965], 3.0), g.cpu().numpy())))
+print('  clip x2 + D2H          %.3f ms' % t(lambda: (L.engine.clip_global_norm(g[:68353], 3.0), L.engine.clip_global_norm(g[68353:136965], 3.0), L._to_host(g))))
 
 # the same for the reference's flagship learner: MPG-v2 defaults (clipped double-Q targets, first-action policy gradient)
 from mpg_b200.learners import MPGLearner
