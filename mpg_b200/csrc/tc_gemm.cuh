@@ -475,11 +475,12 @@ __global__ void pack_big_image(const float* __restrict__ src, int rs, int cs, ui
   *reinterpret_cast<uint4*>(img + stage + off) = h;
   *reinterpret_cast<uint4*>(img + stage + 2 * STAGE_BYTES + off) = l;
 }
-// first-layer image: value(n, k) = k < in_dim ? W1[k][n] : (k == bias_k ? b1[n] : 0); 256 rows x 16 k,
+// first-layer image: value(n, k) = scale * (k < in_dim ? W1[k][n] : (k == bias_k ? b1[n] : 0)); 256 rows x 16 k,
+// (scale = log2(e) for the bf16 image of the BPTT recompute, whose z1 only feeds elu'(z1) = 2^(min(z1, 0) log2 e))
 // INTERLEAVE K-major: [hi 8 KB | lo 8 KB]
 template <bool F16>
 __global__ void pack_l1_image(const float* __restrict__ W1, const float* __restrict__ b1, int in_dim, int bias_k,
-                              uint8_t* __restrict__ img) {
+                              uint8_t* __restrict__ img, float scale = 1.f) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;   // (n, k-half): 256 x 2
   if (idx >= 512) return;
   const int n = idx >> 1, kh = idx & 1;
@@ -487,7 +488,7 @@ __global__ void pack_l1_image(const float* __restrict__ W1, const float* __restr
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
     const int k = kh * 8 + e;
-    x[e] = k < in_dim ? W1[(size_t)k * H + n] : (k == bias_k ? b1[n] : 0.f);
+    x[e] = scale * (k < in_dim ? W1[(size_t)k * H + n] : (k == bias_k ? b1[n] : 0.f));
   }
   uint4 h, l;
   split2x<F16>(x[0], x[1], h.x, l.x); split2x<F16>(x[2], x[3], h.y, l.y); split2x<F16>(x[4], x[5], h.z, l.z); split2x<F16>(x[6], x[7], h.w, l.w);

@@ -228,7 +228,7 @@ __device__ MPG_EPI_INLINE void epi_delta2_blocks(Bars* b, const float* W3, float
     for (int i = 0; i < 16; ++i) {
       const float2 w = *reinterpret_cast<const float2*>(W3 + 2 * (c0 + i));
       const float g = fmaf(d30, w.x, d31 * w.y);
-      v[i] = g * (v[i] > 0.f ? 1.f : v[i] + 1.f);     // elu'(z) expressed through the output h2
+      v[i] = fmaf(g, fminf(v[i], 0.f), g);            // g elu'(z), elu'(z) = 1 + min(h2, 0) expressed through the output h2
     }
     act_store8(act, act + ACT_SPLIT, row, c0 >> 3, v);
     act_store8(act, act + ACT_SPLIT, row, (c0 >> 3) + 1, v + 8);
@@ -265,14 +265,15 @@ __device__ MPG_EPI_INLINE void epi_delta2_from_h2(Bars* b, const float* W3, floa
     for (int i = 0; i < 16; ++i) {
       const float2 w = *reinterpret_cast<const float2*>(W3 + 2 * (c0 + i));
       const float g = fmaf(d30, w.x, d31 * w.y);
-      v[i] = g * (v[i] > 0.f ? 1.f : v[i] + 1.f);     // elu'(z) expressed through the output h2
+      v[i] = fmaf(g, fminf(v[i], 0.f), g);            // g elu'(z), elu'(z) = 1 + min(h2, 0) expressed through the output h2
     }
     act_store8(act, act + ACT_SPLIT, row, c0 >> 3, v);
     act_store8(act, act + ACT_SPLIT, row, (c0 >> 3) + 1, v + 8);
     epi_block_done(b, kb);
   }
 }
-// delta1 = g_h1 (TMEM work) * elu'(z1) (recomputed, streamed through the chunk buffers) -> delta1 image
+// delta1 = g_h1 (TMEM work) * elu'(z1) (z1 log2(e) recomputed with the pre-scaled bf16 first-layer image, streamed through the
+// chunk buffers) -> delta1 image
 __device__ MPG_EPI_INLINE void epi_delta1_blocks(Bars* b, uint32_t tm_work_lane, uint32_t tm_zc_lane, uint8_t* act, int row,
                                                  int hc, bool draining = false, bool elected = false, bool release_img = false) {
   for (int kb = 0; kb < 4; ++kb) {
@@ -284,7 +285,7 @@ __device__ MPG_EPI_INLINE void epi_delta1_blocks(Bars* b, uint32_t tm_work_lane,
     epi_release_chunk(b, kb);
     if (draining) store_wait_block(elected, kb);             // block kb of the old image has been read out
 #pragma unroll
-    for (int i = 0; i < 16; ++i) g[i] *= (z[i] > 0.f ? 1.f : exp_fast(z[i]));
+    for (int i = 0; i < 16; ++i) g[i] *= ex2_ftz(fminf(z[i], 0.f));     // z = z1 log2(e) (l1b image): elu'(z1) = 2^min(z, 0), exactly 1 for z >= 0
     act_store8(act, act + ACT_SPLIT, row, c0 >> 3, g);
     act_store8(act, act + ACT_SPLIT, row, (c0 >> 3) + 1, g + 8);
     epi_block_done(b, kb);
