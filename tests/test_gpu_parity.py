@@ -710,3 +710,46 @@ def test_tc_q_grad_262144_rows_vs_oracle(monkeypatch, residual):
     print('q_grad 262144 rows,', residual, 'residual:', errs, 'cancellation |grad| =', float(np.linalg.norm(ref)))
     assert np.array_equal(grads['auto'], grads['0']), 'the Q regression keeps full hi + lo records at every size'
     assert errs['auto'] <= (TOL_GRAD if residual == 'systematic' else 5e-4), errs
+
+
+def test_tc_mixed_call_sequence_is_bit_reproducible():
+    """A sequence of differently shaped policy-gradient calls on ONE handle (list weights on/off, row shards, explicit
+    noise with M = 1 / 2, first-action mode, 512 tiles = full waves + tail wave + side-stream dW GEMMs) repeated three
+    times: every call must return the same bytes each time.  The kernel's roles meet only through mbarriers, so a
+    protocol error shows up as a run-to-run difference (or as the watchdog's trap) long before it shows up in a tolerance."""
+    from mpg_b200.policy import PolicyWithQs
+    B, n = 65536, 25
+    args = default_args('NADP', PT, replay_batch_size=B)
+    pol = PolicyWithQs(**vars(args))
+    pol.set_weights(synthetic.make_policy_with_qs_weights(1, args.obs_dim, args.act_dim, 256, double_q=False))
+    e = pol.engine
+    if not e.tc_available():
+        pytest.skip('tensor-core backend does not cover this configuration')
+    e.set_backend(1)
+    obs = e.dev(synthetic.make_obs(np.random.default_rng(2), PT, B))
+    Bs = 4096
+    eps = e.dev(synthetic.make_noise(np.random.default_rng(3), n, Bs))
+    eps2 = torch.cat([eps, eps], 1).contiguous()
+    half, small = obs[:B // 2].contiguous(), obs[:Bs].contiguous()
+    kw = dict(full_bptt=True, use_philox=True, noise_seed=11)
+    calls = [
+        lambda: e.policy_grad(obs, [0, n], [0.3, 0.7], **kw),
+        lambda: e.policy_grad(obs, [0, n], [1.0, 0.0], **kw),
+        lambda: e.policy_grad(obs, [0, n], [0.0, 1.0], **kw),
+        lambda: e.policy_grad(half, [0, n], [0.3, 0.7], global_rows=B, row_offset=0, **kw),
+        lambda: e.policy_grad(small, [n], [1.0], M=1, noise=eps, full_bptt=True),
+        lambda: e.policy_grad(small, [n], [1.0], M=2, noise=eps2, full_bptt=True),
+        lambda: e.policy_grad(obs, [0, n], [0.5, 0.5], full_bptt=False, use_philox=True),
+    ]
+    first = None
+    for rep in range(3):
+        out = []
+        for f in calls:
+            g, ret = f()
+            out.append((g.cpu().numpy(), ret.cpu().numpy()))
+        if first is None:
+            first = out
+            continue
+        for k, ((g0, r0), (g1, r1)) in enumerate(zip(first, out)):
+            assert np.array_equal(g0, g1) and np.array_equal(r0, r1), 'call %d differs in repetition %d' % (k, rep)
+    assert all(np.isfinite(g).all() and np.linalg.norm(g) > 0 for g, _ in first)
