@@ -166,6 +166,17 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// One thread of a fully converged warp.  Roles that issue tcgen05.mma / tcgen05.commit / bulk copies from a single thread must
+// be entered through this and not through `lane == 0`: both pick lane 0, but only after elect.sync does the compiler
+// know that exactly one thread is active and emit the uniform-datapath instructions (UTCHMMA, UTCBAR, UBLKCP) straight;
+// behind a thread-index test it wraps EVERY one of them in an ELECT / BRA.U.ANY loop (6 instructions and a branch per UMMA,
+// ~100 cycles each from a lone thread -- the "small UMMAs cost 100 cycles whatever their N" of the first round-2 kernels).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.b32 %0, 1, 0, P;\n}\n" : "=r"(pred));
+  return pred != 0;
+}
+
 // ---- descriptors ---------------------------------------------------------------------------------
 // UMMA shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
 //   [0,14) start>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version=1 | [49,52) base_offset=0 | [61,64) layout

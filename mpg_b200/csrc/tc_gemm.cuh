@@ -93,6 +93,9 @@ enum Role { ROLE_EPI = 0, ROLE_PRODUCER = 1, ROLE_MMA = 2, ROLE_ROW = 3 };
 // ---- producer: stream `nstages` stages of `bytes` each ------------------------------------------------
 __device__ __forceinline__ void produce(Bars* b, uint8_t* ring, Sync& s, const uint8_t* gsrc, int nstages, uint32_t bytes) {
   for (int i = 0; i < nstages; ++i, ++s.stage) {
+#if MPG_EXPERIMENT == 2
+    if (nstages == BIG_STAGES && (i & 2)) { --s.stage; continue; }
+#endif
     const uint32_t slot = s.stage & (NSLOT - 1), par = (s.stage / NSLOT) & 1;
     mbar_wait(&b->empty[slot], par ^ 1, 10000 + __LINE__);
     mbar_expect_tx(&b->full[slot], bytes);
@@ -143,19 +146,24 @@ __device__ __forceinline__ void produce_single(Bars* b, uint8_t* ring, Sync& s, 
 // FMT: element format of BOTH operands (forward GEMMs: fp16 pairs, dX GEMMs: bf16 pairs)
 template <int FMT = FMT_BF16>
 __device__ __forceinline__ void mma_big(Bars* b, uint32_t act_addr, uint32_t ring_addr, Sync& s, uint32_t d_tmem,
-                                        bool wait_a = true) {
+                                        bool wait_a = true, long long* prof = nullptr) {
   constexpr uint32_t idesc = make_idesc(128, 256, 0, 0, FMT, FMT);
   for (int kb = 0; kb < 4; ++kb) {
     if (wait_a) mbar_wait(&b->a_blk[kb], s.g_cnt & 1, 10000 + __LINE__);
+    if (prof) prof[kb * 5] = clock64();          // timeline probe (debug library): A block kb seen
     tc_fence_after();
     const uint64_t dah = make_desc(act_addr + kb * ACT_BLOCK, 16, 1024, LAYOUT_SW128);
     const uint64_t dal = make_desc(act_addr + ACT_SPLIT + kb * ACT_BLOCK, 16, 1024, LAYOUT_SW128);
 #pragma unroll
     for (int sp = 0; sp < 2; ++sp) {
+#if MPG_EXPERIMENT == 2
+      if (sp == 1) continue;
+#endif
 #pragma unroll
       for (int kh = 0; kh < 2; ++kh) {
         const uint32_t slot = s.stage & (NSLOT - 1), par = (s.stage / NSLOT) & 1;
         mbar_wait(&b->full[slot], par, 10000 + __LINE__);
+        if (prof) prof[kb * 5 + 1 + sp * 2 + kh] = clock64();   // stage (kb, sp, kh) seen in its slot
         tc_fence_after();
         const uint64_t db = make_desc(ring_addr + slot * STAGE_BYTES, 16, 512, LAYOUT_SW64);
 #pragma unroll
@@ -164,7 +172,9 @@ __device__ __forceinline__ void mma_big(Bars* b, uint32_t act_addr, uint32_t rin
           const uint64_t kw = (uint64_t)(j * 2);              // +32 bytes inside the 64-byte swizzle atom of the weights
           if (sp == 0) {
             umma_bf16(d_tmem, dah + ka, db + kw, idesc, (kb | kh | j) ? 1u : 0u);   // a_hi . b_hi
+#if MPG_EXPERIMENT != 1
             umma_bf16(d_tmem, dal + ka, db + kw, idesc, 1u);                        // a_lo . b_hi
+#endif
           } else {
             umma_bf16(d_tmem, dah + ka, db + kw, idesc, 1u);                        // a_hi . b_lo
           }
@@ -313,7 +323,7 @@ __device__ __forceinline__ void gemm_issue(int kind, Bars* b, uint8_t* smem, Syn
 // of the big GEMM follow the h1 blocks the epilogue publishes.  Result: z2 in tm_work (d_full).
 template <int ROLE>
 __device__ __forceinline__ void fwd_pair_issue(Bars* b, uint8_t* smem, Sync& s, const uint8_t* l1_img, const uint8_t* big_img,
-                                               uint32_t tm_z1c, uint32_t tm_work) {
+                                               uint32_t tm_z1c, uint32_t tm_work, long long* prof = nullptr) {
   if (ROLE == ROLE_PRODUCER) {
     produce_single(b, smem + SmemMap::RING, s, l1_img);
     produce(b, smem + SmemMap::RING, s, big_img, BIG_STAGES, STAGE_BYTES);
@@ -321,18 +331,24 @@ __device__ __forceinline__ void fwd_pair_issue(Bars* b, uint8_t* smem, Sync& s, 
     const uint32_t base = smem_u32(smem), p_addr = base + SmemMap::PIMG, ring = base + SmemMap::RING;
     mbar_wait(&b->a_full, s.a_cnt & 1, 10000 + __LINE__);
     ++s.a_cnt;
+    if (prof) prof[21] = clock64();           // [p|a|1] image published
     const uint32_t slot = wait_single(b, s);
     const uint32_t bbase = ring + slot * STAGE_BYTES;
+    if (prof) prof[22] = clock64();           // first-layer weight image in its slot
     mma_l1_chunk<FMT_F16>(b, p_addr, bbase, 0, tm_z1c);
     mma_l1_chunk<FMT_F16>(b, p_addr, bbase, 1, tm_z1c);
+    if (prof) prof[23] = clock64();
     mma_l1_chunk<FMT_F16>(b, p_addr, bbase, 2, tm_z1c);
+    if (prof) prof[24] = clock64();
     ++s.stage;
     consume_pad(b, s);                        // hands the empty slot to the big GEMM's first stages right away
+    if (prof) prof[25] = clock64();
     // the last chunk waits for the epilogue to have read chunk 1, which happens about when h1 block 0 is published:
     // issuing it BEFORE the first big UMMAs keeps it from queueing behind them in the tensor pipe
     mma_l1_chunk<FMT_F16>(b, p_addr, bbase, 3, tm_z1c);
     umma_commit(&b->empty[slot]);
-    mma_big<FMT_F16>(b, base + SmemMap::ACT, ring, s, tm_work);
+    if (prof) prof[20] = clock64();              // first-layer chunk 3 issued, layer-2 GEMM starts
+    mma_big<FMT_F16>(b, base + SmemMap::ACT, ring, s, tm_work, true, prof);
     mma_publish_d(b);
   } else {
     epi_publish_a(b);

@@ -452,7 +452,12 @@ __device__ __forceinline__ void run_rollout(const TcArgs& A, uint8_t* smem, Bars
     // the h1 image leaves for the dW operand store behind the K-blocks of the GEMM.
     auto policy_forward = [&](float* zpre, uint8_t* h2slot, uint8_t* slot) {
       if (ROLE == ROLE_MMA) stamp(16);
+#ifdef MPG_DEBUG_PROBES
+      fwd_pair_issue<ROLE>(b, smem, sy, A.pol.l1, A.pol.big_fwd, tm_z1c, tm_work,
+                           (ROLE == ROLE_MMA && A.prof && blockIdx.x == 0 && prof_t >= 0) ? A.prof + 96 : nullptr);
+#else
       fwd_pair_issue<ROLE>(b, smem, sy, A.pol.l1, A.pol.big_fwd, tm_z1c, tm_work);
+#endif
       if (ROLE == ROLE_MMA) stamp(17);
       if (ROLE == ROLE_EPI) {
         stamp(17);
@@ -921,8 +926,8 @@ __global__ void __launch_bounds__(ROLLOUT_THREADS, 1) tc_rollout_kernel(const __
     run_rollout<ENV, BWD, ROLE_ROW>(A, smem, b);
   } else {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(AUX_REGS));
-    if (warp == PRODUCER_WARP) { if (lane == 0) run_rollout<ENV, BWD, ROLE_PRODUCER>(A, smem, b); }
-    else if (warp == MMA_WARP) { if (lane == 0) run_rollout<ENV, BWD, ROLE_MMA>(A, smem, b); }
+    if (warp == PRODUCER_WARP) { if (elect_one()) run_rollout<ENV, BWD, ROLE_PRODUCER>(A, smem, b); }
+    else if (warp == MMA_WARP) { if (elect_one()) run_rollout<ENV, BWD, ROLE_MMA>(A, smem, b); }
   }
   cta_teardown(b, MMA_WARP);
 }
@@ -1019,7 +1024,7 @@ __global__ void __launch_bounds__(DW_THREADS, 1) tc_dw_kernel(const __grid_const
     }
   } else if (warp == DW_CONV_WARPS + 1) {
     // ------------------------------- mma -------------------------------
-    if (lane == 0) {
+    if (elect_one()) {
       constexpr uint32_t id256 = make_idesc(128, 256, 1, 1), id16 = make_idesc(128, 16, 1, 1);
       const uint32_t sbase = smem_u32(stage_buf);
       uint32_t slot = 0, par = 0;

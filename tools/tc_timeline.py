@@ -28,4 +28,7 @@ for full in (1, 0):
     fw = t[16:23] - t[16]; fr = t[80:87] - t[16]
     print('  forward step t=2 (epi): start 0, E1 start', fw[1], 'E1 done', fw[2], 'z2 ready', fw[3], 'E2 done', fw[4], 'next step', fw[6])
     print('  forward step t=2 (mma): enter', t[32 + 16] - t[16], 'all UMMAs issued', t[32 + 17] - t[16])
+    g = t[96:124] - t[16]
+    print('  forward step t=2 (mma): p image seen', g[21], 'W1 image seen', g[22], 'chunks 0,1 issued', g[23], 'chunk 2 issued', g[24], 'pad consumed', g[25])
+    print('  forward step t=2 (mma): layer-2 GEMM starts', g[20], '; per k-block: A block seen / stages seen:', ' | '.join('%d / %s' % (g[kb * 5], ' '.join(str(x) for x in g[kb * 5 + 1: kb * 5 + 5])) for kb in range(4)))
     print('  forward step t=2 (row): start', fr[0], 'zpre', fr[5], 'next step', fr[6])
