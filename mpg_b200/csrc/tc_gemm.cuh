@@ -93,9 +93,6 @@ enum Role { ROLE_EPI = 0, ROLE_PRODUCER = 1, ROLE_MMA = 2, ROLE_ROW = 3 };
 // ---- producer: stream `nstages` stages of `bytes` each ------------------------------------------------
 __device__ __forceinline__ void produce(Bars* b, uint8_t* ring, Sync& s, const uint8_t* gsrc, int nstages, uint32_t bytes) {
   for (int i = 0; i < nstages; ++i, ++s.stage) {
-#if MPG_EXPERIMENT == 2
-    if (nstages == BIG_STAGES && (i & 2)) { --s.stage; continue; }
-#endif
     const uint32_t slot = s.stage & (NSLOT - 1), par = (s.stage / NSLOT) & 1;
     mbar_wait(&b->empty[slot], par ^ 1, 10000 + __LINE__);
     mbar_expect_tx(&b->full[slot], bytes);
@@ -144,9 +141,12 @@ __device__ __forceinline__ void produce_single(Bars* b, uint8_t* ring, Sync& s, 
 // K-block kb is issued as soon as the epilogue has published that 64-feature block of the activation image, so the
 // UMMAs overlap the epilogue that produces A.
 // FMT: element format of BOTH operands (forward GEMMs: fp16 pairs, dX GEMMs: bf16 pairs)
-template <int FMT = FMT_BF16>
+struct NoHook { __device__ __forceinline__ void operator()() const {} };
+// after_first: issued right behind the first two stages (split 0 of K-block 0); the forward pass puts its last first-layer chunk
+// there -- not later: the first-layer image still holds one of the four ring slots, and the third stage needs it back
+template <int FMT = FMT_BF16, typename Hook = NoHook>
 __device__ __forceinline__ void mma_big(Bars* b, uint32_t act_addr, uint32_t ring_addr, Sync& s, uint32_t d_tmem,
-                                        bool wait_a = true, long long* prof = nullptr) {
+                                        bool wait_a = true, long long* prof = nullptr, Hook after_first = Hook()) {
   constexpr uint32_t idesc = make_idesc(128, 256, 0, 0, FMT, FMT);
   for (int kb = 0; kb < 4; ++kb) {
     if (wait_a) mbar_wait(&b->a_blk[kb], s.g_cnt & 1, 10000 + __LINE__);
@@ -156,9 +156,6 @@ __device__ __forceinline__ void mma_big(Bars* b, uint32_t act_addr, uint32_t rin
     const uint64_t dal = make_desc(act_addr + ACT_SPLIT + kb * ACT_BLOCK, 16, 1024, LAYOUT_SW128);
 #pragma unroll
     for (int sp = 0; sp < 2; ++sp) {
-#if MPG_EXPERIMENT == 2
-      if (sp == 1) continue;
-#endif
 #pragma unroll
       for (int kh = 0; kh < 2; ++kh) {
         const uint32_t slot = s.stage & (NSLOT - 1), par = (s.stage / NSLOT) & 1;
@@ -172,9 +169,7 @@ __device__ __forceinline__ void mma_big(Bars* b, uint32_t act_addr, uint32_t rin
           const uint64_t kw = (uint64_t)(j * 2);              // +32 bytes inside the 64-byte swizzle atom of the weights
           if (sp == 0) {
             umma_bf16(d_tmem, dah + ka, db + kw, idesc, (kb | kh | j) ? 1u : 0u);   // a_hi . b_hi
-#if MPG_EXPERIMENT != 1
             umma_bf16(d_tmem, dal + ka, db + kw, idesc, 1u);                        // a_lo . b_hi
-#endif
           } else {
             umma_bf16(d_tmem, dah + ka, db + kw, idesc, 1u);                        // a_hi . b_lo
           }
@@ -182,6 +177,7 @@ __device__ __forceinline__ void mma_big(Bars* b, uint32_t act_addr, uint32_t rin
         umma_commit(&b->empty[slot]);
         ++s.stage;
       }
+      if (kb == 0 && sp == 0) after_first();
     }
     umma_commit(&b->kb_done[kb]);
   }
@@ -220,7 +216,7 @@ __device__ __forceinline__ void epi_release_chunk(Bars* b, int c) {
 // MN-major INTERLEAVE, 8-row groups 128 B apart (LBO), 8-feature chunks 2048 B apart (SBO), 16 rows = 256 B per k-step.
 template <int N, int B_FMT = FMT_BF16>
 __device__ __forceinline__ void mma_acc_half(uint32_t act_addr, uint32_t r_addr, uint32_t r_group, uint32_t d_tmem, int half,
-                                             bool started, bool lin = false) {
+                                             bool started, bool lin = false, bool img_hi_only = false) {
   constexpr uint32_t idesc = make_idesc(128, N, 1, 1, FMT_BF16, B_FMT);
   const uint32_t d = d_tmem + half * N;
 #pragma unroll
@@ -230,7 +226,7 @@ __device__ __forceinline__ void mma_acc_half(uint32_t act_addr, uint32_t r_addr,
     const uint64_t dal = lin ? make_desc(a + ACT_SPLIT, 128, 2048, LAYOUT_NONE) : make_desc(a + ACT_SPLIT, ACT_BLOCK, 1024, LAYOUT_SW128);
     const uint64_t db = make_desc(r_addr + ks * 2 * r_group, r_group, 128, LAYOUT_NONE);   // 8-row groups r_group apart (LBO)
     umma_bf16(d, dah, db, idesc, (started || ks) ? 1u : 0u);
-    umma_bf16(d, dal, db, idesc, 1u);
+    if (!img_hi_only) umma_bf16(d, dal, db, idesc, 1u);
   }
 }
 // first-layer GEMM: D[128 x 256] = P[128 x 16] . W1aug^T ; P is the INTERLEAVE image in shared memory,
@@ -343,12 +339,14 @@ __device__ __forceinline__ void fwd_pair_issue(Bars* b, uint8_t* smem, Sync& s, 
     ++s.stage;
     consume_pad(b, s);                        // hands the empty slot to the big GEMM's first stages right away
     if (prof) prof[25] = clock64();
-    // the last chunk waits for the epilogue to have read chunk 1, which happens about when h1 block 0 is published:
-    // issuing it BEFORE the first big UMMAs keeps it from queueing behind them in the tensor pipe
-    mma_l1_chunk<FMT_F16>(b, p_addr, bbase, 3, tm_z1c);
-    umma_commit(&b->empty[slot]);
-    if (prof) prof[20] = clock64();              // first-layer chunk 3 issued, layer-2 GEMM starts
-    mma_big<FMT_F16>(b, base + SmemMap::ACT, ring, s, tm_work, true, prof);
+    // the last chunk waits for the epilogue to have read chunk 1, i.e. for the START of h1 block 1, while K-block 0 of the
+    // layer-2 GEMM can go as soon as h1 block 0 is published: chunk 3 is issued behind the first two stages of K-block 0
+    // (the epilogue needs it only for block 3, 1.7 K cycles later; in front of K-block 0 it held the GEMM back)
+    if (prof) prof[20] = clock64();              // layer-2 GEMM starts
+    mma_big<FMT_F16>(b, base + SmemMap::ACT, ring, s, tm_work, true, prof, [&]() {
+      mma_l1_chunk<FMT_F16>(b, p_addr, bbase, 3, tm_z1c);
+      umma_commit(&b->empty[slot]);
+    });
     mma_publish_d(b);
   } else {
     epi_publish_a(b);
@@ -413,20 +411,23 @@ __device__ __forceinline__ void bwd_tail_issue(Bars* b, uint8_t* smem, Sync& s, 
 // D3 += h2^T [delta3|0]: the epilogue publishes (h2 image + delta3 image written); the UMMAs complete on d_full
 // twice, once per 128-feature half, so that the delta2 epilogue can start on the first half of the image
 template <int ROLE>
+// h2_hi_only: large policy-gradient contractions (the hi-only dW2 record regime, api.cu: rec_hi_only) also take only the hi
+// plane of h2 into dW3 -- the same 1/sqrt(K) averaging, emulated 1.1e-5 at 16,384 rows x 26 steps, and half the UMMAs
+// between delta3 and the delta2 epilogue
 __device__ __forceinline__ void d3_issue(Bars* b, uint8_t* smem, Sync& s, uint32_t d3_off, bool& d3_started, uint32_t tm_d3,
-                                         bool lin = false) {
+                                         bool lin = false, bool h2_hi_only = false) {
   if (ROLE == ROLE_MMA) {
     const uint32_t base = smem_u32(smem);
     mbar_wait(&b->a_full, s.a_cnt & 1, 10000 + __LINE__);
     ++s.a_cnt;
     tc_fence_after();
-    mma_acc_half<16>(base + SmemMap::ACT, base + d3_off, 256, tm_d3, 0, d3_started, lin);
+    mma_acc_half<16>(base + SmemMap::ACT, base + d3_off, 256, tm_d3, 0, d3_started, lin, h2_hi_only);
     mma_publish_d(b);                      // blocks 0, 1 of the h2 image may be overwritten
     if (lin) {                             // BPTT: the second half of the h2 image arrives separately
       mbar_wait(&b->img_full[1], (s.i_cnt - 1) & 1, 10000 + __LINE__);
       tc_fence_after();
     }
-    mma_acc_half<16>(base + SmemMap::ACT, base + d3_off, 256, tm_d3, 1, d3_started, lin);
+    mma_acc_half<16>(base + SmemMap::ACT, base + d3_off, 256, tm_d3, 1, d3_started, lin, h2_hi_only);
     umma_commit(&b->d_half);               // blocks 2, 3
     d3_started = true;
   } else if (ROLE == ROLE_EPI || ROLE == ROLE_ROW) {

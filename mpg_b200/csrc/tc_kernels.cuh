@@ -238,15 +238,15 @@ __device__ MPG_EPI_INLINE void epi_delta2_blocks(Bars* b, const float* W3, float
 // BPTT variant: h2 arrives from the h2 store in the row-interleaved layout (lin_chunk_off); delta2 is written as the
 // SW128 K-major image the dX UMMAs and the dW2 record expect.  Both layouts keep 64-feature block kb inside the same
 // 16 KB per split, so the conversion is in place block by block: every thread reads its part of block kb, barrier,
-// every thread writes.
+// every thread writes.  wait_d3: the D3 UMMAs (dW3 += h2^T delta3) read the same image; blocks 0, 1 may be overwritten when
+// their first half has completed (d_full), blocks 2, 3 after the second (d_half).  Only the WRITES wait for that: the
+// reads and the arithmetic of blocks 0 and 2 run underneath those UMMAs (16 per half, ~190 cycles each from the
+// no-swizzle image).
 __device__ MPG_EPI_INLINE void epi_delta2_from_h2(Bars* b, const float* W3, float d30, float d31, uint8_t* act, int row, int hc,
-                                                  uint32_t img_parity, Sync* wait_half1 = nullptr) {
+                                                  uint32_t img_parity, Sync* wait_d3 = nullptr) {
   for (int kb = 0; kb < 4; ++kb) {
     const int c0 = kb * 64 + hc * 16;
-    if (kb == 2) {
-      mbar_wait(&b->img_full[1], img_parity, 20000 + __LINE__);                 // second half of the h2 image has landed
-      if (wait_half1) epi_wait_half(b, *wait_half1);          // the D3 UMMAs have read blocks 2, 3 of the h2 image
-    }
+    if (kb == 2) mbar_wait(&b->img_full[1], img_parity, 20000 + __LINE__);      // second half of the h2 image has landed
     float v[16];
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
@@ -260,13 +260,15 @@ __device__ MPG_EPI_INLINE void epi_delta2_from_h2(Bars* b, const float* W3, floa
         v[8 * h + 2 * i + 1] = __uint_as_float(hw[i] & 0xFFFF0000u) + __uint_as_float(lw[i] & 0xFFFF0000u);
       }
     }
-    epi_bar();                                               // block kb has been read by everybody
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
       const float2 w = *reinterpret_cast<const float2*>(W3 + 2 * (c0 + i));
       const float g = fmaf(d30, w.x, d31 * w.y);
       v[i] = fmaf(g, fminf(v[i], 0.f), g);            // g elu'(z), elu'(z) = 1 + min(h2, 0) expressed through the output h2
     }
+    if (wait_d3 && kb == 0) epi_wait_d(b, *wait_d3);         // the D3 UMMAs have read blocks 0, 1 of the h2 image
+    if (wait_d3 && kb == 2) epi_wait_half(b, *wait_d3);      // ... and blocks 2, 3
+    epi_bar();                                               // block kb has been read by everybody
     act_store8(act, act + ACT_SPLIT, row, c0 >> 3, v);
     act_store8(act, act + ACT_SPLIT, row, (c0 >> 3) + 1, v + 8);
     epi_block_done(b, kb);
@@ -780,7 +782,7 @@ __device__ __forceinline__ void run_rollout(const TcArgs& A, uint8_t* smem, Bars
         }
         ++sy.i_cnt;
         if (ROLE == ROLE_MMA) stamp(5);
-        if (want_dw) d3_issue<ROLE>(b, smem, sy, SM_D3IMG, d3_started, tm_d3, true);   // dW3 += h2^T delta3
+        if (want_dw) d3_issue<ROLE>(b, smem, sy, SM_D3IMG, d3_started, tm_d3, true, A.rec_hi_only != 0);   // dW3 += h2^T delta3
         if (ROLE == ROLE_MMA) stamp(6);
         // ---- [p|1] image of step t (first-layer recompute for elu'(z1), D1 operand, db2 record); the D1 UMMAs of the
         // previous step still read the old one ----
@@ -793,7 +795,6 @@ __device__ __forceinline__ void run_rollout(const TcArgs& A, uint8_t* smem, Bars
           stamp(13);
         }
         if (ROLE == ROLE_EPI) {
-          if (want_dw) epi_wait_d(b, sy);                   // blocks 0, 1 of the h2 image read by the D3 UMMAs
           bar_sync(BAR_D3, XCHG_THREADS);                   // delta3 of every row is in MiscF::d3s
         }
         // ---- delta2 image (in place over h2) feeding the dX UMMAs block by block ----
