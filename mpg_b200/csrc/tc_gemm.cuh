@@ -339,14 +339,13 @@ __device__ __forceinline__ void fwd_pair_issue(Bars* b, uint8_t* smem, Sync& s, 
     ++s.stage;
     consume_pad(b, s);                        // hands the empty slot to the big GEMM's first stages right away
     if (prof) prof[25] = clock64();
-    // the last chunk waits for the epilogue to have read chunk 1, i.e. for the START of h1 block 1, while K-block 0 of the
-    // layer-2 GEMM can go as soon as h1 block 0 is published: chunk 3 is issued behind the first two stages of K-block 0
-    // (the epilogue needs it only for block 3, 1.7 K cycles later; in front of K-block 0 it held the GEMM back)
-    if (prof) prof[20] = clock64();              // layer-2 GEMM starts
-    mma_big<FMT_F16>(b, base + SmemMap::ACT, ring, s, tm_work, true, prof, [&]() {
-      mma_l1_chunk<FMT_F16>(b, p_addr, bbase, 3, tm_z1c);
-      umma_commit(&b->empty[slot]);
-    });
+    // the last chunk waits for the epilogue to have read chunk 1, which happens about when h1 block 0 is published:
+    // issuing it BEFORE the first big UMMAs keeps it from queueing behind them in the tensor pipe and frees the ring slot of
+    // the first-layer image (behind the first two stages of K-block 0 it made the third stage wait 1.8 K cycles for that slot)
+    mma_l1_chunk<FMT_F16>(b, p_addr, bbase, 3, tm_z1c);
+    umma_commit(&b->empty[slot]);
+    if (prof) prof[20] = clock64();              // first-layer chunk 3 issued, layer-2 GEMM starts
+    mma_big<FMT_F16>(b, base + SmemMap::ACT, ring, s, tm_work, true, prof);
     mma_publish_d(b);
   } else {
     epi_publish_a(b);

@@ -136,6 +136,8 @@ __device__ __forceinline__ void store_wait(bool elected) {
 
 // z1 (streamed through the two TMEM chunk buffers, bias folded in) -> h1 image
 __device__ MPG_EPI_INLINE void epi_hidden1_blocks(Bars* b, uint32_t tm_zc_lane, uint8_t* act, int row, int hc) {
+  // (reading the two chunk buffers out in pairs, to release chunk 1 early and get chunk 3 out of the layer-2 GEMM's way, was
+  // slower: a first-layer chunk takes ~500 cycles in the tensor pipe, so block 0 started that much later)
   for (int kb = 0; kb < 4; ++kb) {
     const int c0 = kb * 64 + hc * 16;
     float v[16];
