@@ -280,7 +280,8 @@ int fill_rollout_args(mpg_ctx* ctx, const mpg_rollout_params* p, RolloutArgs& a)
 // with 1/sqrt(K); below that the full hi + lo records are kept (at K = 16..256 x 26 hi-only records miss the 1e-4 bar).
 // The rounding error is ~1.1e-3 of the root-sum-square of the terms, so relative to the gradient it grows with the
 // cancellation in the sum (worst case, a gradient that is pure sampling noise: 1.1e-3 of that noise): the Q regression
-// never uses it, and MPG_REC_HI_ONLY=0 keeps full records everywhere (=1 forces hi-only, for tests).
+// never uses it, and MPG_REC_HI_ONLY=0 keeps full records everywhere (=1 forces hi-only, for tests).  The same flag makes
+// dW3 = sum h2^T delta3 -- the other contraction over the batch -- take only the hi plane of h2 (tc_gemm.cuh: d3_issue).
 int rec_hi_only(const mpg_ctx* ctx, long long contraction_rows) {
   (void)ctx;
   const char* e = getenv("MPG_REC_HI_ONLY");
